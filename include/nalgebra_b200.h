@@ -1,0 +1,166 @@
+/*
+ * nalgebra_b200.h -- C ABI of the B200-native dense back end for dimforge/nalgebra's hot path.
+ *
+ * One shared library (libnalgebra_b200.so, hand-written sm_100a CUDA) replaces, for DMatrix<f64>
+ * (and the f32 GEMM), exactly the calls the reference makes on this path.  nalgebra has no plugin
+ * API; the two seams a maintainer binds are:
+ *
+ *   seam 1  the single call into the third-party crate:
+ *             matrixmultiply::dgemm / sgemm, /root/reference/src/base/blas_uninit.rs:298-313, 276-291
+ *   seam 2  the back-end-crate pattern of nalgebra-lapack (same-named structs whose constructors
+ *             call C symbols resolved at link time, nalgebra-lapack/src/lib.rs:33-36), but keeping
+ *             CORE nalgebra's layouts: Cholesky{chol}, LU{lu,p}, PermutationSequence, QR{qr,diag}.
+ *
+ * Conventions
+ *   - Plain pointers and sizes only.  Column-major; strides and leading dimensions in ELEMENTS.
+ *   - The caller owns every buffer; nothing is retained after return.  Factorizations are in place,
+ *     like the reference (the Rust side passes the matrix it consumed by value).
+ *   - Host-pointer entry points block until the result is visible to the host.  `_dev` twins take
+ *     device pointers plus a cudaStream_t (as void*) and are asynchronous on that stream, except
+ *     where a status must be returned (noted below).
+ *   - Shape errors are panics on the Rust side before the FFI; the C side still returns NA_EINVAL.
+ *     Numerical outcomes are values (NA_NOT_PD, NA_SINGULAR), never aborts.  CUDA failures map to
+ *     NA_ECUDA and na_last_error() holds the message.
+ *   - There is NO CPU fallback: without a usable sm_100 device every compute call fails with
+ *     NA_ECUDA.
+ *   - Thread-safe: calls may arrive concurrently from several host threads (the reference types
+ *     are Send + Sync); host-pointer calls serialise on an internal lock, `_dev` calls only touch
+ *     the stream they are given.
+ */
+#ifndef NALGEBRA_B200_H
+#define NALGEBRA_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#if defined(__GNUC__)
+#define NAB_API __attribute__((visibility("default")))
+#else
+#define NAB_API
+#endif
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum na_status {
+    NA_OK = 0,
+    NA_NOT_PD = 1,     /* Cholesky::new -> None            (src/linalg/cholesky.rs:267-268) */
+    NA_SINGULAR = 2,   /* solve_mut -> false               (src/linalg/solve.rs:169-171, qr.rs:242-244) */
+    NA_EINVAL = -1,    /* shape/stride error (a panic in the reference: blas_uninit.rs:244-252) */
+    NA_ECUDA = -2,     /* CUDA runtime/driver failure, or no sm_100 device */
+    NA_ENOMEM = -3,    /* device or pinned-host allocation failed */
+    NA_ENCCL = -4      /* reserved for the multi-GPU layer */
+} na_status;
+
+/* ---- context ------------------------------------------------------------------------------ */
+/* Binds the calling process to `device` (default 0 when never called) and creates the internal
+ * stream.  Idempotent. */
+NAB_API int na_init(int device);
+NAB_API int na_shutdown(void);
+/* Message of the last failure on the calling thread ("" when none). */
+NAB_API const char* na_last_error(void);
+/* "nalgebra_b200 <version> sm_100a". */
+NAB_API const char* na_version(void);
+/* Number of kernels this library has launched since load (bench.py's gpu_launches). */
+NAB_API uint64_t na_kernel_launches(void);
+
+/* ---- device / pinned memory helpers (so callers without a CUDA binding can use *_dev) ------ */
+NAB_API int na_dev_malloc(void** ptr, size_t bytes);
+NAB_API int na_dev_free(void* ptr);
+NAB_API int na_host_alloc_pinned(void** ptr, size_t bytes);
+NAB_API int na_host_free_pinned(void* ptr);
+NAB_API int na_memcpy_h2d(void* dst, const void* src, size_t bytes);
+NAB_API int na_memcpy_d2h(void* dst, const void* src, size_t bytes);
+NAB_API int na_dev_synchronize(void);
+/* Fills a device matrix with the counter-based U[0,1) generator shared with the oracle:
+ * a(i,j) = rand01(seed, i + j*nrows)  (the distribution of DMatrix::new_random,
+ * src/base/construction.rs:293-299). */
+NAB_API int na_fill_uniform_dev(double* a, size_t nrows, size_t ncols, size_t lda, uint64_t seed, void* stream);
+
+/* ---- seam 1: GEMM ------------------------------------------------------------------------- */
+/* Replaces matrixmultiply::dgemm(m, k, n, alpha, a, rsa, csa, b, rsb, csb, beta, c, rsc, csc)
+ * as called at src/base/blas_uninit.rs:298-313 (and through it Matrix::gemm blas.rs:729-746,
+ * mul_to ops.rs:783-795, `&A * &B` ops.rs:554-574; gemm_tr/tr_mul are the same call with A's
+ * strides swapped).  C is m x n, A is m x k, B is k x n, arbitrary element strides.
+ * C is never read when beta == 0 (it may be uninitialised memory, ops.rs:567-571).
+ * k == 0 scales C by beta (or zeroes it), blas_uninit.rs:258-269. */
+NAB_API int na_dgemm(size_t m, size_t k, size_t n, double alpha,
+             const double* a, ptrdiff_t rsa, ptrdiff_t csa,
+             const double* b, ptrdiff_t rsb, ptrdiff_t csb,
+             double beta, double* c, ptrdiff_t rsc, ptrdiff_t csc);
+/* Replaces matrixmultiply::sgemm, src/base/blas_uninit.rs:276-291. */
+NAB_API int na_sgemm(size_t m, size_t k, size_t n, float alpha,
+             const float* a, ptrdiff_t rsa, ptrdiff_t csa,
+             const float* b, ptrdiff_t rsb, ptrdiff_t csb,
+             float beta, float* c, ptrdiff_t rsc, ptrdiff_t csc);
+NAB_API int na_dgemm_dev(size_t m, size_t k, size_t n, double alpha,
+                 const double* a, ptrdiff_t rsa, ptrdiff_t csa,
+                 const double* b, ptrdiff_t rsb, ptrdiff_t csb,
+                 double beta, double* c, ptrdiff_t rsc, ptrdiff_t csc, void* stream);
+NAB_API int na_sgemm_dev(size_t m, size_t k, size_t n, float alpha,
+                 const float* a, ptrdiff_t rsa, ptrdiff_t csa,
+                 const float* b, ptrdiff_t rsb, ptrdiff_t csb,
+                 float beta, float* c, ptrdiff_t rsc, ptrdiff_t csc, void* stream);
+
+/* ---- seam 2: Cholesky --------------------------------------------------------------------- */
+/* Cholesky::new / new_with_substitute (src/linalg/cholesky.rs:196-272).  On NA_OK the lower
+ * triangle (incl. diagonal) of `a` holds L; the strict upper triangle is never read or written
+ * (tests/linalg/cholesky.rs:3-12).  NA_NOT_PD == `None`; *fail_col (may be NULL) receives the
+ * first column whose pivot was <= 0 or NaN.  use_sub/sub = new_with_substitute's `substitute`. */
+NAB_API int na_cholesky_f64(size_t n, double* a, size_t lda, int use_sub, double sub, size_t* fail_col);
+/* Synchronises `stream` before returning (the status is a value). */
+NAB_API int na_cholesky_f64_dev(size_t n, double* a, size_t lda, int use_sub, double sub, size_t* fail_col, void* stream);
+/* Cholesky::solve_mut (cholesky.rs:122-129): b <- (L L^T)^-1 b, b is n x nrhs. */
+NAB_API int na_cholesky_solve_f64(size_t n, const double* l, size_t lda, double* b, size_t ldb, size_t nrhs);
+NAB_API int na_cholesky_solve_f64_dev(size_t n, const double* l, size_t lda, double* b, size_t ldb, size_t nrhs, void* stream);
+
+/* ---- seam 2: LU with partial pivoting ------------------------------------------------------ */
+/* LU::new (src/linalg/lu.rs:93-122).  On return `a` holds the packed factors (strict lower = L
+ * multipliers, upper incl. diagonal = U; row swaps applied to whole rows, LAPACK getrf layout)
+ * and swaps[2*s], swaps[2*s+1] (s < *nswaps) is PermutationSequence's s-th pair (i, i2)
+ * (src/linalg/permutation_sequence.rs:28-34, 84-93: only non-trivial swaps are stored, in
+ * application order).  `swaps` has room for 2*min(m,n) entries; unused entries are set to 0.
+ * Pivot rule = icamax (src/base/min_max.rs:221-240): largest |x|, lowest index wins ties; an
+ * all-zero column is skipped without a swap (lu.rs:107-110).  Never fails numerically. */
+NAB_API int na_lu_f64(size_t m, size_t n, double* a, size_t lda, size_t* swaps, size_t* nswaps);
+/* swaps/nswaps are HOST pointers; synchronises `stream` before returning. */
+NAB_API int na_lu_f64_dev(size_t m, size_t n, double* a, size_t lda, size_t* swaps, size_t* nswaps, void* stream);
+/* LU::solve_mut (lu.rs:242-260): permute rows of b, unit-lower solve, upper solve.
+ * NA_SINGULAR == `false` (an exactly-zero U[i,i]); b is then garbage, as in the reference. */
+NAB_API int na_lu_solve_f64(size_t n, const double* lu, size_t lda, const size_t* swaps, size_t nswaps,
+                    double* b, size_t ldb, size_t nrhs);
+NAB_API int na_lu_solve_f64_dev(size_t n, const double* lu, size_t lda, const size_t* swaps, size_t nswaps,
+                        double* b, size_t ldb, size_t nrhs, void* stream);
+
+/* ---- seam 2: Householder QR ---------------------------------------------------------------- */
+/* QR::new (src/linalg/qr.rs:55-76).  nalgebra's storage, NOT LAPACK's: column i, rows i..m of `a`
+ * hold the unit-2-norm Householder axis u_i (first component included); the strict upper triangle
+ * holds R's off-diagonal; diag[i] (min(m,n) entries) is the signed value returned by
+ * reflection_axis_mut (householder.rs:19-53), so R[i,i] = |diag[i]| (qr.rs:87). */
+NAB_API int na_qr_f64(size_t m, size_t n, double* a, size_t lda, double* diag);
+NAB_API int na_qr_f64_dev(size_t m, size_t n, double* a, size_t lda, double* diag, void* stream);
+/* QR::q (qr.rs:108-129): q is m x min(m,n). */
+NAB_API int na_qr_q_f64(size_t m, size_t n, const double* qr, size_t lda, const double* diag, double* q, size_t ldq);
+NAB_API int na_qr_q_f64_dev(size_t m, size_t n, const double* qr, size_t lda, const double* diag, double* q, size_t ldq, void* stream);
+/* QR::q_tr_mul (qr.rs:157-171): b <- Q^T b, b is m x nrhs. */
+NAB_API int na_qr_q_tr_mul_f64(size_t m, size_t n, const double* qr, size_t lda, const double* diag,
+                       double* b, size_t ldb, size_t nrhs);
+NAB_API int na_qr_q_tr_mul_f64_dev(size_t m, size_t n, const double* qr, size_t lda, const double* diag,
+                           double* b, size_t ldb, size_t nrhs, void* stream);
+/* QR::solve_mut (qr.rs:204-256), square only.  NA_SINGULAR == `false` (a zero in diag). */
+NAB_API int na_qr_solve_f64(size_t n, const double* qr, size_t lda, const double* diag, double* b, size_t ldb, size_t nrhs);
+
+/* ---- triangular solves (src/linalg/solve.rs:55-182) ---------------------------------------- */
+/* op(T) x = b in place on b (n x nrhs).  lower: 1 = lower, 0 = upper triangle of `t` is used.
+ * trans: 0 = T, 1 = T^T.  unit_diag: 1 = implicit unit diagonal (solve_lower_triangular_with_diag_mut
+ * with diag = 1, solve.rs:106-133).  NA_SINGULAR on an exactly-zero diagonal entry. */
+NAB_API int na_tri_solve_f64(int lower, int trans, int unit_diag, size_t n, const double* t, size_t ldt,
+                     double* b, size_t ldb, size_t nrhs);
+NAB_API int na_tri_solve_f64_dev(int lower, int trans, int unit_diag, size_t n, const double* t, size_t ldt,
+                         double* b, size_t ldb, size_t nrhs, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NALGEBRA_B200_H */
