@@ -1,0 +1,371 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of nalgebra_b200 (contract: see the task prompt / DESIGN.md §6).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+
+Metric (BASELINE.json): f64 GEMM GFLOP/s at N=16384 (C = A*B, DMatrix<f64> 16384x16384x16384),
+reported with the fraction of the measured FP64 peak; Cholesky / LU / QR numbers of the same run
+ride along under "extra".  One "step" = one full 16384^3 GEMM.
+
+* value      : device-resident throughput (inputs already in HBM), CUDA events, max over ranks.
+* e2e        : the same GEMM through the host-pointer C-ABI call `na_dgemm` (what nalgebra's
+               gemm_uninit would call instead of matrixmultiply::dgemm) with pinned HOST buffers;
+               H2D of A and B and D2H of C are inside the timed region.
+* roofline   : DMMA tensor-pipe roofline; peak = 37.18 TFLOP/s measured on this pool's B200 by
+               tools/fp64_peak.cu (profiles/fp64_peak_r01.md) -- MEASURED_PEAKS.json carries no FP64
+               number, so this is "of measured (own DMMA micro-benchmark)".
+* cpu_baseline / --impl reference : the oracle's matrixmultiply restatement on the host cores
+               (kind "port": the Rust reference cannot be built in this image).
+* N > 1      : 2D output-tile sharding of the same 16384^3 problem over an r x c process grid
+               (strong scaling), one process per GPU under torchrun.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+N_FULL = 16384
+FP64_PEAK_TFLOPS = 37.18           # measured, profiles/fp64_peak_r01.md (DMMA m8n8k4, 148 SMs @ 1965 MHz)
+GRIDS = {1: (1, 1), 2: (1, 2), 4: (2, 2), 8: (2, 4)}
+
+
+# ------------------------------------------------------------------------------------------------
+# clocks sampler (nvidia-smi during the timed region)
+# ------------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index, self.proc, self.lines = index, None, []
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except OSError:
+            self.proc = None
+        return self
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def __exit__(self, *a):
+        if self.proc:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except Exception:
+                self.proc.kill()
+
+    def summary(self):
+        sm, mx, reasons = [], 0, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for l in self.lines:
+            f = [x.strip() for x in l.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx = max(mx, float(f[1]))
+            except ValueError:
+                continue
+            for name, v in zip(names, f[3:7]):
+                if v == "Active":
+                    reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        busy = sorted(x for x in sm if x > 0.5 * mx) or sorted(sm)
+        return {"sm_mhz": busy[len(busy) // 2], "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU arm: the oracle's matrixmultiply restatement (test infrastructure used as the baseline)
+# ------------------------------------------------------------------------------------------------
+def cpu_gemm_gflops(n: int, nthreads: int, reps: int = 1):
+    import numpy as np
+    import oracle as O
+    a = O.uniform(n, n, 1); b = O.uniform(n, n, 2); c = np.zeros((n, n), order="F")
+    O.gemm(1.0, a[:256, :256].copy(order="F"), b[:256, :256].copy(order="F"), 0.0, c[:256, :256].copy(order="F"), path="mm")  # warm the lib
+    best = None
+    for _ in range(reps):
+        t0 = time.perf_counter()
+        O.gemm(1.0, a, b, 0.0, c, path="mm", nthreads=nthreads)
+        dt = time.perf_counter() - t0
+        best = dt if best is None else min(best, dt)
+    return 2.0 * n ** 3 / best / 1e9, best
+
+
+def run_reference(args):
+    """--impl reference: nalgebra's CPU path for this metric.  The Rust reference cannot be built
+    here (no cargo/rustc), so this times the oracle port of gemm_uninit -> matrixmultiply::dgemm on
+    a bounded sample of the workload, with all host threads (the crate's optional `threading`
+    feature; nalgebra's default is 1 thread, see cpu_baseline in the main arm)."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    n = 4096
+    times = []
+    for i in range(args.warmup + args.steps):
+        gf, dt = cpu_gemm_gflops(n, cores)
+        if i >= args.warmup:
+            times.append(dt)
+    ms = 1e3 * sum(times) / len(times)
+    value = 2.0 * n ** 3 / (ms * 1e-3) / 1e9
+    sample = f"{n}^3 f64 GEMM per step (1/64 of the 16384^3 workload), oracle matrixmultiply port, {cores} threads"
+    line = {
+        "impl": "reference", "metric": "f64_gemm_gflops_n16384", "value": value, "unit": "GFLOP/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"DMatrix<f64> GEMM {N_FULL}x{N_FULL}x{N_FULL} (C = A*B), uniform [0,1) inputs",
+                   "sample": sample},
+        "cpu_baseline": {"value": value, "unit": "GFLOP/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": "GFLOP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------
+# GPU arm
+# ------------------------------------------------------------------------------------------------
+def run_gpu(args):
+    import torch
+    import torch.distributed as dist
+    from nalgebra_b200 import _capi
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local_rank}"))
+    if world != args.gpus and rank == 0 and world > 1:
+        print(f"warning: --gpus {args.gpus} but WORLD_SIZE={world}", file=sys.stderr)
+    ngpus = world
+    torch.cuda.set_device(local_rank)
+    dev = torch.device(f"cuda:{local_rank}")
+    L = _capi.lib()
+    _capi.check(L.na_init(local_rank))
+    stream = torch.cuda.current_stream().cuda_stream
+
+    N = args.n
+    pr, pc = GRIDS.get(ngpus, (1, ngpus))
+    my_r, my_c = rank // pc, rank % pc
+    m_loc, n_loc = N // pr, N // pc
+    row0, col0 = my_r * m_loc, my_c * n_loc
+
+    # inputs resident in HBM: this rank's row panel of A (m_loc x N) and column panel of B (N x n_loc)
+    A = torch.empty(m_loc * N, dtype=torch.float64, device=dev)
+    B = torch.empty(N * n_loc, dtype=torch.float64, device=dev)
+    Cd = torch.empty(m_loc * n_loc, dtype=torch.float64, device=dev)
+    _capi.check(L.na_fill_uniform_block_dev(A.data_ptr(), m_loc, N, m_loc, 1, row0, 0, N, stream))
+    _capi.check(L.na_fill_uniform_block_dev(B.data_ptr(), N, n_loc, N, 2, 0, col0, N, stream))
+
+    def step():
+        _capi.check(L.na_dgemm_dev(m_loc, N, n_loc, 1.0, A.data_ptr(), 1, m_loc, B.data_ptr(), 1, N, 0.0,
+                                   Cd.data_ptr(), 1, m_loc, stream))
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        step()
+    barrier()
+    launches0 = L.na_kernel_launches()
+    e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+    with ClockSampler(local_rank) as clk:
+        e0.record()
+        for _ in range(args.steps):
+            step()
+        e1.record()
+        barrier()
+    launches = L.na_kernel_launches() - launches0
+    ms_total = e0.elapsed_time(e1)
+    t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_step = t.item() / args.steps
+    flops = 2.0 * N ** 3
+    value = flops / (ms_step * 1e-3) / 1e9
+    clocks = clk.summary()
+
+    # per-kernel duration for the roofline: one launch per step on this rank
+    kernel_ms = ms_total / args.steps
+    achieved = (flops / ngpus) / (kernel_ms * 1e-3) / 1e12
+
+    # ---- e2e: host-pointer C-ABI call, pinned host buffers, copies inside the timed region ----
+    e2e = None
+    if not args.no_e2e:
+        hA = torch.empty(m_loc * N, dtype=torch.float64).pin_memory()
+        hB = torch.empty(N * n_loc, dtype=torch.float64).pin_memory()
+        hC = torch.empty(m_loc * n_loc, dtype=torch.float64).pin_memory()
+        hA.copy_(A); hB.copy_(B)
+        torch.cuda.synchronize()
+
+        def e2e_step():
+            _capi.check(L.na_dgemm(m_loc, N, n_loc, 1.0, hA.data_ptr(), 1, m_loc, hB.data_ptr(), 1, N, 0.0,
+                                   hC.data_ptr(), 1, m_loc))
+
+        e2e_steps = max(1, min(args.steps, 3))
+        e2e_step()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            e2e_step()                      # blocks until C is visible on the host
+        dt = time.perf_counter() - t0
+        tt = torch.tensor([dt], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        e2e_ms = tt.item() / e2e_steps * 1e3
+        checksum = float(hC[:1024].sum())
+        e2e = {"value": flops / (e2e_ms * 1e-3) / 1e9, "unit": "GFLOP/s", "ms_per_step": e2e_ms,
+               "h2d_bytes_per_step": int((hA.numel() + hB.numel()) * 8), "d2h_bytes_per_step": int(hC.numel() * 8),
+               "steps": e2e_steps, "api": "na_dgemm (host pointers, pinned)", "checksum": checksum}
+        del hA, hB, hC
+
+    extra = {}
+    if ngpus == 1 and not args.no_extra:
+        try:
+            extra = factorization_extras(L, _capi, torch, dev, stream, N)
+        except Exception as ex:  # a missing entry point must not kill the headline line
+            extra = {"error": repr(ex)}
+
+    cpu = None
+    if rank == 0 and ngpus == 1 and not args.no_cpu:
+        n_s = 4096
+        gf, dt = cpu_gemm_gflops(n_s, 1)
+        cpu = {"value": gf, "unit": "GFLOP/s", "cores": 1, "kind": "port",
+               "sample": f"{n_s}^3 f64 GEMM (1/64 of the workload), oracle matrixmultiply port, 1 thread = nalgebra's default features; {dt:.1f} s"}
+
+    if rank == 0:
+        line = {
+            "metric": "f64_gemm_gflops_n16384", "value": value, "unit": "GFLOP/s", "n_gpus": ngpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": f"DMatrix<f64> GEMM {N}x{N}x{N} (C = A*B), uniform [0,1) inputs (BASELINE.json configs[1])",
+                       "process_grid": f"{pr}x{pc}", "per_gpu_tile": f"{m_loc}x{n_loc}x{N}",
+                       "l2": "inputs (>=1.6 GB per GPU) exceed the 126 MB L2; no explicit flush",
+                       "pct_of_fp64_peak": 100.0 * value / 1e3 / (FP64_PEAK_TFLOPS * ngpus)},
+            "roofline": {"bound": "tensor", "achieved": achieved, "peak": FP64_PEAK_TFLOPS, "unit": "TFLOP/s",
+                         "frac": achieved / FP64_PEAK_TFLOPS, "traffic": None,
+                         "kernel": "dgemm_tma_dmma_kernel", "peak_source": "measured: tools/fp64_peak.cu DMMA chain on this pool's B200 (profiles/fp64_peak_r01.md); MEASURED_PEAKS.json has no FP64 entry",
+                         "algorithmic_flops_per_launch": flops / ngpus},
+            "clocks": clocks, "gpu_launches": int(launches),
+        }
+        if e2e:
+            line["e2e"] = e2e
+        if cpu:
+            line["cpu_baseline"] = cpu
+        if extra:
+            line["extra"] = extra
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def factorization_extras(L, _capi, torch, dev, stream, N):
+    """Cholesky / LU (/ QR) at the BASELINE sizes on one GPU, device resident, CUDA-event timed."""
+    import ctypes as C
+    out = {}
+
+    def timed(fn, reps=2):
+        fn(); torch.cuda.synchronize()
+        e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+        best = None
+        for _ in range(reps):
+            prep = fn.prepare() if hasattr(fn, "prepare") else None
+            e0.record(); fn(); e1.record(); torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1)
+            best = ms if best is None else min(best, ms)
+        return best
+
+    if hasattr(L, "na_cholesky_f64_dev"):
+        A = torch.empty(N * N, dtype=torch.float64, device=dev)
+        A0 = torch.empty(N * N, dtype=torch.float64, device=dev)
+        _capi.check(L.na_fill_uniform_dev(A0.data_ptr(), N, N, N, 5, stream))
+        M = A0.view(N, N)
+        M.copy_((M + M.t()) * 0.5); M.diagonal().add_(float(N))       # (B+B^T)/2 + n*I, SURVEY §8(d) Cfg 3 (ii)
+        fail = C.c_size_t(0)
+        best = None
+        for _ in range(3):
+            A.copy_(A0); torch.cuda.synchronize()
+            e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+            e0.record()
+            st = _capi.check(L.na_cholesky_f64_dev(N, A.data_ptr(), N, 0, 0.0, C.addressof(fail), stream))
+            e1.record(); torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1); best = ms if best is None else min(best, ms)
+        gf = (N ** 3 / 3.0) / (best * 1e-3) / 1e9
+        out["cholesky_n16384"] = {"ms": best, "gflops": gf, "pct_of_fp64_peak": gf / 1e3 / FP64_PEAK_TFLOPS * 100, "status": st}
+        del A, A0
+    if hasattr(L, "na_lu_f64_dev"):
+        A = torch.empty(N * N, dtype=torch.float64, device=dev)
+        A0 = torch.empty(N * N, dtype=torch.float64, device=dev)
+        _capi.check(L.na_fill_uniform_dev(A0.data_ptr(), N, N, N, 6, stream))
+        swaps = (C.c_size_t * (2 * N))(); ns = C.c_size_t(0)
+        best = None
+        for _ in range(3):
+            A.copy_(A0); torch.cuda.synchronize()
+            e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+            e0.record()
+            _capi.check(L.na_lu_f64_dev(N, N, A.data_ptr(), N, swaps, C.addressof(ns), stream))
+            e1.record(); torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1); best = ms if best is None else min(best, ms)
+        gf = (2.0 * N ** 3 / 3.0) / (best * 1e-3) / 1e9
+        out["lu_n16384"] = {"ms": best, "gflops": gf, "pct_of_fp64_peak": gf / 1e3 / FP64_PEAK_TFLOPS * 100, "nswaps": ns.value}
+        del A, A0
+    if hasattr(L, "na_qr_f64_dev"):
+        m, n = 65536, 4096
+        A = torch.empty(m * n, dtype=torch.float64, device=dev)
+        A0 = torch.empty(m * n, dtype=torch.float64, device=dev)
+        diag = torch.empty(n, dtype=torch.float64, device=dev)
+        _capi.check(L.na_fill_uniform_dev(A0.data_ptr(), m, n, m, 8, stream))
+        best = None
+        for _ in range(2):
+            A.copy_(A0); torch.cuda.synchronize()
+            e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+            e0.record()
+            _capi.check(L.na_qr_f64_dev(m, n, A.data_ptr(), m, diag.data_ptr(), stream))
+            e1.record(); torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1); best = ms if best is None else min(best, ms)
+        fl = 2.0 * m * n * n - 2.0 * n ** 3 / 3.0
+        gf = fl / (best * 1e-3) / 1e9
+        out["qr_65536x4096"] = {"ms": best, "gflops": gf, "pct_of_fp64_peak": gf / 1e3 / FP64_PEAK_TFLOPS * 100}
+    return out
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--n", type=int, default=N_FULL, help="problem size (default: the BASELINE config, 16384)")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-extra", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_gpu(args)
+
+
+if __name__ == "__main__":
+    main()

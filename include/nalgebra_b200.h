@@ -77,6 +77,10 @@ NAB_API int na_dev_synchronize(void);
  * a(i,j) = rand01(seed, i + j*nrows)  (the distribution of DMatrix::new_random,
  * src/base/construction.rs:293-299). */
 NAB_API int na_fill_uniform_dev(double* a, size_t nrows, size_t ncols, size_t lda, uint64_t seed, void* stream);
+/* The block [row0, row0+nrows) x [col0, col0+ncols) of the global_rows-tall matrix of the same
+ * generator (sharded inputs: every rank fills only the panels it owns). */
+NAB_API int na_fill_uniform_block_dev(double* a, size_t nrows, size_t ncols, size_t lda, uint64_t seed,
+                                      size_t row0, size_t col0, size_t global_rows, void* stream);
 
 /* ---- seam 1: GEMM ------------------------------------------------------------------------- */
 /* Replaces matrixmultiply::dgemm(m, k, n, alpha, a, rsa, csa, b, rsb, csb, beta, c, rsc, csc)

@@ -34,6 +34,7 @@ SIGNATURES = {
     "na_memcpy_d2h": (_int, [_p, _p, _sz]),
     "na_dev_synchronize": (_int, []),
     "na_fill_uniform_dev": (_int, [_p, _sz, _sz, _sz, _u64, _p]),
+    "na_fill_uniform_block_dev": (_int, [_p, _sz, _sz, _sz, _u64, _sz, _sz, _sz, _p]),
     "na_dgemm": (_int, _GEMM64),
     "na_sgemm": (_int, _GEMM32),
     "na_dgemm_dev": (_int, _GEMM64 + [_p]),

@@ -116,7 +116,13 @@ int na_dgemm(size_t m, size_t k, size_t n, double alpha, const double* a, ptrdif
 
 int na_fill_uniform_dev(double* a, size_t nrows, size_t ncols, size_t lda, uint64_t seed, void* stream) {
     NAB_TRY(ensure_init());
-    return fill_uniform(static_cast<cudaStream_t>(stream), a, nrows, ncols, lda, seed);
+    return fill_uniform(static_cast<cudaStream_t>(stream), a, nrows, ncols, lda, seed, 0, 0, nrows);
+}
+
+int na_fill_uniform_block_dev(double* a, size_t nrows, size_t ncols, size_t lda, uint64_t seed,
+                              size_t row0, size_t col0, size_t global_rows, void* stream) {
+    NAB_TRY(ensure_init());
+    return fill_uniform(static_cast<cudaStream_t>(stream), a, nrows, ncols, lda, seed, row0, col0, global_rows);
 }
 
 }  // extern "C"

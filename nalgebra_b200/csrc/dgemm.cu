@@ -118,12 +118,21 @@ struct FragAddr {
 
 struct GemmParams {
     int M, N, K;
-    int tiles_m, tiles_n;
+    int tiles_m, tiles_n, num_tiles;
     long long ldc;
     double* C;
     double alpha, beta;
     int lower_only;   // 1: SYRK-shaped, only tiles touching the lower triangle; store row >= col only
 };
+
+// lower_only (SYRK-shaped, square C, BM == BN): t enumerates the lower-triangular tiles row by row.
+__device__ __forceinline__ void tile_coords_lower(int t, int& tm, int& tn) {
+    int r = (int)((sqrt(8.0 * (double)t + 1.0) - 1.0) * 0.5);
+    while ((long long)(r + 1) * (r + 2) / 2 <= t) ++r;
+    while ((long long)r * (r + 1) / 2 > t) --r;
+    tm = r;
+    tn = t - (int)((long long)r * (r + 1) / 2);
+}
 
 __device__ __forceinline__ void tile_coords(int t, int tiles_m, int tiles_n, int& tm, int& tn) {
     const int group = cfg::GROUP_M * tiles_n;
@@ -155,7 +164,7 @@ dgemm_tma_dmma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
     }
     __syncthreads();
 
-    const int num_tiles = p.tiles_m * p.tiles_n;
+    const int num_tiles = p.num_tiles;
     const int kblocks = (p.K + BK - 1) / BK;
 
     if (warp >= CONSUMER_WARPS) {
@@ -168,8 +177,7 @@ dgemm_tma_dmma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
             uint32_t phase = 0;
             for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
                 int tm, tn;
-                tile_coords(t, p.tiles_m, p.tiles_n, tm, tn);
-                if (p.lower_only && tn * BN > tm * BM + BM - 1) continue;
+                if (p.lower_only) tile_coords_lower(t, tm, tn); else tile_coords(t, p.tiles_m, p.tiles_n, tm, tn);
                 for (int kb = 0; kb < kblocks; ++kb) {
                     ptx::mbar_wait(bar_base + 8 * (STAGES + stage), phase ^ 1);
                     const uint32_t full = bar_base + 8 * stage;
@@ -209,8 +217,7 @@ dgemm_tma_dmma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
     uint32_t phase = 0;
     for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
         int tm, tn;
-        tile_coords(t, p.tiles_m, p.tiles_n, tm, tn);
-        if (p.lower_only && tn * BN > tm * BM + BM - 1) continue;
+        if (p.lower_only) tile_coords_lower(t, tm, tn); else tile_coords(t, p.tiles_m, p.tiles_n, tm, tn);
 
         double acc[MT][NT][2];
 #pragma unroll
@@ -331,13 +338,35 @@ __device__ __forceinline__ uint64_t mix64(uint64_t z) {
     z ^= z >> 31;
     return z;
 }
-__global__ void fill_uniform_kernel(double* __restrict__ a, long long nrows, long long ncols, long long lda, uint64_t seed) {
+// a(i,j) = rand01(seed, (row0+i) + (col0+j)*global_rows): a block of the global matrix.
+__global__ void fill_uniform_kernel(double* __restrict__ a, long long nrows, long long ncols, long long lda, uint64_t seed,
+                                    long long row0, long long col0, long long global_rows) {
     const long long total = nrows * ncols;
     for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
         const long long r = idx % nrows, c = idx / nrows;
-        const uint64_t h = mix64((uint64_t)idx + (seed + 1) * 0x9E3779B97F4A7C15ULL);
+        const uint64_t gidx = (uint64_t)((row0 + r) + (col0 + c) * global_rows);
+        const uint64_t h = mix64(gidx + (seed + 1) * 0x9E3779B97F4A7C15ULL);
         a[r + c * lda] = (double)(h >> 11) * (1.0 / 9007199254740992.0);
     }
+}
+
+__global__ void copy_strided_kernel(double* __restrict__ dst, long long rsd, long long csd, const double* __restrict__ src,
+                                    long long rss, long long css, long long rows, long long cols, int dst_row_fast) {
+    const long long total = rows * cols;
+    for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+        long long r, c;
+        if (dst_row_fast) { r = idx % rows; c = idx / rows; } else { c = idx % cols; r = idx / cols; }
+        dst[r * rsd + c * csd] = src[r * rss + c * css];
+    }
+}
+int copy_strided(cudaStream_t s, double* dst, ptrdiff_t rsd, ptrdiff_t csd, const double* src, ptrdiff_t rss, ptrdiff_t css,
+                 size_t rows, size_t cols) {
+    if (rows == 0 || cols == 0) return NA_OK;
+    const int row_fast = (rsd < 0 ? -rsd : rsd) <= (csd < 0 ? -csd : csd) ? 1 : 0;
+    int blocks = (int)std::min<size_t>(ceil_div(rows * cols, 256), (size_t)ctx().sm_count * 16);
+    copy_strided_kernel<<<blocks, 256, 0, s>>>(dst, rsd, csd, src, rss, css, (long long)rows, (long long)cols, row_fast);
+    NAB_LAUNCH_CHECK();
+    return NA_OK;
 }
 
 int pack_strided(cudaStream_t s, double* dst, size_t ldd, const double* src, ptrdiff_t rs, ptrdiff_t cs, size_t rows, size_t cols) {
@@ -364,11 +393,13 @@ int scale_strided(cudaStream_t s, double* c, ptrdiff_t rs, ptrdiff_t cs, size_t 
     NAB_LAUNCH_CHECK();
     return NA_OK;
 }
-int fill_uniform(cudaStream_t s, double* a, size_t nrows, size_t ncols, size_t lda, uint64_t seed) {
+int fill_uniform(cudaStream_t s, double* a, size_t nrows, size_t ncols, size_t lda, uint64_t seed,
+                 size_t row0, size_t col0, size_t global_rows) {
     if (nrows == 0 || ncols == 0) return NA_OK;
     size_t total = nrows * ncols;
     int blocks = (int)std::min<size_t>(ceil_div(total, 256), (size_t)ctx().sm_count * 16);
-    fill_uniform_kernel<<<blocks, 256, 0, s>>>(a, (long long)nrows, (long long)ncols, (long long)lda, seed);
+    fill_uniform_kernel<<<blocks, 256, 0, s>>>(a, (long long)nrows, (long long)ncols, (long long)lda, seed,
+                                               (long long)row0, (long long)col0, (long long)global_rows);
     NAB_LAUNCH_CHECK();
     return NA_OK;
 }
@@ -419,8 +450,7 @@ static int launch_gemm(cudaStream_t s, bool a_kmajor, bool b_kmajor, const CUten
         e = cudaFuncSetAttribute(dgemm_tma_dmma_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES); if (e) attr_err = e;
     });
     if (attr_err != cudaSuccess) return cuda_fail(attr_err, "cudaFuncSetAttribute(dgemm)", __FILE__, __LINE__);
-    const int num_tiles = p.tiles_m * p.tiles_n;
-    const int grid = std::min(num_tiles, ctx().sm_count);
+    const int grid = std::min(p.num_tiles, ctx().sm_count);
     if (a_kmajor) {
         if (b_kmajor) dgemm_tma_dmma_kernel<true, true><<<grid, THREADS, SMEM_BYTES, s>>>(ma, mb, p);
         else dgemm_tma_dmma_kernel<true, false><<<grid, THREADS, SMEM_BYTES, s>>>(ma, mb, p);
@@ -450,6 +480,13 @@ static int gemm_colmajor_c(cudaStream_t s, bool lower_only, size_t m, size_t n, 
     p.M = (int)m; p.N = (int)n; p.K = (int)k;
     p.tiles_m = (int)ceil_div(m, BM); p.tiles_n = (int)ceil_div(n, BN);
     p.ldc = (long long)ldc; p.C = c; p.alpha = alpha; p.beta = beta; p.lower_only = lower_only ? 1 : 0;
+    if (lower_only) {
+        if (m != n) { set_error("gemm: lower_only needs a square C"); return NA_EINVAL; }
+        p.num_tiles = (int)((long long)p.tiles_m * (p.tiles_m + 1) / 2);
+    } else {
+        if ((long long)p.tiles_m * p.tiles_n > 0x7fffffffLL) { set_error("gemm: too many tiles"); return NA_EINVAL; }
+        p.num_tiles = p.tiles_m * p.tiles_n;
+    }
     return launch_gemm(s, a_km, b_km, ma, mb, p);
 }
 

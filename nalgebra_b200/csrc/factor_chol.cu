@@ -1,0 +1,232 @@
+// factor_chol.cu -- blocked triangular solves and the blocked Cholesky on the DGEMM tile engine,
+// plus their extern "C" entry points.
+//
+// Reference semantics: Cholesky::new / new_with_substitute / solve_mut
+// (/root/reference/src/linalg/cholesky.rs:196-272, 122-129) and the triangular solves of
+// /root/reference/src/linalg/solve.rs.  The reference runs unblocked Level-1 loops; here the
+// O(n^3) work is restructured as recursive panel + TRSM + SYRK so that it runs on the DMMA GEMM
+// engine.  Parity is therefore on results (residuals, failure column), not on operation order.
+#include "common.cuh"
+#include "kernels.cuh"
+
+namespace nab {
+
+constexpr size_t IBs = kInvBlock;
+
+// ------------------------------------------------------------------------------------------------
+// TRSM (left side): M X = B, recursive; base case X_b = inv(M_bb) * B_b through the GEMM engine.
+// ------------------------------------------------------------------------------------------------
+struct TrsmCtx {
+    cudaStream_t s;
+    bool eff_lower;
+    const double* m; ptrdiff_t rsm, csm;
+    const double* inv;            // [nblk][128*128]
+    double* b; ptrdiff_t rsb, csb; size_t nrhs;
+    double* tmp; ptrdiff_t rst, cst;   // 128 x nrhs scratch with B's orientation
+};
+
+static int trsm_rec(const TrsmCtx& c, size_t r0, size_t len) {
+    if (len == 0) return NA_OK;
+    if (len <= IBs) {
+        const double* inv = c.inv + (r0 / IBs) * IBs * IBs;
+        double* brow = c.b + (ptrdiff_t)r0 * c.rsb;
+        NAB_TRY(dgemm_device(c.s, false, len, len, c.nrhs, 1.0, inv, 1, (ptrdiff_t)IBs, brow, c.rsb, c.csb, 0.0, c.tmp, c.rst, c.cst));
+        return copy_strided(c.s, brow, c.rsb, c.csb, c.tmp, c.rst, c.cst, len, c.nrhs);
+    }
+    const size_t h = round_up(len / 2, IBs);
+    const size_t r1 = r0 + h, len1 = len - h;
+    if (c.eff_lower) {
+        NAB_TRY(trsm_rec(c, r0, h));
+        // B[r1:] -= M[r1:, r0:r1] * B[r0:r1]
+        NAB_TRY(dgemm_device(c.s, false, len1, h, c.nrhs, -1.0, c.m + (ptrdiff_t)r1 * c.rsm + (ptrdiff_t)r0 * c.csm, c.rsm, c.csm,
+                             c.b + (ptrdiff_t)r0 * c.rsb, c.rsb, c.csb, 1.0, c.b + (ptrdiff_t)r1 * c.rsb, c.rsb, c.csb));
+        return trsm_rec(c, r1, len1);
+    } else {
+        NAB_TRY(trsm_rec(c, r1, len1));
+        // B[r0:r1] -= M[r0:r1, r1:] * B[r1:]
+        NAB_TRY(dgemm_device(c.s, false, h, len1, c.nrhs, -1.0, c.m + (ptrdiff_t)r0 * c.rsm + (ptrdiff_t)r1 * c.csm, c.rsm, c.csm,
+                             c.b + (ptrdiff_t)r1 * c.rsb, c.rsb, c.csb, 1.0, c.b + (ptrdiff_t)r0 * c.rsb, c.rsb, c.csb));
+        return trsm_rec(c, r0, h);
+    }
+}
+
+int trsm_left(cudaStream_t s, bool eff_lower, bool unit, size_t n, const double* m, ptrdiff_t rsm, ptrdiff_t csm,
+              const double* diag_abs, const double* inv_blocks, double* b, ptrdiff_t rsb, ptrdiff_t csb, size_t nrhs) {
+    if (n == 0 || nrhs == 0) return NA_OK;
+    Scratch inv, tmp;
+    if (!inv_blocks) {
+        NAB_TRY(inv.alloc(ceil_div(n, IBs) * IBs * IBs * sizeof(double), s));
+        NAB_TRY(trtri_blocks(s, m, rsm, csm, n, eff_lower, unit, diag_abs, inv.as<double>()));
+        inv_blocks = inv.as<double>();
+    }
+    TrsmCtx c{s, eff_lower, m, rsm, csm, inv_blocks, b, rsb, csb, nrhs, nullptr, 0, 0};
+    const bool b_row_fast = (rsb == 1);
+    const size_t ldt = b_row_fast ? IBs : round_up(nrhs, 2);
+    NAB_TRY(tmp.alloc((b_row_fast ? ldt * nrhs : ldt * IBs) * sizeof(double), s));
+    c.tmp = tmp.as<double>();
+    c.rst = b_row_fast ? 1 : (ptrdiff_t)ldt;
+    c.cst = b_row_fast ? (ptrdiff_t)ldt : 1;
+    return trsm_rec(c, 0, n);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Cholesky: recursive, leaves = POTF2 on 128-blocks (+ TRTRI of the leaf for the TRSMs above it).
+// ------------------------------------------------------------------------------------------------
+struct CholCtx {
+    cudaStream_t s;
+    double* a; size_t lda;
+    int use_sub; double sub;
+    double* inv;                      // [n/128][128*128] inverses of L's diagonal blocks
+    unsigned long long* fail;         // device: first failing column (init ~0)
+};
+
+static int chol_rec(const CholCtx& c, size_t j0, size_t n) {
+    if (n == 0) return NA_OK;
+    double* ajj = c.a + j0 + j0 * c.lda;
+    if (n <= IBs) {
+        NAB_TRY(potf2(c.s, ajj, c.lda, (int)n, c.use_sub, c.sub, j0, c.fail));
+        return trtri_blocks(c.s, ajj, 1, (ptrdiff_t)c.lda, n, true, false, nullptr, c.inv + (j0 / IBs) * IBs * IBs);
+    }
+    const size_t n1 = round_up(n / 2, IBs), n2 = n - n1;
+    NAB_TRY(chol_rec(c, j0, n1));
+    double* a21 = ajj + n1;
+    // A21 <- A21 * L11^-T   <=>   L11 * X^T = A21^T  (left solve on the transposed view of A21)
+    NAB_TRY(trsm_left(c.s, true, false, n1, ajj, 1, (ptrdiff_t)c.lda, nullptr, c.inv + (j0 / IBs) * IBs * IBs,
+                      a21, (ptrdiff_t)c.lda, 1, n2));
+    // A22 <- A22 - A21 * A21^T, lower triangle only
+    double* a22 = ajj + n1 + n1 * c.lda;
+    NAB_TRY(dgemm_device(c.s, true, n2, n1, n2, -1.0, a21, 1, (ptrdiff_t)c.lda, a21, (ptrdiff_t)c.lda, 1, 1.0, a22, 1, (ptrdiff_t)c.lda));
+    return chol_rec(c, j0 + n1, n2);
+}
+
+int cholesky_device(cudaStream_t s, size_t n, double* a, size_t lda, int use_sub, double sub, size_t* fail_col) {
+    if (n == 0) return NA_OK;
+    if (lda < n) { set_error("cholesky: lda < n"); return NA_EINVAL; }
+    Scratch inv, flag;
+    NAB_TRY(inv.alloc(ceil_div(n, IBs) * IBs * IBs * sizeof(double), s));
+    NAB_TRY(flag.alloc(sizeof(unsigned long long), s));
+    NAB_CUDA(cudaMemsetAsync(flag.p, 0xff, sizeof(unsigned long long), s));
+    CholCtx c{s, a, lda, use_sub, sub, inv.as<double>(), flag.as<unsigned long long>()};
+    NAB_TRY(chol_rec(c, 0, n));
+    unsigned long long h = 0;
+    NAB_CUDA(cudaMemcpyAsync(&h, flag.p, sizeof(h), cudaMemcpyDeviceToHost, s));
+    NAB_CUDA(cudaStreamSynchronize(s));
+    if (h != ~0ull) {
+        if (fail_col) *fail_col = (size_t)h;
+        return NA_NOT_PD;
+    }
+    return NA_OK;
+}
+
+// Cholesky::solve_mut: L y = b, then L^T x = y (cholesky.rs:127-128).
+int cholesky_solve_device(cudaStream_t s, size_t n, const double* l, size_t lda, double* b, size_t ldb, size_t nrhs) {
+    if (n == 0 || nrhs == 0) return NA_OK;
+    Scratch inv;
+    NAB_TRY(inv.alloc(ceil_div(n, IBs) * IBs * IBs * sizeof(double), s));
+    NAB_TRY(trtri_blocks(s, l, 1, (ptrdiff_t)lda, n, true, false, nullptr, inv.as<double>()));
+    NAB_TRY(trsm_left(s, true, false, n, l, 1, (ptrdiff_t)lda, nullptr, inv.as<double>(), b, 1, (ptrdiff_t)ldb, nrhs));
+    // L^T is effectively upper; inverse of the diagonal blocks of L^T = transposes of inv(L_bb)
+    Scratch invt;
+    NAB_TRY(invt.alloc(ceil_div(n, IBs) * IBs * IBs * sizeof(double), s));
+    NAB_TRY(trtri_blocks(s, l, (ptrdiff_t)lda, 1, n, false, false, nullptr, invt.as<double>()));
+    return trsm_left(s, false, false, n, l, (ptrdiff_t)lda, 1, nullptr, invt.as<double>(), b, 1, (ptrdiff_t)ldb, nrhs);
+}
+
+// ---- host <-> device staging of an ld-strided column-major matrix --------------------------------
+int upload_matrix(cudaStream_t s, Scratch& buf, size_t& ldd, const double* h, size_t ldh, size_t rows, size_t cols) {
+    ldd = round_up(std::max<size_t>(rows, 1), 2);
+    NAB_TRY(buf.alloc(ldd * std::max<size_t>(cols, 1) * sizeof(double), s));
+    if (rows && cols) NAB_CUDA(cudaMemcpy2DAsync(buf.p, ldd * 8, h, ldh * 8, rows * 8, cols, cudaMemcpyHostToDevice, s));
+    return NA_OK;
+}
+int download_matrix(cudaStream_t s, double* h, size_t ldh, const double* d, size_t ldd, size_t rows, size_t cols) {
+    if (rows && cols) NAB_CUDA(cudaMemcpy2DAsync(h, ldh * 8, d, ldd * 8, rows * 8, cols, cudaMemcpyDeviceToHost, s));
+    return NA_OK;
+}
+
+}  // namespace nab
+
+using namespace nab;
+
+extern "C" {
+
+int na_cholesky_f64_dev(size_t n, double* a, size_t lda, int use_sub, double sub, size_t* fail_col, void* stream) {
+    NAB_TRY(ensure_init());
+    return cholesky_device(static_cast<cudaStream_t>(stream), n, a, lda, use_sub, sub, fail_col);
+}
+
+int na_cholesky_f64(size_t n, double* a, size_t lda, int use_sub, double sub, size_t* fail_col) {
+    NAB_TRY(ensure_init());
+    if (n == 0) return NA_OK;
+    if (!a || lda < n) { set_error("cholesky: bad arguments"); return NA_EINVAL; }
+    std::lock_guard<std::mutex> lock(host_api_mutex());
+    cudaStream_t s = ctx().stream;
+    Scratch d; size_t ldd;
+    NAB_TRY(upload_matrix(s, d, ldd, a, lda, n, n));
+    int st = cholesky_device(s, n, d.as<double>(), ldd, use_sub, sub, fail_col);
+    if (st < 0) return st;
+    NAB_TRY(download_matrix(s, a, lda, d.as<double>(), ldd, n, n));
+    NAB_CUDA(cudaStreamSynchronize(s));
+    return st;
+}
+
+int na_cholesky_solve_f64_dev(size_t n, const double* l, size_t lda, double* b, size_t ldb, size_t nrhs, void* stream) {
+    NAB_TRY(ensure_init());
+    return cholesky_solve_device(static_cast<cudaStream_t>(stream), n, l, lda, b, ldb, nrhs);
+}
+
+int na_cholesky_solve_f64(size_t n, const double* l, size_t lda, double* b, size_t ldb, size_t nrhs) {
+    NAB_TRY(ensure_init());
+    if (n == 0 || nrhs == 0) return NA_OK;
+    if (!l || !b || lda < n || ldb < n) { set_error("cholesky_solve: bad arguments"); return NA_EINVAL; }
+    std::lock_guard<std::mutex> lock(host_api_mutex());
+    cudaStream_t s = ctx().stream;
+    Scratch dl, db; size_t ldl, lddb;
+    NAB_TRY(upload_matrix(s, dl, ldl, l, lda, n, n));
+    NAB_TRY(upload_matrix(s, db, lddb, b, ldb, n, nrhs));
+    NAB_TRY(cholesky_solve_device(s, n, dl.as<double>(), ldl, db.as<double>(), lddb, nrhs));
+    NAB_TRY(download_matrix(s, b, ldb, db.as<double>(), lddb, n, nrhs));
+    NAB_CUDA(cudaStreamSynchronize(s));
+    return NA_OK;
+}
+
+// op(T) x = b.  NA_SINGULAR on an exactly-zero diagonal (checked variants of solve.rs:55-182).
+int na_tri_solve_f64_dev(int lower, int trans, int unit_diag, size_t n, const double* t, size_t ldt,
+                         double* b, size_t ldb, size_t nrhs, void* stream) {
+    NAB_TRY(ensure_init());
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    if (n == 0 || nrhs == 0) return NA_OK;
+    if (!t || !b || ldt < n || ldb < n) { set_error("tri_solve: bad arguments"); return NA_EINVAL; }
+    if (!unit_diag) {
+        Scratch flag;
+        NAB_TRY(flag.alloc(sizeof(int), s));
+        NAB_CUDA(cudaMemsetAsync(flag.p, 0, sizeof(int), s));
+        NAB_TRY(zero_diag_check(s, t, ldt, nullptr, n, flag.as<int>()));
+        int h = 0;
+        NAB_CUDA(cudaMemcpyAsync(&h, flag.p, sizeof(int), cudaMemcpyDeviceToHost, s));
+        NAB_CUDA(cudaStreamSynchronize(s));
+        if (h) return NA_SINGULAR;
+    }
+    const bool eff_lower = (lower != 0) != (trans != 0);
+    const ptrdiff_t rsm = trans ? (ptrdiff_t)ldt : 1, csm = trans ? 1 : (ptrdiff_t)ldt;
+    return trsm_left(s, eff_lower, unit_diag != 0, n, t, rsm, csm, nullptr, nullptr, b, 1, (ptrdiff_t)ldb, nrhs);
+}
+
+int na_tri_solve_f64(int lower, int trans, int unit_diag, size_t n, const double* t, size_t ldt,
+                     double* b, size_t ldb, size_t nrhs) {
+    NAB_TRY(ensure_init());
+    if (n == 0 || nrhs == 0) return NA_OK;
+    if (!t || !b || ldt < n || ldb < n) { set_error("tri_solve: bad arguments"); return NA_EINVAL; }
+    std::lock_guard<std::mutex> lock(host_api_mutex());
+    cudaStream_t s = ctx().stream;
+    Scratch dt, db; size_t ldd, lddb;
+    NAB_TRY(upload_matrix(s, dt, ldd, t, ldt, n, n));
+    NAB_TRY(upload_matrix(s, db, lddb, b, ldb, n, nrhs));
+    int st = na_tri_solve_f64_dev(lower, trans, unit_diag, n, dt.as<double>(), ldd, db.as<double>(), lddb, nrhs, s);
+    if (st != NA_OK) return st;
+    NAB_TRY(download_matrix(s, b, ldb, db.as<double>(), lddb, n, nrhs));
+    NAB_CUDA(cudaStreamSynchronize(s));
+    return NA_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,175 @@
+// factor_lu.cu -- recursive blocked LU with partial pivoting and LU solve, on the DGEMM engine.
+//
+// Reference: LU::new (/root/reference/src/linalg/lu.rs:93-122), gauss_step(_swap) (:337-389),
+// LU::solve_mut (:242-260), PermutationSequence (src/linalg/permutation_sequence.rs).
+// The reference is a right-looking rank-1 loop; here the columns are split recursively
+// (left half -> row swaps + TRSM + GEMM on the right half -> right half -> row swaps on the left
+// half), so all O(n^3) work is GEMM/TRSM on the DMMA engine and the leaves are the cooperative
+// GETF2 panel kernel.  Whole rows are swapped, so the packed result has the reference's layout
+// (identical to LAPACK getrf).  Everything stays on the device: no host pivoting.
+#include <vector>
+
+#include "common.cuh"
+#include "kernels.cuh"
+
+namespace nab {
+
+struct LuCtx {
+    cudaStream_t s;
+    double* a; size_t lda; size_t M;
+    size_t W;                 // leaf panel width
+    int* ipiv;                // device, absolute pivot rows
+    int* iota;                // device, 0..mn-1
+    void* ws_getf2; void* ws_perm;
+};
+
+static int lu_apply_swaps(const LuCtx& c, size_t k0, size_t K, double* cols, size_t ncols) {
+    if (K == 0 || ncols == 0) return NA_OK;
+    NAB_TRY(rowperm_build(c.s, c.iota + k0, c.ipiv + k0, K, 1, c.M, c.ws_perm));
+    return rowperm_apply(c.s, cols, c.lda, ncols, std::min(2 * K, c.M), c.ws_perm, c.M);
+}
+
+static int lu_rec(const LuCtx& c, size_t j0, size_t nc) {
+    if (nc == 0) return NA_OK;
+    double* ajj = c.a + j0 + j0 * c.lda;
+    if (nc <= c.W) return getf2_panel(c.s, ajj, c.lda, c.M - j0, nc, j0, c.ipiv, c.ws_getf2);
+    size_t n1 = round_up(nc / 2, c.W);
+    if (n1 >= nc) n1 = nc - c.W;
+    const size_t n2 = nc - n1;
+    NAB_TRY(lu_rec(c, j0, n1));
+    double* a12 = ajj + n1 * c.lda;
+    NAB_TRY(lu_apply_swaps(c, j0, n1, a12 - j0, n2));                         // whole rows: columns start at row 0
+    // U12 = L11^-1 * A12 (unit lower)
+    NAB_TRY(trsm_left(c.s, true, true, n1, ajj, 1, (ptrdiff_t)c.lda, nullptr, nullptr, a12, 1, (ptrdiff_t)c.lda, n2));
+    // A22 -= A21 * U12
+    const size_t m2 = c.M - j0 - n1;
+    if (m2 > 0)
+        NAB_TRY(dgemm_device(c.s, false, m2, n1, n2, -1.0, ajj + n1, 1, (ptrdiff_t)c.lda, a12, 1, (ptrdiff_t)c.lda, 1.0,
+                             a12 + n1, 1, (ptrdiff_t)c.lda));
+    NAB_TRY(lu_rec(c, j0 + n1, n2));
+    return lu_apply_swaps(c, j0 + n1, std::min(n2, c.M - j0 - n1), c.a + j0 * c.lda, n1);
+}
+
+static size_t lu_leaf_width(size_t M) {
+    if (M <= 28000) return 128;
+    if (M <= 56000) return 64;
+    if (M <= 113000) return 32;
+    return 16;
+}
+
+// swaps/nswaps: HOST outputs (PermutationSequence pairs).
+int lu_device(cudaStream_t s, size_t M, size_t N, double* a, size_t lda, size_t* swaps, size_t* nswaps) {
+    const size_t mn = std::min(M, N);
+    if (nswaps) *nswaps = 0;
+    if (mn == 0) return NA_OK;
+    if (lda < M) { set_error("lu: lda < m"); return NA_EINVAL; }
+    if (M > 0x7fffff00ull || N > 0x7fffff00ull) { set_error("lu: dimension exceeds 2^31"); return NA_EINVAL; }
+    Scratch ipiv, iota, wsg, wsp;
+    NAB_TRY(ipiv.alloc(mn * sizeof(int), s));
+    NAB_TRY(iota.alloc(mn * sizeof(int), s));
+    NAB_TRY(wsg.alloc(getf2_workspace_bytes(), s));
+    NAB_TRY(wsp.alloc(rowperm_workspace_bytes(M), s));
+    NAB_TRY(iota_int(s, iota.as<int>(), mn, 0));
+    NAB_TRY(iota_int(s, ipiv.as<int>(), mn, 0));
+    LuCtx c{s, a, lda, M, lu_leaf_width(M), ipiv.as<int>(), iota.as<int>(), wsg.p, wsp.p};
+    NAB_TRY(lu_rec(c, 0, mn));
+    if (N > mn) {   // wide matrix: the columns right of the square part
+        double* ar = a + mn * lda;
+        NAB_TRY(lu_apply_swaps(c, 0, mn, ar, N - mn));
+        NAB_TRY(trsm_left(s, true, true, mn, a, 1, (ptrdiff_t)lda, nullptr, nullptr, ar, 1, (ptrdiff_t)lda, N - mn));
+    }
+    std::vector<int> h(mn);
+    NAB_CUDA(cudaMemcpyAsync(h.data(), ipiv.p, mn * sizeof(int), cudaMemcpyDeviceToHost, s));
+    NAB_CUDA(cudaStreamSynchronize(s));
+    // PermutationSequence::append_permutation keeps only i != i2 (permutation_sequence.rs:84-93)
+    size_t len = 0;
+    if (swaps) {
+        for (size_t i = 0; i < mn; ++i)
+            if ((size_t)h[i] != i) { swaps[2 * len] = i; swaps[2 * len + 1] = (size_t)h[i]; ++len; }
+        for (size_t i = 2 * len; i < 2 * mn; ++i) swaps[i] = 0;
+    }
+    if (nswaps) *nswaps = len;
+    return NA_OK;
+}
+
+// LU::solve_mut: permute rows, unit-lower solve, upper solve with zero-diagonal check.
+int lu_solve_device(cudaStream_t s, size_t n, const double* lu, size_t lda, const size_t* swaps, size_t nswaps,
+                    double* b, size_t ldb, size_t nrhs) {
+    if (n == 0 || nrhs == 0) return NA_OK;
+    if (n > 0x7fffff00ull) { set_error("lu_solve: dimension exceeds 2^31"); return NA_EINVAL; }
+    if (nswaps) {
+        std::vector<int> h(2 * nswaps);
+        for (size_t i = 0; i < 2 * nswaps; ++i) {
+            if (swaps[i] >= n) { set_error("lu_solve: swap index out of range"); return NA_EINVAL; }
+            h[i] = (int)swaps[i];
+        }
+        Scratch dsw, wsp;
+        NAB_TRY(dsw.alloc(2 * nswaps * sizeof(int), s));
+        NAB_TRY(wsp.alloc(rowperm_workspace_bytes(n), s));
+        NAB_CUDA(cudaMemcpyAsync(dsw.p, h.data(), 2 * nswaps * sizeof(int), cudaMemcpyHostToDevice, s));
+        NAB_TRY(rowperm_build(s, dsw.as<int>(), dsw.as<int>() + 1, nswaps, 2, n, wsp.p));
+        NAB_TRY(rowperm_apply(s, b, ldb, nrhs, std::min(2 * nswaps, n), wsp.p, n));
+        NAB_CUDA(cudaStreamSynchronize(s));   // h must outlive the copy
+    }
+    NAB_TRY(trsm_left(s, true, true, n, lu, 1, (ptrdiff_t)lda, nullptr, nullptr, b, 1, (ptrdiff_t)ldb, nrhs));
+    Scratch flag;
+    NAB_TRY(flag.alloc(sizeof(int), s));
+    NAB_CUDA(cudaMemsetAsync(flag.p, 0, sizeof(int), s));
+    NAB_TRY(zero_diag_check(s, lu, lda, nullptr, n, flag.as<int>()));
+    int hflag = 0;
+    NAB_CUDA(cudaMemcpyAsync(&hflag, flag.p, sizeof(int), cudaMemcpyDeviceToHost, s));
+    NAB_CUDA(cudaStreamSynchronize(s));
+    if (hflag) return NA_SINGULAR;                                 // solve.rs:169-171
+    return trsm_left(s, false, false, n, lu, 1, (ptrdiff_t)lda, nullptr, nullptr, b, 1, (ptrdiff_t)ldb, nrhs);
+}
+
+}  // namespace nab
+
+using namespace nab;
+
+extern "C" {
+
+int na_lu_f64_dev(size_t m, size_t n, double* a, size_t lda, size_t* swaps, size_t* nswaps, void* stream) {
+    NAB_TRY(ensure_init());
+    return lu_device(static_cast<cudaStream_t>(stream), m, n, a, lda, swaps, nswaps);
+}
+
+int na_lu_f64(size_t m, size_t n, double* a, size_t lda, size_t* swaps, size_t* nswaps) {
+    NAB_TRY(ensure_init());
+    if (nswaps) *nswaps = 0;
+    if (m == 0 || n == 0) return NA_OK;
+    if (!a || lda < m) { set_error("lu: bad arguments"); return NA_EINVAL; }
+    std::lock_guard<std::mutex> lock(host_api_mutex());
+    cudaStream_t s = ctx().stream;
+    Scratch d; size_t ldd;
+    NAB_TRY(upload_matrix(s, d, ldd, a, lda, m, n));
+    NAB_TRY(lu_device(s, m, n, d.as<double>(), ldd, swaps, nswaps));
+    NAB_TRY(download_matrix(s, a, lda, d.as<double>(), ldd, m, n));
+    NAB_CUDA(cudaStreamSynchronize(s));
+    return NA_OK;
+}
+
+int na_lu_solve_f64_dev(size_t n, const double* lu, size_t lda, const size_t* swaps, size_t nswaps,
+                        double* b, size_t ldb, size_t nrhs, void* stream) {
+    NAB_TRY(ensure_init());
+    return lu_solve_device(static_cast<cudaStream_t>(stream), n, lu, lda, swaps, nswaps, b, ldb, nrhs);
+}
+
+int na_lu_solve_f64(size_t n, const double* lu, size_t lda, const size_t* swaps, size_t nswaps,
+                    double* b, size_t ldb, size_t nrhs) {
+    NAB_TRY(ensure_init());
+    if (n == 0 || nrhs == 0) return NA_OK;
+    if (!lu || !b || lda < n || ldb < n || (nswaps && !swaps)) { set_error("lu_solve: bad arguments"); return NA_EINVAL; }
+    std::lock_guard<std::mutex> lock(host_api_mutex());
+    cudaStream_t s = ctx().stream;
+    Scratch dl, db; size_t ldl, lddb;
+    NAB_TRY(upload_matrix(s, dl, ldl, lu, lda, n, n));
+    NAB_TRY(upload_matrix(s, db, lddb, b, ldb, n, nrhs));
+    int st = lu_solve_device(s, n, dl.as<double>(), ldl, swaps, nswaps, db.as<double>(), lddb, nrhs);
+    if (st < 0) return st;
+    NAB_TRY(download_matrix(s, b, ldb, db.as<double>(), lddb, n, nrhs));   // garbage on NA_SINGULAR, like the reference
+    NAB_CUDA(cudaStreamSynchronize(s));
+    return st;
+}
+
+}  // extern "C"

@@ -14,6 +14,38 @@ int dgemm_device(cudaStream_t s, bool lower_only, size_t m, size_t k, size_t n, 
 int pack_strided(cudaStream_t s, double* dst, size_t ldd, const double* src, ptrdiff_t rs, ptrdiff_t cs, size_t rows, size_t cols);
 int scatter_strided(cudaStream_t s, double* dst, ptrdiff_t rs, ptrdiff_t cs, const double* src, size_t lds, size_t rows, size_t cols);
 int scale_strided(cudaStream_t s, double* c, ptrdiff_t rs, ptrdiff_t cs, size_t rows, size_t cols, double beta);
-int fill_uniform(cudaStream_t s, double* a, size_t nrows, size_t ncols, size_t lda, uint64_t seed);
+int fill_uniform(cudaStream_t s, double* a, size_t nrows, size_t ncols, size_t lda, uint64_t seed,
+                 size_t row0, size_t col0, size_t global_rows);
+
+// general strided 2D copy dst(i,j) = src(i,j)
+int copy_strided(cudaStream_t s, double* dst, ptrdiff_t rsd, ptrdiff_t csd, const double* src, ptrdiff_t rss, ptrdiff_t css,
+                 size_t rows, size_t cols);
+
+// ---- panel_chol_tri.cu ---------------------------------------------------------------------------
+constexpr int kInvBlock = 128;     // diagonal-block size of POTF2 / TRTRI / the TRSM base case
+int potf2(cudaStream_t st, double* a, size_t lda, int n, int use_sub, double sub, size_t col0, unsigned long long* fail_col);
+int trtri_blocks(cudaStream_t st, const double* t, ptrdiff_t rs, ptrdiff_t cs, size_t n, bool eff_lower, bool unit,
+                 const double* diag_abs, double* out);
+int zero_diag_check(cudaStream_t st, const double* t, size_t ldt, const double* diag_abs, size_t n, int* flag);
+int set_identity(cudaStream_t st, double* a, size_t lda, size_t rows, size_t cols);
+
+// ---- panel_lu.cu ---------------------------------------------------------------------------------
+constexpr int kLuPanel = 128;      // widest GETF2 leaf panel
+size_t getf2_workspace_bytes();
+int getf2_panel(cudaStream_t st, double* a_panel, size_t lda, size_t m, size_t w, size_t j0, int* ipiv, void* ws);
+size_t rowperm_workspace_bytes(size_t n);
+int rowperm_build(cudaStream_t st, const int* sa, const int* sb, size_t K, size_t stride, size_t n, void* ws);
+int rowperm_apply(cudaStream_t st, double* a, size_t lda, size_t ncols, size_t max_touched, const void* ws, size_t n);
+int iota_int(cudaStream_t st, int* p, size_t n, int offset);
+
+// ---- factor.cu -----------------------------------------------------------------------------------
+// Solves M X = B in place on B (n x nrhs, strides rsb/csb, one of them 1).  M (strides rsm/csm) is
+// effectively lower or upper triangular.  inv_blocks: optional precomputed inverses of M's 128x128
+// diagonal blocks (trtri_blocks layout); computed internally when null.
+int trsm_left(cudaStream_t s, bool eff_lower, bool unit, size_t n, const double* m, ptrdiff_t rsm, ptrdiff_t csm,
+              const double* diag_abs, const double* inv_blocks, double* b, ptrdiff_t rsb, ptrdiff_t csb, size_t nrhs);
+int cholesky_device(cudaStream_t s, size_t n, double* a, size_t lda, int use_sub, double sub, size_t* fail_col);
+int upload_matrix(cudaStream_t s, Scratch& buf, size_t& ldd, const double* h, size_t ldh, size_t rows, size_t cols);
+int download_matrix(cudaStream_t s, double* h, size_t ldh, const double* d, size_t ldd, size_t rows, size_t cols);
 
 }  // namespace nab

@@ -1,0 +1,330 @@
+// panel_lu.cu -- LU panel kernels: cooperative GETF2 with partial pivoting, swap-sequence ->
+// permutation, parallel row permutation (LASWP).
+//
+// Reference semantics: LU::new's column step (/root/reference/src/linalg/lu.rs:103-119):
+//   piv = icamax(A[i.., i]) + i   -- largest |x|, LOWEST index wins ties, a NaN only wins at
+//                                    index 0 (src/base/min_max.rs:221-240)
+//   diag == 0 -> skip the column (no swap, no scaling)               (lu.rs:107-110)
+//   swap whole rows, multiply the column by 1/diag (reciprocal, lu.rs:344-349), rank-1 update.
+#include <algorithm>
+
+#include "common.cuh"
+#include "kernels.cuh"
+
+namespace nab {
+
+// ------------------------------------------------------------------------------------------------
+// GETF2: m x w panel (w <= 128), rows distributed over G co-resident CTAs and kept in shared
+// memory for the whole panel; one grid-wide barrier per column.
+//
+// Per column c every CTA publishes its local pivot candidate (|value|, row, the candidate's full
+// row of w values) to a global slot; CTA 0 also publishes the current row c.  After the barrier
+// every CTA reduces the G candidates to the same winner, reads the winner's row (= the pivot row)
+// and row c, performs its share of the swap in shared memory, scales its rows of column c by the
+// reciprocal pivot and applies the rank-1 update to columns c+1..w-1.  Slots are double-buffered
+// by column parity (a CTA can be at most one barrier ahead).
+// ------------------------------------------------------------------------------------------------
+struct Getf2Params {
+    double* a; long long lda;      // panel origin = A[j0, j0]
+    int m, w;                      // panel rows / cols
+    int rp;                        // rows per CTA (multiple of 32)
+    int j0;                        // global row/col offset of the panel (for ipiv values)
+    int* ipiv;                     // ipiv[j0 + c] = global pivot row of column c
+    double* slots;                 // [2][G][w + 2]  (absval, row, candidate row values)
+    double* rowc;                  // [2][w]          current row c, published by its owner
+    unsigned int* counter;         // grid barrier, zeroed before launch
+};
+
+__device__ __forceinline__ void grid_barrier(unsigned int* counter, unsigned int target) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        atomicAdd(counter, 1u);
+        while (*((volatile unsigned int*)counter) < target) {
+        }
+        __threadfence();
+    }
+    __syncthreads();
+}
+
+// candidate ordering of icamax: larger value wins; on equal values the lower row wins.
+__device__ __forceinline__ bool cand_better(double v1, int r1, double v2, int r2) {
+    return (v1 > v2) || (v1 == v2 && r1 < r2);
+}
+
+__global__ void __launch_bounds__(256, 1) getf2_coop_kernel(const Getf2Params p) {
+    extern __shared__ double sm[];
+    const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, warp = tid >> 5;
+    const int G = gridDim.x, cta = blockIdx.x;
+    const int w = p.w, rp = p.rp;
+    const int r_begin = cta * rp;
+    const int nrows = max(0, min(rp, p.m - r_begin));
+    double* s = sm;                        // [w][rp] column-major chunk
+    double* prow = sm + (size_t)w * rp;    // [w] pivot row
+    double* crow = prow + w;               // [w] old row c
+    __shared__ double red_v[8];
+    __shared__ int red_r[8], red_w[8];
+    __shared__ double s_gval;
+    __shared__ int s_grow, s_gcta, s_lrow;
+
+    // load this CTA's rows
+    for (int c = 0; c < w; ++c)
+        for (int r = tid; r < nrows; r += nt) s[r + c * rp] = p.a[(long long)(r_begin + r) + (long long)c * p.lda];
+    __syncthreads();
+
+    const int slot_stride = w + 2;
+    for (int c = 0; c < w && c < p.m; ++c) {
+        const int par = c & 1;
+        // ---- 1. local candidate over rows with global index >= c ----
+        double bv = -1.0; int br = 0x7fffffff;
+        for (int r = tid; r < nrows; r += nt) {
+            const int gr = r_begin + r;
+            if (gr < c) continue;
+            double v = fabs(s[r + c * rp]);
+            if (v != v) v = (gr == c) ? __longlong_as_double(0x7ff0000000000000LL) : -1.0;   // NaN: wins only at index 0
+            if (cand_better(v, gr, bv, br)) { bv = v; br = gr; }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const double ov = __shfl_xor_sync(0xffffffffu, bv, o);
+            const int orow = __shfl_xor_sync(0xffffffffu, br, o);
+            if (cand_better(ov, orow, bv, br)) { bv = ov; br = orow; }
+        }
+        if (lane == 0) { red_v[warp] = bv; red_r[warp] = br; }
+        __syncthreads();
+        if (tid == 0) {
+            for (int i = 1; i < nt / 32; ++i)
+                if (cand_better(red_v[i], red_r[i], bv, br)) { bv = red_v[i]; br = red_r[i]; }
+            double* slot = p.slots + ((size_t)par * G + cta) * slot_stride;
+            slot[0] = bv;
+            slot[1] = (double)br;
+            s_lrow = br;
+        }
+        __syncthreads();
+        {
+            const int lr = s_lrow;
+            double* slot = p.slots + ((size_t)par * G + cta) * slot_stride;
+            if (lr != 0x7fffffff)
+                for (int cc = tid; cc < w; cc += nt) slot[2 + cc] = s[(lr - r_begin) + cc * rp];
+            if (c >= r_begin && c < r_begin + nrows)
+                for (int cc = tid; cc < w; cc += nt) p.rowc[par * w + cc] = s[(c - r_begin) + cc * rp];
+        }
+        // ---- 2. grid barrier ----
+        grid_barrier(p.counter, (unsigned int)(c + 1) * (unsigned int)G);
+        // ---- 3. every CTA reduces the G candidates identically ----
+        {
+            double v = -2.0; int r = 0x7fffffff, who = -1;
+            for (int i = tid; i < G; i += nt) {
+                const volatile double* slot = p.slots + ((size_t)par * G + i) * slot_stride;
+                const double sv = slot[0]; const int sr = (int)slot[1];
+                if (cand_better(sv, sr, v, r)) { v = sv; r = sr; who = i; }
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                const double ov = __shfl_xor_sync(0xffffffffu, v, o);
+                const int orow = __shfl_xor_sync(0xffffffffu, r, o);
+                const int ow = __shfl_xor_sync(0xffffffffu, who, o);
+                if (cand_better(ov, orow, v, r)) { v = ov; r = orow; who = ow; }
+            }
+            __syncthreads();   // red_* reuse
+            if (lane == 0) { red_v[warp] = v; red_r[warp] = r; red_w[warp] = who; }
+            __syncthreads();
+            if (tid == 0) {
+                for (int i = 1; i < nt / 32; ++i)
+                    if (cand_better(red_v[i], red_r[i], v, r)) { v = red_v[i]; r = red_r[i]; who = red_w[i]; }
+                s_gval = v; s_grow = r; s_gcta = who;
+            }
+            __syncthreads();
+        }
+        const int grow = s_grow, gcta = s_gcta;
+        {
+            const volatile double* wslot = p.slots + ((size_t)par * G + gcta) * slot_stride;
+            for (int cc = tid; cc < w; cc += nt) {
+                prow[cc] = wslot[2 + cc];
+                crow[cc] = ((const volatile double*)p.rowc)[par * w + cc];
+            }
+        }
+        __syncthreads();
+        const double pivot = prow[c];
+        if (cta == 0 && tid == 0) p.ipiv[p.j0 + c] = p.j0 + ((pivot == 0.0) ? c : grow);
+        if (pivot == 0.0) continue;                      // lu.rs:107-110: nothing to eliminate (uniform across CTAs)
+        // ---- 4. swap rows c <-> grow inside shared memory ----
+        if (grow != c) {
+            if (grow >= r_begin && grow < r_begin + nrows)
+                for (int cc = tid; cc < w; cc += nt) s[(grow - r_begin) + cc * rp] = crow[cc];
+            if (c >= r_begin && c < r_begin + nrows)
+                for (int cc = tid; cc < w; cc += nt) s[(c - r_begin) + cc * rp] = prow[cc];
+            __syncthreads();
+        }
+        // ---- 5. scale by the reciprocal pivot and rank-1 update (unfused mul/add like the reference) ----
+        const double inv = 1.0 / pivot;
+        for (int r = tid; r < nrows; r += nt) {
+            const int gr = r_begin + r;
+            if (gr <= c) continue;
+            const double l = __dmul_rn(s[r + c * rp], inv);
+            s[r + c * rp] = l;
+            for (int cc = c + 1; cc < w; ++cc)
+                s[r + cc * rp] = __dadd_rn(__dmul_rn(-prow[cc], l), s[r + cc * rp]);
+        }
+        __syncthreads();
+    }
+    // write back
+    for (int c = 0; c < w; ++c)
+        for (int r = tid; r < nrows; r += nt) p.a[(long long)(r_begin + r) + (long long)c * p.lda] = s[r + c * rp];
+}
+
+// Factors the m x w panel at A[j0.., j0..j0+w).  ws: device workspace from getf2_workspace_bytes().
+size_t getf2_workspace_bytes() { return (2 * 160 * (kLuPanel + 2) + 2 * kLuPanel) * sizeof(double) + 256; }
+
+int getf2_panel(cudaStream_t st, double* a_panel, size_t lda, size_t m, size_t w, size_t j0, int* ipiv, void* ws) {
+    if (m == 0 || w == 0) return NA_OK;
+    if (w > (size_t)kLuPanel) { set_error("getf2: panel too wide"); return NA_EINVAL; }
+    const int sms = ctx().sm_count;
+    const size_t smem_budget = 200 * 1024;
+    // rows per CTA: as few CTAs as fit (fewer barrier participants), but at least 64 rows each
+    size_t rp_max = (smem_budget - 2 * w * 8) / (w * 8);
+    rp_max = rp_max / 32 * 32;
+    size_t G = ceil_div(m, rp_max);
+    if (G > (size_t)sms) { set_error("getf2: panel of %zu x %zu rows does not fit %d SMs of shared memory", m, w, sms); return NA_EINVAL; }
+    // spread rows evenly over G CTAs, but use more CTAs (up to 64) when rows are plentiful
+    size_t G_pref = std::min<size_t>(std::min<size_t>(64, (size_t)sms), ceil_div(m, (size_t)128));
+    if (G_pref > G) G = G_pref;
+    size_t rp = round_up(ceil_div(m, G), 32);
+    G = ceil_div(m, rp);
+    const size_t smem = ((size_t)w * rp + 2 * w) * sizeof(double);
+    static std::once_flag once;
+    std::call_once(once, [] { cudaFuncSetAttribute(getf2_coop_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024); });
+    Getf2Params p;
+    p.a = a_panel; p.lda = (long long)lda; p.m = (int)m; p.w = (int)w; p.rp = (int)rp; p.j0 = (int)j0; p.ipiv = ipiv;
+    char* wsp = static_cast<char*>(ws);
+    p.counter = reinterpret_cast<unsigned int*>(wsp);
+    p.slots = reinterpret_cast<double*>(wsp + 256);
+    p.rowc = p.slots + 2 * 160 * (kLuPanel + 2);
+    NAB_CUDA(cudaMemsetAsync(p.counter, 0, sizeof(unsigned int), st));
+    void* args[] = {(void*)&p};
+    NAB_CUDA(cudaLaunchCooperativeKernel((void*)getf2_coop_kernel, dim3((unsigned)G), dim3(256), args, smem, st));
+    count_launch();
+    return NA_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// swap sequence -> permutation.  Applies swaps (a_s, b_s), s = 0..K-1, to the identity arrangement
+// of rows [0, n) and emits the touched rows: dest[i] <- src[i] means "row dest[i] of the result is
+// row src[i] of the input".  One CTA; the arrangement lives in shared memory (int32, n <= 51200)
+// or in a global scratch array for taller matrices.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(1024, 1)
+perm_from_swaps_kernel(const int* __restrict__ sa, const int* __restrict__ sb, int K, int sa_stride, int n,
+                       int* __restrict__ gperm, int use_global, int* __restrict__ dest, int* __restrict__ src, int* __restrict__ count) {
+    extern __shared__ int sperm[];
+    int* perm = use_global ? gperm : sperm;
+    const int tid = threadIdx.x, nt = blockDim.x;
+    for (int r = tid; r < n; r += nt) perm[r] = r;
+    __shared__ int s_count;
+    if (tid == 0) s_count = 0;
+    __syncthreads();
+    if (tid == 0) {
+        for (int s = 0; s < K; ++s) {
+            const int x = sa[(size_t)s * sa_stride], y = sb[(size_t)s * sa_stride];
+            if (x != y) { const int t = perm[x]; perm[x] = perm[y]; perm[y] = t; }
+        }
+    }
+    __syncthreads();
+    // compact the touched rows (order irrelevant)
+    for (int r = tid; r < n; r += nt) {
+        const int v = perm[r];
+        if (v != r) { const int i = atomicAdd(&s_count, 1); dest[i] = r; src[i] = v; }
+    }
+    __syncthreads();
+    if (tid == 0) *count = s_count;
+}
+
+// rows of columns [0, ncols): out-of-place gather through shared memory, one CTA per column.
+__global__ void __launch_bounds__(256)
+permute_rows_kernel(double* __restrict__ a, long long lda, const int* __restrict__ dest, const int* __restrict__ src,
+                    const int* __restrict__ count, int max_stage) {
+    extern __shared__ double stage[];
+    const int np = min(*count, max_stage);   // np <= max_stage is guaranteed by the host
+    double* acol = a + (long long)blockIdx.x * lda;
+    for (int i = threadIdx.x; i < np; i += blockDim.x) stage[i] = acol[src[i]];
+    __syncthreads();
+    for (int i = threadIdx.x; i < np; i += blockDim.x) acol[dest[i]] = stage[i];
+}
+
+// Variant for very long permutations: stage through global memory (tmp: np x ncols).
+__global__ void permute_rows_gather_kernel(const double* __restrict__ a, long long lda, const int* __restrict__ src,
+                                           const int* __restrict__ count, double* __restrict__ tmp, long long ldt, long long ncols) {
+    const int np = *count;
+    const long long total = (long long)np * ncols;
+    for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+        const long long i = idx % np, col = idx / np;
+        tmp[i + col * ldt] = a[src[i] + col * lda];
+    }
+}
+__global__ void permute_rows_scatter_kernel(double* __restrict__ a, long long lda, const int* __restrict__ dest,
+                                            const int* __restrict__ count, const double* __restrict__ tmp, long long ldt, long long ncols) {
+    const int np = *count;
+    const long long total = (long long)np * ncols;
+    for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+        const long long i = idx % np, col = idx / np;
+        a[dest[i] + col * lda] = tmp[i + col * ldt];
+    }
+}
+
+// RowPerm workspace: dest[n], src[n], count, (gperm[n] when n is large)
+size_t rowperm_workspace_bytes(size_t n) { return (3 * n + 64) * sizeof(int); }
+
+// Builds the permutation equivalent to the swap sequence (sa[s*stride], sb[s*stride]), s < K, over rows [0, n).
+int rowperm_build(cudaStream_t st, const int* sa, const int* sb, size_t K, size_t stride, size_t n, void* ws) {
+    int* w = static_cast<int*>(ws);
+    int* count = w; int* dest = w + 64; int* src = dest + n; int* gperm = src + n;
+    const bool use_global = n * sizeof(int) > 200 * 1024;
+    const size_t smem = use_global ? 0 : n * sizeof(int);
+    static std::once_flag once;
+    std::call_once(once, [] { cudaFuncSetAttribute(perm_from_swaps_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); });
+    perm_from_swaps_kernel<<<1, 1024, smem, st>>>(sa, sb, (int)K, (int)stride, (int)n, gperm, use_global ? 1 : 0, dest, src, count);
+    NAB_LAUNCH_CHECK();
+    return NA_OK;
+}
+
+// Applies a built permutation to columns [0, ncols) of `a` (n rows).  max_touched bounds *count.
+int rowperm_apply(cudaStream_t st, double* a, size_t lda, size_t ncols, size_t max_touched, const void* ws, size_t n) {
+    if (ncols == 0 || max_touched == 0) return NA_OK;
+    const int* w = static_cast<const int*>(ws);
+    const int* count = w; const int* dest = w + 64; const int* src = dest + n;
+    const size_t stage_bytes = max_touched * sizeof(double);
+    if (stage_bytes <= 200 * 1024) {
+        static std::once_flag once;
+        std::call_once(once, [] { cudaFuncSetAttribute(permute_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); });
+        // one CTA per column; gridDim.x limited to 2^31-1
+        permute_rows_kernel<<<(unsigned)ncols, 256, stage_bytes, st>>>(a, (long long)lda, dest, src, count, (int)max_touched);
+        NAB_LAUNCH_CHECK();
+        return NA_OK;
+    }
+    // global staging, in column chunks of <= 64 MiB
+    const size_t chunk = std::max<size_t>(1, (64ull << 20) / stage_bytes);
+    Scratch tmp;
+    NAB_TRY(tmp.alloc(std::min(chunk, ncols) * stage_bytes, st));
+    for (size_t c0 = 0; c0 < ncols; c0 += chunk) {
+        const size_t nc = std::min(chunk, ncols - c0);
+        const int blocks = ctx().sm_count * 8;
+        permute_rows_gather_kernel<<<blocks, 256, 0, st>>>(a + c0 * lda, (long long)lda, src, count, tmp.as<double>(), (long long)max_touched, (long long)nc);
+        NAB_LAUNCH_CHECK();
+        permute_rows_scatter_kernel<<<blocks, 256, 0, st>>>(a + c0 * lda, (long long)lda, dest, count, tmp.as<double>(), (long long)max_touched, (long long)nc);
+        NAB_LAUNCH_CHECK();
+    }
+    return NA_OK;
+}
+
+// ipiv (int, device) helpers -------------------------------------------------------------------
+__global__ void iota_kernel(int* p, int n, int offset) {
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) p[i] = i + offset;
+}
+int iota_int(cudaStream_t st, int* p, size_t n, int offset) {
+    if (n == 0) return NA_OK;
+    iota_kernel<<<(int)std::min<size_t>(ceil_div(n, 256), 1024), 256, 0, st>>>(p, (int)n, offset);
+    NAB_LAUNCH_CHECK();
+    return NA_OK;
+}
+
+}  // namespace nab

@@ -1,0 +1,434 @@
+"""Host-side mirror of nalgebra's interface for the hot path, over the C ABI.
+
+The reference is Rust and this image has no Rust toolchain, so the host side above the C ABI is
+mirrored here (and in ``nalgebra_b200/host/nalgebra_b200.hpp`` for C++ callers; the Rust crate a
+maintainer would add is shown in INTEGRATION.md).  Names, argument meaning and error behaviour
+follow the reference:
+
+* ``gemm(alpha, a, b, beta, c)``      -- ``Matrix::gemm``      src/base/blas.rs:729-746
+* ``gemm_tr`` / ``mul_to`` / ``mul``  -- blas.rs:770-803, ops.rs:783-795, ops.rs:554-574
+* ``Cholesky``                        -- src/linalg/cholesky.rs
+* ``LU`` + ``PermutationSequence``    -- src/linalg/lu.rs, permutation_sequence.rs
+* ``QR``                              -- src/linalg/qr.rs
+
+A ``DMatrix<f64>`` is a numpy float64 array (any strides; ``VecStorage`` = Fortran order).  Shape
+errors raise ``ValueError`` (the reference panics); numerical failure is a value (``None`` /
+``False``) exactly like the reference.  All arithmetic happens in libnalgebra_b200.so on the GPU --
+there is no CPU fallback; only O(n^2) accessors (``l()``, ``u()``, ``r()``, determinants) are host
+code, as they are plain loops in the reference too.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _capi
+from ._capi import NA_NOT_PD, NA_OK, NA_SINGULAR, check
+
+
+def _strides(a: np.ndarray):
+    it = a.itemsize
+    if a.ndim == 1:
+        return a.strides[0] // it, 0
+    return a.strides[0] // it, a.strides[1] // it
+
+
+def _as_matrix(a, dtype=np.float64) -> np.ndarray:
+    a = np.asarray(a, dtype=dtype)
+    if a.ndim == 1:
+        a = a.reshape(-1, 1)
+    if a.ndim != 2:
+        raise ValueError("expected a matrix")
+    return a
+
+
+def _owned(a) -> np.ndarray:
+    """``clone_owned``: a column-major copy (VecStorage layout)."""
+    return np.array(a, dtype=np.float64, order="F", copy=True, ndmin=2)
+
+
+def kernel_launches() -> int:
+    return int(_capi.lib().na_kernel_launches())
+
+
+# ---------------------------------------------------------------------------------------------
+# GEMM family
+# ---------------------------------------------------------------------------------------------
+def gemm(alpha: float, a, b, beta: float, c: np.ndarray) -> np.ndarray:
+    """``c.gemm(alpha, &a, &b, beta)``: c <- alpha*a*b + beta*c in place; c is not read when
+    beta == 0.  Views with arbitrary strides are accepted, like the reference."""
+    a = _as_matrix(a); b = _as_matrix(b)
+    if not isinstance(c, np.ndarray) or c.dtype != np.float64 or c.ndim != 2 or not c.flags.writeable:
+        raise ValueError("c must be a writable float64 matrix")
+    (m, k), (k2, n) = a.shape, b.shape
+    if k != k2:
+        raise ValueError("gemm: dimensions mismatch for multiplication.")      # blas_uninit.rs:244-247
+    if c.shape != (m, n):
+        raise ValueError("gemm: dimensions mismatch for addition.")            # blas_uninit.rs:248-252
+    rsa, csa = _strides(a); rsb, csb = _strides(b); rsc, csc = _strides(c)
+    check(_capi.lib().na_dgemm(m, k, n, float(alpha), a.ctypes.data, rsa, csa, b.ctypes.data, rsb, csb,
+                               float(beta), c.ctypes.data, rsc, csc))
+    return c
+
+
+def gemm_tr(alpha: float, a, b, beta: float, c: np.ndarray) -> np.ndarray:
+    """``c.gemm_tr(alpha, &a, &b, beta)``: c <- alpha*a^T*b + beta*c (blas.rs:770-803)."""
+    a = _as_matrix(a)
+    if a.shape[0] != _as_matrix(b).shape[0]:
+        raise ValueError("gemm: dimensions mismatch for multiplication.")
+    return gemm(alpha, a.T, b, beta, c)
+
+
+def mul_to(a, b, out: np.ndarray) -> np.ndarray:
+    """``a.mul_to(&b, &mut out)`` = ``out.gemm(1, a, b, 0)`` (ops.rs:783-795)."""
+    return gemm(1.0, a, b, 0.0, out)
+
+
+def mul(a, b) -> np.ndarray:
+    """``&a * &b``: allocates an uninitialised result and calls gemm with beta = 0 (ops.rs:554-574)."""
+    a = _as_matrix(a); b = _as_matrix(b)
+    if a.shape[1] != b.shape[0]:
+        raise ValueError("Matrix multiplication dimensions mismatch")
+    out = np.empty((a.shape[0], b.shape[1]), dtype=np.float64, order="F")
+    return gemm(1.0, a, b, 0.0, out)
+
+
+def tr_mul(a, b) -> np.ndarray:
+    """``a.tr_mul(&b)`` = a^T * b (ops.rs:674-779): same kernel with A's strides swapped."""
+    a = _as_matrix(a); b = _as_matrix(b)
+    if a.shape[0] != b.shape[0]:
+        raise ValueError("Matrix multiplication dimensions mismatch")
+    out = np.empty((a.shape[1], b.shape[1]), dtype=np.float64, order="F")
+    return gemm(1.0, a.T, b, 0.0, out)
+
+
+def gemm_f32(alpha: float, a, b, beta: float, c: np.ndarray) -> np.ndarray:
+    """f32 twin (matrixmultiply::sgemm, blas_uninit.rs:276-291)."""
+    a = _as_matrix(a, np.float32); b = _as_matrix(b, np.float32)
+    (m, k), (k2, n) = a.shape, b.shape
+    if k != k2 or c.shape != (m, n) or c.dtype != np.float32:
+        raise ValueError("gemm: dimensions mismatch")
+    rsa, csa = _strides(a); rsb, csb = _strides(b); rsc, csc = _strides(c)
+    check(_capi.lib().na_sgemm(m, k, n, float(alpha), a.ctypes.data, rsa, csa, b.ctypes.data, rsb, csb,
+                               float(beta), c.ctypes.data, rsc, csc))
+    return c
+
+
+# ---------------------------------------------------------------------------------------------
+# PermutationSequence  (src/linalg/permutation_sequence.rs)
+# ---------------------------------------------------------------------------------------------
+class PermutationSequence:
+    """``{len, ipiv}``: the non-trivial row interchanges (i, i2) in application order."""
+
+    def __init__(self, ipiv: np.ndarray, capacity: int):
+        self.ipiv = np.ascontiguousarray(ipiv, dtype=np.uint64).reshape(-1, 2)
+        self.capacity = capacity
+
+    @classmethod
+    def identity(cls, n: int) -> "PermutationSequence":
+        return cls(np.zeros((0, 2), dtype=np.uint64), n)
+
+    def __len__(self) -> int:
+        return self.ipiv.shape[0]
+
+    def is_empty(self) -> bool:
+        return len(self) == 0
+
+    def append_permutation(self, i: int, i2: int) -> None:           # :84-93
+        if i != i2:
+            if len(self) >= self.capacity:
+                raise ValueError("Maximum number of permutations exceeded.")
+            self.ipiv = np.vstack([self.ipiv, np.array([[i, i2]], dtype=np.uint64)])
+
+    def permute_rows(self, rhs: np.ndarray) -> None:                  # :97-104
+        for i, i2 in self.ipiv:
+            rhs[[int(i), int(i2)]] = rhs[[int(i2), int(i)]]
+
+    def inv_permute_rows(self, rhs: np.ndarray) -> None:              # :108-116
+        for i, i2 in self.ipiv[::-1]:
+            rhs[[int(i), int(i2)]] = rhs[[int(i2), int(i)]]
+
+    def permute_columns(self, rhs: np.ndarray) -> None:
+        for i, i2 in self.ipiv:
+            rhs[:, [int(i), int(i2)]] = rhs[:, [int(i2), int(i)]]
+
+    def inv_permute_columns(self, rhs: np.ndarray) -> None:
+        for i, i2 in self.ipiv[::-1]:
+            rhs[:, [int(i), int(i2)]] = rhs[:, [int(i2), int(i)]]
+
+    def determinant(self) -> float:                                   # :158-164
+        return 1.0 if len(self) % 2 == 0 else -1.0
+
+
+# ---------------------------------------------------------------------------------------------
+# Cholesky  (src/linalg/cholesky.rs)
+# ---------------------------------------------------------------------------------------------
+class Cholesky:
+    """``Cholesky{chol}``: L in the lower triangle (incl. diagonal) of ``chol``; the strict upper
+    triangle is the caller's original data, never read nor written."""
+
+    def __init__(self, chol: np.ndarray):
+        self.chol = chol
+
+    @classmethod
+    def new(cls, matrix) -> "Cholesky | None":                        # :196-198
+        return cls._new_internal(matrix, None)
+
+    @classmethod
+    def new_with_substitute(cls, matrix, substitute: float) -> "Cholesky | None":   # :217-219
+        return cls._new_internal(matrix, substitute)
+
+    @classmethod
+    def _new_internal(cls, matrix, substitute):
+        m = _owned(matrix)
+        if m.shape[0] != m.shape[1]:
+            raise ValueError("The input matrix must be square.")      # :222
+        n = m.shape[0]
+        fail = C.c_size_t(0)
+        st = check(_capi.lib().na_cholesky_f64(n, m.ctypes.data, max(n, 1), 0 if substitute is None else 1,
+                                               0.0 if substitute is None else float(substitute), C.addressof(fail)))
+        if st == NA_NOT_PD:
+            return None
+        return cls(m)
+
+    @classmethod
+    def pack_dirty(cls, matrix) -> "Cholesky":
+        return cls(_owned(matrix))
+
+    def unpack(self) -> np.ndarray:                                   # :88-91
+        return np.asfortranarray(np.tril(self.chol))
+
+    def unpack_dirty(self) -> np.ndarray:
+        return self.chol
+
+    def l(self) -> np.ndarray:                                        # :104-106
+        return np.asfortranarray(np.tril(self.chol))
+
+    def l_dirty(self) -> np.ndarray:
+        return self.chol
+
+    def solve_mut(self, b: np.ndarray) -> None:                       # :122-129
+        n = self.chol.shape[0]
+        if b.shape[0] != n:
+            raise ValueError("Cholesky solve matrix dimension mismatch.")
+        x = _owned(b)
+        check(_capi.lib().na_cholesky_solve_f64(n, self.chol.ctypes.data, max(n, 1), x.ctypes.data, max(n, 1), x.shape[1]))
+        b[...] = x.reshape(b.shape, order="F")
+
+    def solve(self, b) -> np.ndarray:                                 # :134-143
+        res = np.array(b, dtype=np.float64, order="F", copy=True)
+        self.solve_mut(res)
+        return res
+
+    def inverse(self) -> np.ndarray:                                  # :147-153
+        res = np.asfortranarray(np.eye(self.chol.shape[0]))
+        self.solve_mut(res)
+        return res
+
+    def determinant(self) -> float:                                   # :157-164
+        prod = 1.0
+        for d in np.diag(self.chol):
+            prod *= d
+        return prod * prod
+
+    def ln_determinant(self) -> float:                                # :172-185
+        return float(sum(np.log(d * d) for d in np.diag(self.chol)))
+
+
+# ---------------------------------------------------------------------------------------------
+# LU  (src/linalg/lu.rs)
+# ---------------------------------------------------------------------------------------------
+class LU:
+    """``LU{lu, p}``: packed factors (strict lower = L multipliers, upper incl. diagonal = U) and the
+    row PermutationSequence."""
+
+    def __init__(self, lu: np.ndarray, p: PermutationSequence):
+        self.lu, self._p = lu, p
+
+    @classmethod
+    def new(cls, matrix) -> "LU":                                     # :93-122
+        m = _owned(matrix)
+        nrows, ncols = m.shape
+        mn = min(nrows, ncols)
+        swaps = np.zeros(2 * max(mn, 1), dtype=np.uint64)
+        ns = C.c_size_t(0)
+        check(_capi.lib().na_lu_f64(nrows, ncols, m.ctypes.data, max(nrows, 1), swaps.ctypes.data, C.addressof(ns)))
+        return cls(m, PermutationSequence(swaps[: 2 * ns.value].copy(), mn))
+
+    def lu_internal(self) -> np.ndarray:
+        return self.lu
+
+    def l(self) -> np.ndarray:                                        # :132-141
+        m, n = self.lu.shape
+        mn = min(m, n)
+        return np.asfortranarray(np.tril(self.lu[:, :mn], -1) + np.eye(m, mn))
+
+    def u(self) -> np.ndarray:                                        # :176-182
+        m, n = self.lu.shape
+        return np.asfortranarray(np.triu(self.lu[: min(m, n), :]))
+
+    def p(self) -> PermutationSequence:                               # :186-188
+        return self._p
+
+    def unpack(self):                                                 # :192-210
+        return self._p, self.l(), self.u()
+
+    def solve_mut(self, b: np.ndarray) -> bool:                       # :242-260
+        n = self.lu.shape[0]
+        if b.shape[0] != n:
+            raise ValueError("LU solve matrix dimension mismatch.")
+        if self.lu.shape[0] != self.lu.shape[1]:
+            raise ValueError("LU solve: unable to solve a non-square system.")
+        x = _owned(b)
+        sw = np.ascontiguousarray(self._p.ipiv.reshape(-1))
+        st = check(_capi.lib().na_lu_solve_f64(n, self.lu.ctypes.data, max(n, 1), sw.ctypes.data, len(self._p),
+                                               x.ctypes.data, max(n, 1), x.shape[1]))
+        b[...] = x.reshape(b.shape, order="F")
+        return st != NA_SINGULAR
+
+    def solve(self, b):                                               # :221-236
+        res = np.array(b, dtype=np.float64, order="F", copy=True)
+        return res if self.solve_mut(res) else None
+
+    def try_inverse(self):                                            # :266-280
+        if self.lu.shape[0] != self.lu.shape[1]:
+            raise ValueError("LU inverse: unable to compute the inverse of a non-square matrix.")
+        res = np.asfortranarray(np.eye(self.lu.shape[0]))
+        return res if self.solve_mut(res) else None
+
+    def determinant(self) -> float:                                   # :301-314
+        if self.lu.shape[0] != self.lu.shape[1]:
+            raise ValueError("LU determinant: unable to compute the determinant of a non-square matrix.")
+        res = 1.0
+        for d in np.diag(self.lu):
+            res *= d
+        return res * self._p.determinant()
+
+    def is_invertible(self) -> bool:                                  # :318-331
+        if self.lu.shape[0] != self.lu.shape[1]:
+            raise ValueError("LU: unable to test the invertibility of a non-square matrix.")
+        return bool(np.all(np.diag(self.lu) != 0.0))
+
+
+# ---------------------------------------------------------------------------------------------
+# QR  (src/linalg/qr.rs)
+# ---------------------------------------------------------------------------------------------
+class QR:
+    """``QR{qr, diag}`` in nalgebra's storage: column i, rows i.. = unit Householder axis; strict
+    upper = R off-diagonal; R[i,i] = |diag[i]|."""
+
+    def __init__(self, qr: np.ndarray, diag: np.ndarray):
+        self.qr, self.diag = qr, diag
+
+    @classmethod
+    def new(cls, matrix) -> "QR":                                     # :55-76
+        m = _owned(matrix)
+        nrows, ncols = m.shape
+        mn = min(nrows, ncols)
+        diag = np.zeros(max(mn, 1))
+        check(_capi.lib().na_qr_f64(nrows, ncols, m.ctypes.data, max(nrows, 1), diag.ctypes.data))
+        return cls(m, diag[:mn].copy())
+
+    def qr_internal(self) -> np.ndarray:
+        return self.qr
+
+    def diag_internal(self) -> np.ndarray:
+        return self.diag
+
+    def r(self) -> np.ndarray:                                        # :81-89
+        m, n = self.qr.shape
+        mn = min(m, n)
+        res = np.triu(self.qr[:mn, :])
+        res[np.arange(mn), np.arange(mn)] = np.abs(self.diag)
+        return np.asfortranarray(res)
+
+    unpack_r = r
+
+    def q(self) -> np.ndarray:                                        # :108-129
+        m, n = self.qr.shape
+        mn = min(m, n)
+        q = np.zeros((m, max(mn, 1)), order="F")
+        check(_capi.lib().na_qr_q_f64(m, n, self.qr.ctypes.data, max(m, 1), np.ascontiguousarray(self.diag).ctypes.data,
+                                      q.ctypes.data, max(m, 1)))
+        return q[:, :mn]
+
+    def unpack(self):
+        return self.q(), self.r()
+
+    def q_tr_mul(self, rhs: np.ndarray) -> None:                      # :157-171
+        m, n = self.qr.shape
+        if rhs.shape[0] != m:
+            raise ValueError("q_tr_mul: dimension mismatch")
+        x = _owned(rhs)
+        check(_capi.lib().na_qr_q_tr_mul_f64(m, n, self.qr.ctypes.data, max(m, 1), np.ascontiguousarray(self.diag).ctypes.data,
+                                             x.ctypes.data, max(m, 1), x.shape[1]))
+        rhs[...] = x.reshape(rhs.shape, order="F")
+
+    def solve_mut(self, b: np.ndarray) -> bool:                       # :204-221
+        n = self.qr.shape[0]
+        if b.shape[0] != n:
+            raise ValueError("QR solve matrix dimension mismatch.")
+        if self.qr.shape[0] != self.qr.shape[1]:
+            raise ValueError("QR solve: unable to solve a non-square system.")
+        x = _owned(b)
+        st = check(_capi.lib().na_qr_solve_f64(n, self.qr.ctypes.data, max(n, 1), np.ascontiguousarray(self.diag).ctypes.data,
+                                               x.ctypes.data, max(n, 1), x.shape[1]))
+        b[...] = x.reshape(b.shape, order="F")
+        return st != NA_SINGULAR
+
+    def solve(self, b):                                               # :186-200
+        res = np.array(b, dtype=np.float64, order="F", copy=True)
+        return res if self.solve_mut(res) else None
+
+    def try_inverse(self):                                            # :262-277
+        if self.qr.shape[0] != self.qr.shape[1]:
+            raise ValueError("QR inverse: unable to compute the inverse of a non-square matrix.")
+        res = np.asfortranarray(np.eye(self.qr.shape[0]))
+        return res if self.solve_mut(res) else None
+
+    def is_invertible(self) -> bool:                                  # :281-294
+        if self.qr.shape[0] != self.qr.shape[1]:
+            raise ValueError("QR: unable to test the invertibility of a non-square matrix.")
+        return bool(np.all(self.diag != 0.0))
+
+
+# ---------------------------------------------------------------------------------------------
+# triangular solves  (src/linalg/solve.rs)
+# ---------------------------------------------------------------------------------------------
+def _tri_solve(t, b, lower: bool, trans: bool, unit: bool):
+    t = _owned(t)
+    n = t.shape[0]
+    x = _owned(b)
+    if x.shape[0] != n:
+        raise ValueError("triangular solve: dimension mismatch")
+    st = check(_capi.lib().na_tri_solve_f64(int(lower), int(trans), int(unit), n, t.ctypes.data, max(n, 1),
+                                            x.ctypes.data, max(n, 1), x.shape[1]))
+    if st == NA_SINGULAR:
+        return None
+    return x.reshape(np.shape(b), order="F")
+
+
+def solve_lower_triangular(t, b):
+    return _tri_solve(t, b, True, False, False)
+
+
+def solve_upper_triangular(t, b):
+    return _tri_solve(t, b, False, False, False)
+
+
+def tr_solve_lower_triangular(t, b):
+    return _tri_solve(t, b, True, True, False)
+
+
+def tr_solve_upper_triangular(t, b):
+    return _tri_solve(t, b, False, True, False)
+
+
+def solve_lower_triangular_with_diag(t, b, diag: float):
+    """solve.rs:106-133 with the implicit diagonal `diag` (the reference's LU uses diag = 1)."""
+    if diag == 0.0:
+        return None
+    if diag != 1.0:
+        raise NotImplementedError("only the unit diagonal the reference's LU uses is accelerated")
+    return _tri_solve(t, b, True, False, True)
