@@ -123,6 +123,9 @@ struct GemmParams {
     double* C;
     double alpha, beta;
     int lower_only;   // 1: SYRK-shaped, only tiles touching the lower triangle; store row >= col only
+    int splits;       // split-K: work item = (tile, split); each split writes its raw partial sums to
+    int kb_per_split; //   C + split*split_stride (alpha = 1, beta = 0); splitk_reduce_kernel finishes the job
+    long long split_stride;
 };
 
 // lower_only (SYRK-shaped, square C, BM == BN): t enumerates the lower-triangular tiles row by row.
@@ -177,8 +180,10 @@ dgemm_tma_dmma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
             uint32_t phase = 0;
             for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
                 int tm, tn;
-                if (p.lower_only) tile_coords_lower(t, tm, tn); else tile_coords(t, p.tiles_m, p.tiles_n, tm, tn);
-                for (int kb = 0; kb < kblocks; ++kb) {
+                const int tile = t / p.splits, split = t - tile * p.splits;
+                if (p.lower_only) tile_coords_lower(tile, tm, tn); else tile_coords(tile, p.tiles_m, p.tiles_n, tm, tn);
+                const int kb0 = split * p.kb_per_split, kb1 = min(kblocks, kb0 + p.kb_per_split);
+                for (int kb = kb0; kb < kb1; ++kb) {
                     ptx::mbar_wait(bar_base + 8 * (STAGES + stage), phase ^ 1);
                     const uint32_t full = bar_base + 8 * stage;
                     const uint32_t sa = smem_base + stage * STAGE_BYTES, sb = sa + A_BYTES;
@@ -217,7 +222,9 @@ dgemm_tma_dmma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
     uint32_t phase = 0;
     for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
         int tm, tn;
-        if (p.lower_only) tile_coords_lower(t, tm, tn); else tile_coords(t, p.tiles_m, p.tiles_n, tm, tn);
+        const int tile = t / p.splits, split = t - tile * p.splits;
+        if (p.lower_only) tile_coords_lower(tile, tm, tn); else tile_coords(tile, p.tiles_m, p.tiles_n, tm, tn);
+        const int kb0 = split * p.kb_per_split, kb1 = min(kblocks, kb0 + p.kb_per_split);
 
         double acc[MT][NT][2];
 #pragma unroll
@@ -225,7 +232,7 @@ dgemm_tma_dmma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
 #pragma unroll
             for (int j = 0; j < NT; ++j) { acc[i][j][0] = 0.0; acc[i][j][1] = 0.0; }
 
-        for (int kb = 0; kb < kblocks; ++kb) {
+        for (int kb = kb0; kb < kb1; ++kb) {
             ptx::mbar_wait(bar_base + 8 * stage, phase);
             const uint8_t* sptr = smem_gen + stage * STAGE_BYTES;
 #pragma unroll
@@ -254,7 +261,7 @@ dgemm_tma_dmma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
             for (int e = 0; e < 2; ++e) {
                 const long long col = gn0 + frag_row<B_KMAJOR>(j, 2 * q + e);
                 if (col >= p.N) continue;
-                double* ccol = p.C + col * p.ldc;
+                double* ccol = p.C + (long long)split * p.split_stride + col * p.ldc;
 #pragma unroll
                 for (int i = 0; i < MT; ++i) {
                     const long long row = gm0 + frag_row<A_KMAJOR>(i, g);
@@ -462,6 +469,20 @@ static int launch_gemm(cudaStream_t s, bool a_kmajor, bool b_kmajor, const CUten
     return NA_OK;
 }
 
+// C <- alpha * sum_s ws[s] + beta * C   (split-K epilogue; C not read when beta == 0)
+__global__ void splitk_reduce_kernel(double* __restrict__ c, long long ldc, const double* __restrict__ ws, long long ldw,
+                                     long long split_stride, int splits, long long m, long long n, double alpha, double beta) {
+    const long long total = m * n;
+    for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+        const long long r = idx % m, col = idx / m;
+        double s = 0.0;
+        for (int k = 0; k < splits; ++k) s += ws[k * split_stride + r + col * ldw];
+        double v = alpha * s;
+        if (beta != 0.0) v += beta * c[r + col * ldc];
+        c[r + col * ldc] = v;
+    }
+}
+
 // C(m x n, unit row stride, ldc) <- alpha * A * B + beta * C on device.
 static int gemm_colmajor_c(cudaStream_t s, bool lower_only, size_t m, size_t n, size_t k, double alpha,
                            const Operand& A, const Operand& B, double beta, double* c, size_t ldc) {
@@ -480,12 +501,36 @@ static int gemm_colmajor_c(cudaStream_t s, bool lower_only, size_t m, size_t n, 
     p.M = (int)m; p.N = (int)n; p.K = (int)k;
     p.tiles_m = (int)ceil_div(m, BM); p.tiles_n = (int)ceil_div(n, BN);
     p.ldc = (long long)ldc; p.C = c; p.alpha = alpha; p.beta = beta; p.lower_only = lower_only ? 1 : 0;
+    p.splits = 1; p.kb_per_split = (int)ceil_div(k, BK); p.split_stride = 0;
     if (lower_only) {
         if (m != n) { set_error("gemm: lower_only needs a square C"); return NA_EINVAL; }
         p.num_tiles = (int)((long long)p.tiles_m * (p.tiles_m + 1) / 2);
     } else {
         if ((long long)p.tiles_m * p.tiles_n > 0x7fffffffLL) { set_error("gemm: too many tiles"); return NA_EINVAL; }
         p.num_tiles = p.tiles_m * p.tiles_n;
+        // split-K for few-tile / deep-K shapes (V^T C in the blocked QR, Gram matrices)
+        const int sms = ctx().sm_count;
+        const int kblocks = (int)ceil_div(k, BK);
+        if (p.num_tiles * 2 <= sms && kblocks >= 64) {
+            int splits = std::min(std::min(sms / p.num_tiles, kblocks / 32), 32);
+            if (splits > 1) {
+                const int kbs = (int)ceil_div((size_t)kblocks, (size_t)splits);
+                splits = (int)ceil_div((size_t)kblocks, (size_t)kbs);
+                Scratch ws;
+                const size_t ldw = round_up(m, 2);
+                NAB_TRY(ws.alloc((size_t)splits * ldw * n * sizeof(double), s));
+                GemmParams ps = p;
+                ps.C = ws.as<double>(); ps.ldc = (long long)ldw; ps.alpha = 1.0; ps.beta = 0.0;
+                ps.splits = splits; ps.kb_per_split = kbs; ps.split_stride = (long long)(ldw * n);
+                ps.num_tiles = p.num_tiles * splits;
+                NAB_TRY(launch_gemm(s, a_km, b_km, ma, mb, ps));
+                const int blocks = (int)std::min<size_t>(ceil_div(m * n, 256), (size_t)sms * 8);
+                splitk_reduce_kernel<<<blocks, 256, 0, s>>>(c, (long long)ldc, ws.as<double>(), (long long)ldw, ps.split_stride, splits,
+                                                            (long long)m, (long long)n, alpha, beta);
+                NAB_LAUNCH_CHECK();
+                return NA_OK;
+            }
+        }
     }
     return launch_gemm(s, a_km, b_km, ma, mb, p);
 }

@@ -84,8 +84,7 @@ static int chol_rec(const CholCtx& c, size_t j0, size_t n) {
     if (n == 0) return NA_OK;
     double* ajj = c.a + j0 + j0 * c.lda;
     if (n <= IBs) {
-        NAB_TRY(potf2(c.s, ajj, c.lda, (int)n, c.use_sub, c.sub, j0, c.fail));
-        return trtri_blocks(c.s, ajj, 1, (ptrdiff_t)c.lda, n, true, false, nullptr, c.inv + (j0 / IBs) * IBs * IBs);
+        return potf2(c.s, ajj, c.lda, (int)n, c.use_sub, c.sub, j0, c.fail, c.inv + (j0 / IBs) * IBs * IBs);
     }
     const size_t n1 = round_up(n / 2, IBs), n2 = n - n1;
     NAB_TRY(chol_rec(c, j0, n1));

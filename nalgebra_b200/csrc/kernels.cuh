@@ -23,7 +23,8 @@ int copy_strided(cudaStream_t s, double* dst, ptrdiff_t rsd, ptrdiff_t csd, cons
 
 // ---- panel_chol_tri.cu ---------------------------------------------------------------------------
 constexpr int kInvBlock = 128;     // diagonal-block size of POTF2 / TRTRI / the TRSM base case
-int potf2(cudaStream_t st, double* a, size_t lda, int n, int use_sub, double sub, size_t col0, unsigned long long* fail_col);
+int potf2(cudaStream_t st, double* a, size_t lda, int n, int use_sub, double sub, size_t col0, unsigned long long* fail_col,
+          double* inv_out);
 int trtri_blocks(cudaStream_t st, const double* t, ptrdiff_t rs, ptrdiff_t cs, size_t n, bool eff_lower, bool unit,
                  const double* diag_abs, double* out);
 int zero_diag_check(cudaStream_t st, const double* t, size_t ldt, const double* diag_abs, size_t n, int* flag);
@@ -37,6 +38,17 @@ size_t rowperm_workspace_bytes(size_t n);
 int rowperm_build(cudaStream_t st, const int* sa, const int* sb, size_t K, size_t stride, size_t n, void* ws);
 int rowperm_apply(cudaStream_t st, double* a, size_t lda, size_t ncols, size_t max_touched, const void* ws, size_t n);
 int iota_int(cudaStream_t st, int* p, size_t n, int offset);
+
+// ---- panel_qr.cu ---------------------------------------------------------------------------------
+constexpr int kQrLeaf = 32;        // GEQR2 leaf panel width
+size_t geqr2_workspace_bytes();
+int geqr2_panel(cudaStream_t st, double* a_panel, size_t lda, size_t m, size_t w, double* tau, void* ws, int* seq_state);
+int extract_v(cudaStream_t st, double* vw, size_t ldv, const double* a, size_t lda, size_t m, size_t w, const double* tau, int mode);
+int build_s(cudaStream_t st, double* g, size_t ldg, size_t w, const double* tau);
+int tau_from_diag(cudaStream_t st, double* tau_out, const double* diag, size_t n);
+int qr_convert_to_nalgebra(cudaStream_t st, double* a, size_t lda, size_t m, size_t n, const double* tau, double* csign, double* diag);
+int qr_signs_from_diag(cudaStream_t st, const double* diag, size_t k, double* csign);
+int scale_signs(cudaStream_t st, double* b, size_t ldb, size_t rows, size_t cols, const double* csign, size_t k, bool by_cols);
 
 // ---- factor.cu -----------------------------------------------------------------------------------
 // Solves M X = B in place on B (n x nrhs, strides rsb/csb, one of them 1).  M (strides rsm/csm) is

@@ -11,61 +11,145 @@ namespace nab {
 constexpr int IB = kInvBlock;   // 128
 
 // ------------------------------------------------------------------------------------------------
-// POTF2: in-place lower Cholesky of an n x n (n <= 128) diagonal block held in shared memory.
-// Follows Cholesky::new_internal's pivot rule (/root/reference/src/linalg/cholesky.rs:237-268):
-// pivot <= 0 or NaN -> use `sub` when allowed (and itself > 0), else record the failing column;
-// the column is divided (true division) by sqrt(pivot).  The strict upper triangle is not touched.
+// Register-blocked 128x128 leaf kernels.  256 threads form a 16x16 grid; thread (tx, ty) owns the
+// elements (i = tx + 16a, k = ty + 16b), a,b < 8, of the block in registers (cyclic distribution,
+// so the shrinking active region stays balanced).  Each column/row step is one rank-1 update:
+// the step's vector is broadcast through shared memory, 16 LDS + 64 predicated DFMA per thread,
+// one __syncthreads per step.
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256, 1)
-potf2_kernel(double* __restrict__ a, long long lda, int n, int use_sub, double sub, long long col0, unsigned long long* fail_col) {
-    extern __shared__ double sm[];
-    const int LDS = IB + 1;
-    double* s = sm;                                   // n x n, ld = 129
-    __shared__ double s_rdiag;
-    __shared__ int s_fail;
-    const int tid = threadIdx.x, nt = blockDim.x;
-    for (int idx = tid; idx < n * n; idx += nt) {
-        const int i = idx % n, j = idx / n;
-        if (i >= j) s[i + j * LDS] = a[i + j * lda];
-    }
-    if (tid == 0) s_fail = 0;
-    __syncthreads();
+struct Tile16 {
+    double r[8][8];
+};
+
+// X <- inverse of the n x n lower-triangular matrix held in sL (ld 128, diagonal included unless
+// unit).  Forward substitution on the identity, right-looking: for step j, row j of X is scaled by
+// 1/L[j,j] and eliminated from the rows below.  Result left in `x` (register tile).
+__device__ __forceinline__ void tile_trtri_lower(const double* __restrict__ sL, double* __restrict__ rowbuf /*[2][128]*/,
+                                                 int n, bool unit, Tile16& x, int tx, int ty) {
+#pragma unroll
+    for (int a = 0; a < 8; ++a)
+#pragma unroll
+        for (int b = 0; b < 8; ++b) x.r[a][b] = (tx + 16 * a == ty + 16 * b) ? 1.0 : 0.0;
     for (int j = 0; j < n; ++j) {
-        if (tid == 0) {
-            double d = s[j + j * LDS];
-            bool ok = d > 0.0;                         // false for NaN and for <= 0
-            if (!ok && use_sub && sub > 0.0) { d = sub; ok = true; }
-            if (!ok) {
-                atomicMin(fail_col, (unsigned long long)(col0 + j));
-                s_fail = 1;
-                d = 1.0;                               // keep going on garbage; the driver reports NOT_PD
+        double* rb = rowbuf + (j & 1) * 128;
+        if (tx == (j & 15)) {                       // owners of row j of X
+            const int a = j >> 4;
+            const double rd = unit ? 1.0 : 1.0 / sL[j + j * 128];
+#pragma unroll
+            for (int b = 0; b < 8; ++b) {
+                double v = 0.0;
+#pragma unroll
+                for (int aa = 0; aa < 8; ++aa) if (aa == a) v = x.r[aa][b];
+                v *= rd;
+#pragma unroll
+                for (int aa = 0; aa < 8; ++aa) if (aa == a) x.r[aa][b] = v;
+                rb[ty + 16 * b] = v;
             }
-            const double sd = sqrt(d);
-            s[j + j * LDS] = sd;
-            s_rdiag = sd;
         }
         __syncthreads();
-        const double sd = s_rdiag;
-        for (int i = j + 1 + tid; i < n; i += nt) s[i + j * LDS] = s[i + j * LDS] / sd;
-        __syncthreads();
-        // trailing update of the lower triangle: a[i,k] -= a[i,j]*a[k,j], j < k <= i
-        const int rem = n - j - 1;
-        for (int idx = tid; idx < rem * rem; idx += nt) {
-            const int i = j + 1 + idx % rem, k = j + 1 + idx / rem;
-            if (i >= k) s[i + k * LDS] -= s[i + j * LDS] * s[k + j * LDS];
-        }
-        __syncthreads();
-    }
-    for (int idx = tid; idx < n * n; idx += nt) {
-        const int i = idx % n, j = idx / n;
-        if (i >= j) a[i + j * lda] = s[i + j * LDS];
+        double lcol[8], xrow[8];
+#pragma unroll
+        for (int a = 0; a < 8; ++a) { const int i = tx + 16 * a; lcol[a] = (i > j && i < n) ? sL[i + j * 128] : 0.0; }
+#pragma unroll
+        for (int b = 0; b < 8; ++b) { const int k = ty + 16 * b; xrow[b] = (k <= j) ? rb[k] : 0.0; }
+#pragma unroll
+        for (int a = 0; a < 8; ++a)
+#pragma unroll
+            for (int b = 0; b < 8; ++b) x.r[a][b] -= lcol[a] * xrow[b];
     }
 }
 
-int potf2(cudaStream_t st, double* a, size_t lda, int n, int use_sub, double sub, size_t col0, unsigned long long* fail_col) {
+// POTF2 + TRTRI of one diagonal block (n <= 128): in-place lower Cholesky following
+// Cholesky::new_internal's pivot rule (/root/reference/src/linalg/cholesky.rs:237-268): pivot <= 0
+// or NaN -> `sub` when allowed (and itself > 0), else the failing column is recorded; the column is
+// divided (true division) by sqrt(pivot).  The strict upper triangle is neither read nor written.
+// inv_out (128x128, ld 128) receives inverse(L), identity padded.
+__global__ void __launch_bounds__(256, 1)
+potf2_trtri_kernel(double* __restrict__ a, long long lda, int n, int use_sub, double sub, long long col0,
+                   unsigned long long* fail_col, double* __restrict__ inv_out) {
+    extern __shared__ double sm[];
+    double* sL = sm;                   // 128 x 128 factor, column j filled at step j
+    double* rowbuf = sm + 128 * 128;   // [2][128]
+    const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+    Tile16 t;
+#pragma unroll
+    for (int b = 0; b < 8; ++b)
+#pragma unroll
+        for (int aa = 0; aa < 8; ++aa) {
+            const int i = tx + 16 * aa, k = ty + 16 * b;
+            t.r[aa][b] = (i < n && k < n && i >= k) ? a[i + k * lda] : 0.0;
+        }
+    for (int j = 0; j < n; ++j) {
+        if (ty == (j & 15)) {                       // owners of column j: half a warp (lanes 16*(ty&1)..+15)
+            const int b = j >> 4;
+            double colv[8];
+#pragma unroll
+            for (int aa = 0; aa < 8; ++aa) {
+                double v = 0.0;
+#pragma unroll
+                for (int bb = 0; bb < 8; ++bb) if (bb == b) v = t.r[aa][bb];
+                colv[aa] = v;
+            }
+            // diagonal element lives in lane tx == j%16, slot a == j/16
+            double d = 0.0;
+#pragma unroll
+            for (int aa = 0; aa < 8; ++aa) if (aa == (j >> 4)) d = colv[aa];
+            d = __shfl_sync(0xffffu << (tid & 16), d, (j & 15) + (tid & 16), 32);   // only this half-warp is converged here
+            bool ok = d > 0.0;                      // false for NaN and for <= 0
+            if (!ok && use_sub && sub > 0.0) { d = sub; ok = true; }
+            if (!ok) {
+                if (tx == 0) atomicMin(fail_col, (unsigned long long)(col0 + j));
+                d = 1.0;                            // keep going on garbage; the driver reports NOT_PD
+            }
+            const double sd = sqrt(d);
+#pragma unroll
+            for (int aa = 0; aa < 8; ++aa) {
+                const int i = tx + 16 * aa;
+                double v = (i == j) ? sd : (i > j ? colv[aa] / sd : 0.0);
+                sL[i + j * 128] = v;
+#pragma unroll
+                for (int bb = 0; bb < 8; ++bb) if (bb == b) t.r[aa][bb] = v;
+            }
+        }
+        __syncthreads();
+        double ci[8], ck[8];
+#pragma unroll
+        for (int aa = 0; aa < 8; ++aa) { const int i = tx + 16 * aa; ci[aa] = (i > j) ? sL[i + j * 128] : 0.0; }
+#pragma unroll
+        for (int b = 0; b < 8; ++b) { const int k = ty + 16 * b; ck[b] = (k > j) ? sL[k + j * 128] : 0.0; }
+#pragma unroll
+        for (int aa = 0; aa < 8; ++aa)
+#pragma unroll
+            for (int b = 0; b < 8; ++b) t.r[aa][b] -= ci[aa] * ck[b];   // entries with i < k are never stored
+    }
+    // store L (lower triangle only)
+#pragma unroll
+    for (int b = 0; b < 8; ++b)
+#pragma unroll
+        for (int aa = 0; aa < 8; ++aa) {
+            const int i = tx + 16 * aa, k = ty + 16 * b;
+            if (i < n && k < n && i >= k) a[i + k * lda] = t.r[aa][b];
+        }
+    __syncthreads();
+    if (inv_out) {
+        Tile16 x;
+        tile_trtri_lower(sL, rowbuf, n, false, x, tx, ty);
+#pragma unroll
+        for (int b = 0; b < 8; ++b)
+#pragma unroll
+            for (int aa = 0; aa < 8; ++aa) {
+                const int i = tx + 16 * aa, k = ty + 16 * b;
+                inv_out[i + k * 128] = (i < n && k < n) ? (i >= k ? x.r[aa][b] : 0.0) : (i == k ? 1.0 : 0.0);
+            }
+    }
+}
+
+int potf2(cudaStream_t st, double* a, size_t lda, int n, int use_sub, double sub, size_t col0, unsigned long long* fail_col,
+          double* inv_out) {
     static std::once_flag once;
-    std::call_once(once, [] { cudaFuncSetAttribute(potf2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, IB * (IB + 1) * 8); });
-    potf2_kernel<<<1, 256, IB * (IB + 1) * 8, st>>>(a, (long long)lda, n, use_sub, sub, (long long)col0, fail_col);
+    const int smem = (128 * 128 + 256) * 8;
+    std::call_once(once, [smem] { cudaFuncSetAttribute(potf2_trtri_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); });
+    potf2_trtri_kernel<<<1, 256, smem, st>>>(a, (long long)lda, n, use_sub, sub, (long long)col0, fail_col, inv_out);
     NAB_LAUNCH_CHECK();
     return NA_OK;
 }
@@ -76,73 +160,50 @@ int potf2(cudaStream_t st, double* a, size_t lda, int n, int use_sub, double sub
 // out[b] (128 x 128 column-major, ld 128) receives inverse(M_bb), zero outside the triangle and
 // identity-padded when the last block is short.  unit: implicit unit diagonal.  diag_abs != null:
 // the diagonal is |diag_abs[i]| instead of M[i,i] (nalgebra's QR keeps R's diagonal in `diag`,
-// /root/reference/src/linalg/qr.rs:224-256).
-//
-// One CTA of 128 threads per block, thread j owns column j of the inverse.  A single 128x128
-// shared buffer holds M's strict lower triangle and, transposed into the upper triangle + diagonal,
-// the inverse being built (thread j touches row j only: conflict-free); upper-triangular blocks
-// are handled by reversing the index order, which maps them to lower-triangular ones.
+// /root/reference/src/linalg/qr.rs:224-256).  Upper-triangular blocks are handled by reversing the
+// index order, which maps them to lower-triangular ones.  One CTA per block.
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(128, 1)
+__global__ void __launch_bounds__(256, 1)
 trtri_blocks_kernel(const double* __restrict__ t, long long rs, long long cs, long long n, int eff_lower, int unit,
                     const double* __restrict__ diag_abs, double* __restrict__ out) {
     extern __shared__ double sm[];
-    double* buf = sm;                  // 128 x 128, ld 128
-    double* rdiag = sm + IB * IB;      // 128
-    const int b = blockIdx.x, tid = threadIdx.x;
+    double* sL = sm;
+    double* rowbuf = sm + 128 * 128;
+    const int b = blockIdx.x, tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
     const long long base = (long long)b * IB;
     const int nb = (int)min((long long)IB, n - base);
-    // local index li <-> global index: lower: base+li ; upper: base + (nb-1-li)
     auto gidx = [&](int li) -> long long { return eff_lower ? base + li : base + (nb - 1 - li); };
     for (int idx = tid; idx < nb * nb; idx += blockDim.x) {
         const int i = idx % nb, k = idx / nb;
-        if (i > k) buf[i + k * IB] = t[gidx(i) * rs + gidx(k) * cs];
-    }
-    if (tid < nb) {
-        double d = 1.0;
-        if (!unit) d = diag_abs ? fabs(diag_abs[gidx(tid)]) : t[gidx(tid) * rs + gidx(tid) * cs];
-        rdiag[tid] = 1.0 / d;
+        if (i > k) sL[i + k * 128] = t[gidx(i) * rs + gidx(k) * cs];
+        else if (i == k) sL[i + k * 128] = unit ? 1.0 : (diag_abs ? fabs(diag_abs[gidx(i)]) : t[gidx(i) * rs + gidx(i) * cs]);
     }
     __syncthreads();
-    const int j = tid;
-    if (j < nb) {
-        // X[i,j] for i >= j, stored at buf[j + i*IB]
-        buf[j + j * IB] = rdiag[j];
-        for (int i = j + 1; i < nb; ++i) {
-            double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
-            int k = j;
-            for (; k + 3 < i; k += 4) {
-                s0 += buf[i + k * IB] * buf[j + k * IB];
-                s1 += buf[i + (k + 1) * IB] * buf[j + (k + 1) * IB];
-                s2 += buf[i + (k + 2) * IB] * buf[j + (k + 2) * IB];
-                s3 += buf[i + (k + 3) * IB] * buf[j + (k + 3) * IB];
-            }
-            for (; k < i; ++k) s0 += buf[i + k * IB] * buf[j + k * IB];
-            buf[j + i * IB] = -((s0 + s1) + (s2 + s3)) * rdiag[i];
-        }
-    }
-    __syncthreads();
-    // write out: out_b[gi, gj] (block-local global order) = X[li, lj]
+    Tile16 x;
+    tile_trtri_lower(sL, rowbuf, nb, unit != 0, x, tx, ty);
     double* ob = out + (long long)b * IB * IB;
-    for (int idx = tid; idx < IB * IB; idx += blockDim.x) {
-        const int r = idx % IB, c = idx / IB;     // block-local position in global order
-        double v = (r == c) ? 1.0 : 0.0;          // identity padding
-        if (r < nb && c < nb) {
-            const int li = eff_lower ? r : nb - 1 - r, lj = eff_lower ? c : nb - 1 - c;
-            v = (li >= lj) ? buf[lj + li * IB] : 0.0;
+#pragma unroll
+    for (int bb = 0; bb < 8; ++bb)
+#pragma unroll
+        for (int aa = 0; aa < 8; ++aa) {
+            const int li = tx + 16 * aa, lj = ty + 16 * bb;          // local (lower) indices
+            if (li < nb && lj < nb) {
+                const int r = eff_lower ? li : nb - 1 - li, c = eff_lower ? lj : nb - 1 - lj;
+                ob[r + c * IB] = (li >= lj) ? x.r[aa][bb] : 0.0;
+            } else {
+                ob[li + lj * IB] = (li == lj) ? 1.0 : 0.0;            // identity padding
+            }
         }
-        ob[r + c * IB] = v;
-    }
 }
 
 int trtri_blocks(cudaStream_t st, const double* t, ptrdiff_t rs, ptrdiff_t cs, size_t n, bool eff_lower, bool unit,
                  const double* diag_abs, double* out) {
     if (n == 0) return NA_OK;
     static std::once_flag once;
-    const int smem = (IB * IB + IB) * 8;
+    const int smem = (IB * IB + 256) * 8;
     std::call_once(once, [smem] { cudaFuncSetAttribute(trtri_blocks_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); });
     const int nblk = (int)ceil_div(n, IB);
-    trtri_blocks_kernel<<<nblk, 128, smem, st>>>(t, rs, cs, (long long)n, eff_lower ? 1 : 0, unit ? 1 : 0, diag_abs, out);
+    trtri_blocks_kernel<<<nblk, 256, smem, st>>>(t, rs, cs, (long long)n, eff_lower ? 1 : 0, unit ? 1 : 0, diag_abs, out);
     NAB_LAUNCH_CHECK();
     return NA_OK;
 }

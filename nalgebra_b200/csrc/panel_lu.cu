@@ -30,26 +30,21 @@ struct Getf2Params {
     int rp;                        // rows per CTA (multiple of 32)
     int j0;                        // global row/col offset of the panel (for ipiv values)
     int* ipiv;                     // ipiv[j0 + c] = global pivot row of column c
-    double* slots;                 // [2][G][w + 2]  (absval, row, candidate row values)
-    double* rowc;                  // [2][w]          current row c, published by its owner
+    double* cand_val;              // [2][G]      |candidate|
+    int* cand_row;                 // [2][G]      candidate row (panel-relative)
+    double* cand_vals;             // [2][G][w]   the candidate's row of the panel
+    double* rowc;                  // [2][w]      current row c, published by its owner
     unsigned int* counter;         // grid barrier, zeroed before launch
 };
-
-__device__ __forceinline__ void grid_barrier(unsigned int* counter, unsigned int target) {
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        __threadfence();
-        atomicAdd(counter, 1u);
-        while (*((volatile unsigned int*)counter) < target) {
-        }
-        __threadfence();
-    }
-    __syncthreads();
-}
 
 // candidate ordering of icamax: larger value wins; on equal values the lower row wins.
 __device__ __forceinline__ bool cand_better(double v1, int r1, double v2, int r2) {
     return (v1 > v2) || (v1 == v2 && r1 < r2);
+}
+// |x| as a pivot key: a NaN wins only at index 0 of the searched range (min_max.rs:221-240)
+__device__ __forceinline__ double pivot_key(double x, bool first) {
+    const double v = fabs(x);
+    return (v != v) ? (first ? __longlong_as_double(0x7ff0000000000000LL) : -1.0) : v;
 }
 
 __global__ void __launch_bounds__(256, 1) getf2_coop_kernel(const Getf2Params p) {
@@ -64,26 +59,25 @@ __global__ void __launch_bounds__(256, 1) getf2_coop_kernel(const Getf2Params p)
     double* crow = prow + w;               // [w] old row c
     __shared__ double red_v[8];
     __shared__ int red_r[8], red_w[8];
-    __shared__ double s_gval;
-    __shared__ int s_grow, s_gcta, s_lrow;
+    __shared__ int s_lrow;
 
-    // load this CTA's rows
     for (int c = 0; c < w; ++c)
         for (int r = tid; r < nrows; r += nt) s[r + c * rp] = p.a[(long long)(r_begin + r) + (long long)c * p.lda];
     __syncthreads();
 
-    const int slot_stride = w + 2;
-    for (int c = 0; c < w && c < p.m; ++c) {
+    // candidates of column 0
+    double bv = -1.0; int br = 0x7fffffff;
+    for (int r = tid; r < nrows; r += nt) {
+        const int gr = r_begin + r;
+        const double v = pivot_key(s[r], gr == 0);
+        if (cand_better(v, gr, bv, br)) { bv = v; br = gr; }
+    }
+
+    const int ncol = min(w, p.m);
+    unsigned int bar_target = 0;
+    for (int c = 0; c < ncol; ++c) {
         const int par = c & 1;
-        // ---- 1. local candidate over rows with global index >= c ----
-        double bv = -1.0; int br = 0x7fffffff;
-        for (int r = tid; r < nrows; r += nt) {
-            const int gr = r_begin + r;
-            if (gr < c) continue;
-            double v = fabs(s[r + c * rp]);
-            if (v != v) v = (gr == c) ? __longlong_as_double(0x7ff0000000000000LL) : -1.0;   // NaN: wins only at index 0
-            if (cand_better(v, gr, bv, br)) { bv = v; br = gr; }
-        }
+        // ---- A. local winner ----
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) {
             const double ov = __shfl_xor_sync(0xffffffffu, bv, o);
@@ -92,89 +86,111 @@ __global__ void __launch_bounds__(256, 1) getf2_coop_kernel(const Getf2Params p)
         }
         if (lane == 0) { red_v[warp] = bv; red_r[warp] = br; }
         __syncthreads();
-        if (tid == 0) {
-            for (int i = 1; i < nt / 32; ++i)
-                if (cand_better(red_v[i], red_r[i], bv, br)) { bv = red_v[i]; br = red_r[i]; }
-            double* slot = p.slots + ((size_t)par * G + cta) * slot_stride;
-            slot[0] = bv;
-            slot[1] = (double)br;
-            s_lrow = br;
+        if (warp == 0) {
+            double v = lane < 8 ? red_v[lane] : -2.0; int r = lane < 8 ? red_r[lane] : 0x7fffffff;
+#pragma unroll
+            for (int o = 4; o > 0; o >>= 1) {
+                const double ov = __shfl_xor_sync(0xffffffffu, v, o);
+                const int orow = __shfl_xor_sync(0xffffffffu, r, o);
+                if (cand_better(ov, orow, v, r)) { v = ov; r = orow; }
+            }
+            if (lane == 0) {
+                p.cand_val[par * G + cta] = v;
+                p.cand_row[par * G + cta] = r;
+                s_lrow = r;
+            }
         }
         __syncthreads();
         {
             const int lr = s_lrow;
-            double* slot = p.slots + ((size_t)par * G + cta) * slot_stride;
-            if (lr != 0x7fffffff)
-                for (int cc = tid; cc < w; cc += nt) slot[2 + cc] = s[(lr - r_begin) + cc * rp];
+            if (lr != 0x7fffffff) {
+                double* dst = p.cand_vals + ((size_t)par * G + cta) * w;
+                for (int cc = tid; cc < w; cc += nt) dst[cc] = s[(lr - r_begin) + cc * rp];
+            }
             if (c >= r_begin && c < r_begin + nrows)
                 for (int cc = tid; cc < w; cc += nt) p.rowc[par * w + cc] = s[(c - r_begin) + cc * rp];
         }
-        // ---- 2. grid barrier ----
-        grid_barrier(p.counter, (unsigned int)(c + 1) * (unsigned int)G);
-        // ---- 3. every CTA reduces the G candidates identically ----
-        {
-            double v = -2.0; int r = 0x7fffffff, who = -1;
-            for (int i = tid; i < G; i += nt) {
-                const volatile double* slot = p.slots + ((size_t)par * G + i) * slot_stride;
-                const double sv = slot[0]; const int sr = (int)slot[1];
-                if (cand_better(sv, sr, v, r)) { v = sv; r = sr; who = i; }
+        // ---- B. grid barrier ----
+        bar_target += (unsigned int)G;
+        __syncthreads();
+        if (tid == 0) {
+            __threadfence();
+            atomicAdd(p.counter, 1u);
+            while (*((volatile unsigned int*)p.counter) < bar_target) {
             }
+            __threadfence();
+        }
+        __syncthreads();
+        // ---- C. every CTA reduces the G candidates identically ----
+        double gv = -2.0; int grow = 0x7fffffff, gcta = -1;
+        for (int i = tid; i < G; i += nt) {
+            const double sv = ((const volatile double*)p.cand_val)[par * G + i];
+            const int sr = ((const volatile int*)p.cand_row)[par * G + i];
+            if (cand_better(sv, sr, gv, grow)) { gv = sv; grow = sr; gcta = i; }
+        }
+        const int nw_used = min(8, (G + 31) / 32);
+        if (warp < nw_used) {
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) {
-                const double ov = __shfl_xor_sync(0xffffffffu, v, o);
-                const int orow = __shfl_xor_sync(0xffffffffu, r, o);
-                const int ow = __shfl_xor_sync(0xffffffffu, who, o);
-                if (cand_better(ov, orow, v, r)) { v = ov; r = orow; who = ow; }
+                const double ov = __shfl_xor_sync(0xffffffffu, gv, o);
+                const int orow = __shfl_xor_sync(0xffffffffu, grow, o);
+                const int ow = __shfl_xor_sync(0xffffffffu, gcta, o);
+                if (cand_better(ov, orow, gv, grow)) { gv = ov; grow = orow; gcta = ow; }
             }
-            __syncthreads();   // red_* reuse
-            if (lane == 0) { red_v[warp] = v; red_r[warp] = r; red_w[warp] = who; }
-            __syncthreads();
-            if (tid == 0) {
-                for (int i = 1; i < nt / 32; ++i)
-                    if (cand_better(red_v[i], red_r[i], v, r)) { v = red_v[i]; r = red_r[i]; who = red_w[i]; }
-                s_gval = v; s_grow = r; s_gcta = who;
-            }
-            __syncthreads();
+            if (lane == 0) { red_v[warp] = gv; red_r[warp] = grow; red_w[warp] = gcta; }
         }
-        const int grow = s_grow, gcta = s_gcta;
+        __syncthreads();
+        gv = red_v[0]; grow = red_r[0]; gcta = red_w[0];
+        for (int i = 1; i < nw_used; ++i)
+            if (cand_better(red_v[i], red_r[i], gv, grow)) { gv = red_v[i]; grow = red_r[i]; gcta = red_w[i]; }
+        // ---- D. pivot row and old row c ----
         {
-            const volatile double* wslot = p.slots + ((size_t)par * G + gcta) * slot_stride;
-            for (int cc = tid; cc < w; cc += nt) {
-                prow[cc] = wslot[2 + cc];
-                crow[cc] = ((const volatile double*)p.rowc)[par * w + cc];
-            }
+            const volatile double* wv = p.cand_vals + ((size_t)par * G + gcta) * w;
+            const volatile double* rc = p.rowc + par * w;
+            for (int cc = tid; cc < w; cc += nt) { prow[cc] = wv[cc]; crow[cc] = rc[cc]; }
         }
         __syncthreads();
         const double pivot = prow[c];
-        if (cta == 0 && tid == 0) p.ipiv[p.j0 + c] = p.j0 + ((pivot == 0.0) ? c : grow);
-        if (pivot == 0.0) continue;                      // lu.rs:107-110: nothing to eliminate (uniform across CTAs)
-        // ---- 4. swap rows c <-> grow inside shared memory ----
-        if (grow != c) {
-            if (grow >= r_begin && grow < r_begin + nrows)
-                for (int cc = tid; cc < w; cc += nt) s[(grow - r_begin) + cc * rp] = crow[cc];
-            if (c >= r_begin && c < r_begin + nrows)
-                for (int cc = tid; cc < w; cc += nt) s[(c - r_begin) + cc * rp] = prow[cc];
-            __syncthreads();
+        const bool elim = pivot != 0.0;                  // lu.rs:107-110: an all-zero column is skipped
+        if (cta == 0 && tid == 0) p.ipiv[p.j0 + c] = p.j0 + (elim ? grow : c);
+        // ---- E. swap rows c <-> grow inside shared memory ----
+        if (elim && grow != c) {
+            const bool own_g = grow >= r_begin && grow < r_begin + nrows;
+            const bool own_c = c >= r_begin && c < r_begin + nrows;
+            if (own_g) for (int cc = tid; cc < w; cc += nt) s[(grow - r_begin) + cc * rp] = crow[cc];
+            if (own_c) for (int cc = tid; cc < w; cc += nt) s[(c - r_begin) + cc * rp] = prow[cc];
+            if (own_g || own_c) __syncthreads();
         }
-        // ---- 5. scale by the reciprocal pivot and rank-1 update (unfused mul/add like the reference) ----
+        // ---- F. scale by the reciprocal pivot, rank-1 update (unfused mul/add like the reference),
+        //         and pick up the candidates of column c+1 on the way ----
         const double inv = 1.0 / pivot;
+        bv = -1.0; br = 0x7fffffff;
         for (int r = tid; r < nrows; r += nt) {
             const int gr = r_begin + r;
             if (gr <= c) continue;
-            const double l = __dmul_rn(s[r + c * rp], inv);
-            s[r + c * rp] = l;
-            for (int cc = c + 1; cc < w; ++cc)
-                s[r + cc * rp] = __dadd_rn(__dmul_rn(-prow[cc], l), s[r + cc * rp]);
+            if (elim) {
+                const double l = __dmul_rn(s[r + c * rp], inv);
+                s[r + c * rp] = l;
+                for (int cc = c + 1; cc < w; ++cc)
+                    s[r + cc * rp] = __dadd_rn(__dmul_rn(-prow[cc], l), s[r + cc * rp]);
+            }
+            if (c + 1 < w) {
+                const double v = pivot_key(s[r + (c + 1) * rp], gr == c + 1);
+                if (cand_better(v, gr, bv, br)) { bv = v; br = gr; }
+            }
         }
-        __syncthreads();
     }
-    // write back
+    __syncthreads();
     for (int c = 0; c < w; ++c)
         for (int r = tid; r < nrows; r += nt) p.a[(long long)(r_begin + r) + (long long)c * p.lda] = s[r + c * rp];
 }
 
 // Factors the m x w panel at A[j0.., j0..j0+w).  ws: device workspace from getf2_workspace_bytes().
-size_t getf2_workspace_bytes() { return (2 * 160 * (kLuPanel + 2) + 2 * kLuPanel) * sizeof(double) + 256; }
+constexpr size_t kGetf2MaxCtas = 160;
+size_t getf2_workspace_bytes() {
+    return 256 + 2 * kGetf2MaxCtas * sizeof(double) + 2 * kGetf2MaxCtas * sizeof(int) +
+           (2 * kGetf2MaxCtas * kLuPanel + 2 * kLuPanel) * sizeof(double);
+}
 
 int getf2_panel(cudaStream_t st, double* a_panel, size_t lda, size_t m, size_t w, size_t j0, int* ipiv, void* ws) {
     if (m == 0 || w == 0) return NA_OK;
@@ -198,8 +214,10 @@ int getf2_panel(cudaStream_t st, double* a_panel, size_t lda, size_t m, size_t w
     p.a = a_panel; p.lda = (long long)lda; p.m = (int)m; p.w = (int)w; p.rp = (int)rp; p.j0 = (int)j0; p.ipiv = ipiv;
     char* wsp = static_cast<char*>(ws);
     p.counter = reinterpret_cast<unsigned int*>(wsp);
-    p.slots = reinterpret_cast<double*>(wsp + 256);
-    p.rowc = p.slots + 2 * 160 * (kLuPanel + 2);
+    p.cand_val = reinterpret_cast<double*>(wsp + 256);
+    p.cand_vals = p.cand_val + 2 * kGetf2MaxCtas;
+    p.rowc = p.cand_vals + 2 * kGetf2MaxCtas * kLuPanel;
+    p.cand_row = reinterpret_cast<int*>(p.rowc + 2 * kLuPanel);
     NAB_CUDA(cudaMemsetAsync(p.counter, 0, sizeof(unsigned int), st));
     void* args[] = {(void*)&p};
     NAB_CUDA(cudaLaunchCooperativeKernel((void*)getf2_coop_kernel, dim3((unsigned)G), dim3(256), args, smem, st));

@@ -56,6 +56,32 @@ if "lu" in which:
     m3 = np.array([[0.0, -1, 2], [-1, 2, -1], [2, -1, 0]]); assert nab.LU.new(m3).determinant() == -4.0
     print("lu ok")
 
+if "qr" in which:
+    for (m, n) in [(1, 1), (3, 1), (1, 4), (7, 5), (5, 7), (33, 33), (40, 40), (64, 20), (100, 64), (257, 130), (130, 257), (300, 300), (700, 300), (1000, 513), (2000, 600)]:
+        A = O.uniform(m, n, 8) - 0.5
+        qr = nab.QR.new(A)
+        qref, dref = O.qr(A)
+        k = min(m, n)
+        e1 = np.abs(qr.qr_internal() - qref).max(); e2 = np.abs(qr.diag_internal() - dref).max()
+        q, r = qr.q(), qr.r()
+        res = np.linalg.norm(q @ r - A) / np.linalg.norm(A); orth = np.linalg.norm(q.T @ q - np.eye(k))
+        qo = O.qr_q(qref, dref)
+        B = O.uniform(m, 3, 4); Bq = B.copy(order="F"); qr.q_tr_mul(Bq)
+        e3 = np.abs(Bq - O.qr_q_tr_mul(qref, dref, B)).max()
+        print(f"qr {m}x{n}: |qr-ref|={e1:.2e} |diag-ref|={e2:.2e} |q-qref|={np.abs(q-qo).max():.2e} resid={res:.2e} orth={orth:.2e} qtmul={e3:.2e}")
+        assert e1 < 1e-10 and e2 < 1e-10 and res <= 10 * max(m, n) * eps and orth <= 10 * max(m, n) * eps and e3 < 1e-10
+    A = O.uniform(200, 200, 8); qr = nab.QR.new(A); b = O.uniform(200, 5, 7); x = qr.solve(b)
+    print("qr solve resid", np.abs(A @ x - b).max()); assert np.abs(A @ x - b).max() < 1e-9
+    A = O.uniform(20, 12, 8) - 0.5; A[:, 4] = 0.0
+    qr = nab.QR.new(A); qref, dref = O.qr(A)
+    print("qr zero col", np.abs(qr.qr_internal() - qref).max(), np.abs(qr.diag_internal() - dref).max())
+    assert np.abs(qr.qr_internal() - qref).max() < 1e-12
+    print("qr ok")
+    a32 = (O.uniform(300, 200, 1) - 0.5).astype(np.float32); b32 = (O.uniform(200, 150, 2) - 0.5).astype(np.float32)
+    c32 = np.ones((300, 150), dtype=np.float32, order="F")
+    nab.gemm_f32(1.5, a32, b32.T.copy().T, 0.5, c32)
+    print("sgemm err", np.abs(c32 - (1.5 * a32.astype(np.float64) @ b32.astype(np.float64) + 0.5)).max())
+
 N = int(sys.argv[1]) if len(sys.argv) > 1 else 0
 if N:
     import torch
@@ -76,6 +102,25 @@ if N:
         R = Lm @ Lm.t() - A0.view(N, N).t()
         print("  resid", (torch.linalg.norm(torch.tril(R)) / torch.linalg.norm(torch.tril(A0.view(N, N).t()))).item(), "bound", 10 * N * eps)
         del A0, A, Lm, R, M
+    if "qr" in which:
+        m, n = 65536, 4096
+        A0 = torch.empty(m * n, dtype=torch.float64, device=dev); A = torch.empty_like(A0); dg = torch.empty(n, dtype=torch.float64, device=dev)
+        _capi.check(L.na_fill_uniform_dev(A0.data_ptr(), m, n, m, 8, s))
+        for it in range(2):
+            A.copy_(A0); torch.cuda.synchronize()
+            e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+            l0 = L.na_kernel_launches()
+            e0.record(); st = L.na_qr_f64_dev(m, n, A.data_ptr(), m, dg.data_ptr(), s); e1.record(); torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1); fl = 2.0 * m * n * n - 2.0 * n ** 3 / 3
+            print(f"qr {m}x{n}: status {st} {ms:.2f} ms {fl/ms/1e9:.2f} TFLOP/s ({fl/ms/1e9/37.18*100:.1f}%) launches {L.na_kernel_launches()-l0}")
+        Q = torch.empty(m * n, dtype=torch.float64, device=dev)
+        e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+        e0.record(); _capi.check(L.na_qr_q_f64_dev(m, n, A.data_ptr(), m, dg.data_ptr(), Q.data_ptr(), m, s)); e1.record(); torch.cuda.synchronize()
+        print(f"  q(): {e0.elapsed_time(e1):.2f} ms")
+        Qm = Q.view(n, m).t(); R = torch.triu(A.view(n, m).t()[:n, :]); R.diagonal().copy_(dg.abs())
+        A0m = A0.view(n, m).t()
+        print("  resid |A-QR|/|A|", (torch.linalg.norm(A0m - Qm @ R) / torch.linalg.norm(A0m)).item(), "orth", torch.linalg.norm(Qm.t() @ Qm - torch.eye(n, device=dev, dtype=torch.float64)).item(), "bound", 10 * m * eps)
+        del A0, A, Q, Qm, R
     if "lu" in which:
         A0 = torch.empty(N * N, dtype=torch.float64, device=dev)
         _capi.check(L.na_fill_uniform_dev(A0.data_ptr(), N, N, N, 6, s))
