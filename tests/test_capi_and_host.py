@@ -1,0 +1,105 @@
+"""CPU: the C-ABI library builds, loads and exports every symbol include/nalgebra_b200.h declares;
+the host-side mirror behaves like the reference on shapes/errors; no compute without a GPU."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared_symbols():
+    src = open(os.path.join(ROOT, "include", "nalgebra_b200.h")).read()
+    return sorted(set(re.findall(r"NAB_API\s+[\w\s\*]+?\b(na_\w+)\s*\(", src)))
+
+
+def test_header_symbols_are_exported(nab):
+    from nalgebra_b200 import _capi
+    lib = _capi.lib()
+    declared = _declared_symbols()
+    assert len(declared) >= 34
+    missing = [s for s in declared if not hasattr(lib, s)]
+    assert not missing, f"not exported: {missing}"
+    # the ctypes signature table covers exactly the header
+    assert sorted(_capi.SIGNATURES) == declared
+    assert lib.na_version().decode().startswith("nalgebra_b200")
+
+
+def test_library_has_no_torch_or_oracle_dependency(nab):
+    from nalgebra_b200 import _capi
+    import subprocess
+    out = subprocess.run(["ldd", _capi.LIB_PATH], capture_output=True, text=True).stdout
+    assert "torch" not in out and "oracle" not in out and "libcudart" not in out   # static cudart, plain C ABI
+
+
+def test_product_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, "nalgebra_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".hpp", ".h")):
+                txt = open(os.path.join(dirpath, f)).read()
+                assert "import oracle" not in txt and "nalgebra_oracle" not in txt, f
+
+
+def _has_gpu():
+    try:
+        import torch
+        return torch.cuda.is_available()
+    except Exception:
+        return False
+
+
+@pytest.mark.skipif(_has_gpu(), reason="needs a machine WITHOUT a GPU")
+def test_compute_fails_loudly_without_gpu(nab):
+    from nalgebra_b200 import _capi
+    a = np.ones((8, 8), order="F")
+    with pytest.raises(_capi.NalgebraB200Error) as e:
+        nab.gemm(1.0, a, a, 0.0, a.copy(order="F"))
+    assert e.value.status == _capi.NA_ECUDA and "no CPU fallback" in str(e.value)
+    with pytest.raises(_capi.NalgebraB200Error):
+        nab.Cholesky.new(np.eye(4))
+    with pytest.raises(_capi.NalgebraB200Error):
+        nab.LU.new(np.eye(4))
+    with pytest.raises(_capi.NalgebraB200Error):
+        nab.QR.new(np.eye(4))
+
+
+def test_shape_errors_mirror_reference_panics(nab):
+    a = np.ones((3, 4), order="F")
+    with pytest.raises(ValueError, match="multiplication"):
+        nab.gemm(1.0, a, a, 0.0, np.zeros((3, 4), order="F"))
+    with pytest.raises(ValueError, match="addition"):
+        nab.gemm(1.0, a, a.T, 0.0, np.zeros((4, 4), order="F"))
+    with pytest.raises(ValueError, match="square"):
+        nab.Cholesky.new(a)
+    with pytest.raises(ValueError, match="non-square"):
+        nab.LU(a, nab.PermutationSequence.identity(3)).solve(np.ones((3, 1)))
+
+
+def test_permutation_sequence_semantics(nab, oracle):
+    p = nab.PermutationSequence.identity(4)
+    p.append_permutation(0, 2); p.append_permutation(1, 1); p.append_permutation(2, 3)
+    assert len(p) == 2 and p.determinant() == 1.0
+    m = np.arange(16.0).reshape(4, 4)
+    x = m.copy(); p.permute_rows(x)
+    assert np.array_equal(x, oracle.permute_rows(p.ipiv, m))
+    p.inv_permute_rows(x)
+    assert np.array_equal(x, m)
+    p.append_permutation(0, 1)
+    assert p.determinant() == -1.0
+    with pytest.raises(ValueError):
+        q = nab.PermutationSequence.identity(1); q.append_permutation(0, 1); q.append_permutation(0, 1)
+
+
+def test_sharding_grid_arithmetic():
+    from nalgebra_b200 import sharding as S
+    assert [S.process_grid(w) for w in (1, 2, 4, 8)] == [(1, 1), (1, 2), (2, 2), (2, 4)]
+    for world in (1, 2, 3, 4, 8):
+        cover = np.zeros((37, 53), dtype=int)
+        for r in range(world):
+            r0, r1, c0, c1 = S.gemm_tile(r, world, 37, 53)
+            cover[r0:r1, c0:c1] += 1
+        assert (cover == 1).all()
+    assert S.block_cyclic_local_blocks(1, 4, 10) == [1, 5, 9] and S.block_cyclic_owner(7, 4) == 3
