@@ -145,6 +145,7 @@ def run_gpu(args):
     import torch
     import torch.distributed as dist
     from nalgebra_b200 import _capi
+    from nalgebra_b200.sharding import process_grid
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -162,7 +163,7 @@ def run_gpu(args):
     stream = torch.cuda.current_stream().cuda_stream
 
     N = args.n
-    pr, pc = GRIDS.get(ngpus, (1, ngpus))
+    pr, pc = process_grid(ngpus)
     my_r, my_c = rank // pc, rank % pc
     m_loc, n_loc = N // pr, N // pc
     row0, col0 = my_r * m_loc, my_c * n_loc
@@ -208,6 +209,14 @@ def run_gpu(args):
     # per-kernel duration for the roofline: one launch per step on this rank
     kernel_ms = ms_total / args.steps
     achieved = (flops / ngpus) / (kernel_ms * 1e-3) / 1e12
+    traffic = None
+    try:   # DRAM bytes of one launch from the committed `ncu --set full` capture (same workload only)
+        with open(os.path.join(ROOT, "profiles", "r01_dgemm_traffic.json")) as f:
+            tj = json.load(f)
+        if ngpus == 1 and N == N_FULL:
+            traffic = tj["traffic_bytes_per_launch"]
+    except Exception:
+        pass
 
     # ---- e2e: host-pointer C-ABI call, pinned host buffers, copies inside the timed region ----
     e2e = None
@@ -263,7 +272,7 @@ def run_gpu(args):
                        "l2": "inputs (>=1.6 GB per GPU) exceed the 126 MB L2; no explicit flush",
                        "pct_of_fp64_peak": 100.0 * value / 1e3 / (FP64_PEAK_TFLOPS * ngpus)},
             "roofline": {"bound": "tensor", "achieved": achieved, "peak": FP64_PEAK_TFLOPS, "unit": "TFLOP/s",
-                         "frac": achieved / FP64_PEAK_TFLOPS, "traffic": None,
+                         "frac": achieved / FP64_PEAK_TFLOPS, "traffic": traffic,
                          "kernel": "dgemm_tma_dmma_kernel", "peak_source": "measured: tools/fp64_peak.cu DMMA chain on this pool's B200 (profiles/fp64_peak_r01.md); MEASURED_PEAKS.json has no FP64 entry",
                          "algorithmic_flops_per_launch": flops / ngpus},
             "clocks": clocks, "gpu_launches": int(launches),
@@ -283,17 +292,6 @@ def factorization_extras(L, _capi, torch, dev, stream, N):
     """Cholesky / LU (/ QR) at the BASELINE sizes on one GPU, device resident, CUDA-event timed."""
     import ctypes as C
     out = {}
-
-    def timed(fn, reps=2):
-        fn(); torch.cuda.synchronize()
-        e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
-        best = None
-        for _ in range(reps):
-            prep = fn.prepare() if hasattr(fn, "prepare") else None
-            e0.record(); fn(); e1.record(); torch.cuda.synchronize()
-            ms = e0.elapsed_time(e1)
-            best = ms if best is None else min(best, ms)
-        return best
 
     if hasattr(L, "na_cholesky_f64_dev"):
         A = torch.empty(N * N, dtype=torch.float64, device=dev)
