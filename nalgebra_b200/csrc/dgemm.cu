@@ -128,13 +128,16 @@ struct GemmParams {
     long long split_stride;
 };
 
-// lower_only (SYRK-shaped, square C, BM == BN): t enumerates the lower-triangular tiles row by row.
-__device__ __forceinline__ void tile_coords_lower(int t, int& tm, int& tn) {
-    int r = (int)((sqrt(8.0 * (double)t + 1.0) - 1.0) * 0.5);
-    while ((long long)(r + 1) * (r + 2) / 2 <= t) ++r;
-    while ((long long)r * (r + 1) / 2 > t) --r;
-    tm = r;
-    tn = t - (int)((long long)r * (r + 1) / 2);
+// lower_only (SYRK-shaped, C is M x N with M >= N, BM == BN): t enumerates the tiles with tm >= tn,
+// tile column by tile column: column tn holds T - tn tiles, prefix(tn) = tn*T - tn*(tn-1)/2, T = tiles_m.
+__device__ __forceinline__ void tile_coords_lower(int t, int T, int& tm, int& tn) {
+    const double b = 2.0 * T + 1.0;
+    int c = (int)((b - sqrt(b * b - 8.0 * (double)t)) * 0.5);
+    c = max(0, min(c, T - 1));
+    while (c + 1 < T && (long long)(c + 1) * T - (long long)(c + 1) * c / 2 <= t) ++c;
+    while (c > 0 && (long long)c * T - (long long)c * (c - 1) / 2 > t) --c;
+    tn = c;
+    tm = c + (t - (int)((long long)c * T - (long long)c * (c - 1) / 2));
 }
 
 __device__ __forceinline__ void tile_coords(int t, int tiles_m, int tiles_n, int& tm, int& tn) {
@@ -181,7 +184,7 @@ dgemm_tma_dmma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
             for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
                 int tm, tn;
                 const int tile = t / p.splits, split = t - tile * p.splits;
-                if (p.lower_only) tile_coords_lower(tile, tm, tn); else tile_coords(tile, p.tiles_m, p.tiles_n, tm, tn);
+                if (p.lower_only) tile_coords_lower(tile, p.tiles_m, tm, tn); else tile_coords(tile, p.tiles_m, p.tiles_n, tm, tn);
                 const int kb0 = split * p.kb_per_split, kb1 = min(kblocks, kb0 + p.kb_per_split);
                 for (int kb = kb0; kb < kb1; ++kb) {
                     ptx::mbar_wait(bar_base + 8 * (STAGES + stage), phase ^ 1);
@@ -223,7 +226,7 @@ dgemm_tma_dmma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
     for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
         int tm, tn;
         const int tile = t / p.splits, split = t - tile * p.splits;
-        if (p.lower_only) tile_coords_lower(tile, tm, tn); else tile_coords(tile, p.tiles_m, p.tiles_n, tm, tn);
+        if (p.lower_only) tile_coords_lower(tile, p.tiles_m, tm, tn); else tile_coords(tile, p.tiles_m, p.tiles_n, tm, tn);
         const int kb0 = split * p.kb_per_split, kb1 = min(kblocks, kb0 + p.kb_per_split);
 
         double acc[MT][NT][2];
@@ -445,6 +448,11 @@ static int prepare_operand(cudaStream_t s, const Operand& op, Scratch& scratch, 
     return NA_OK;
 }
 
+// Upper bound on the CTAs a GEMM launch may use (look-ahead: panel work and the bulk trailing update
+// run concurrently on disjoint sets of SMs).  0 = all SMs.  Thread local: set by the blocked drivers.
+static thread_local int g_sm_limit = 0;
+void set_gemm_sm_limit(int limit) { g_sm_limit = limit; }
+
 static int launch_gemm(cudaStream_t s, bool a_kmajor, bool b_kmajor, const CUtensorMap& ma, const CUtensorMap& mb, const GemmParams& p) {
     using namespace cfg;
     static std::once_flag once;
@@ -457,7 +465,8 @@ static int launch_gemm(cudaStream_t s, bool a_kmajor, bool b_kmajor, const CUten
         e = cudaFuncSetAttribute(dgemm_tma_dmma_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES); if (e) attr_err = e;
     });
     if (attr_err != cudaSuccess) return cuda_fail(attr_err, "cudaFuncSetAttribute(dgemm)", __FILE__, __LINE__);
-    const int grid = std::min(p.num_tiles, ctx().sm_count);
+    int grid = std::min(p.num_tiles, ctx().sm_count);
+    if (g_sm_limit > 0) grid = std::min(grid, g_sm_limit);
     if (a_kmajor) {
         if (b_kmajor) dgemm_tma_dmma_kernel<true, true><<<grid, THREADS, SMEM_BYTES, s>>>(ma, mb, p);
         else dgemm_tma_dmma_kernel<true, false><<<grid, THREADS, SMEM_BYTES, s>>>(ma, mb, p);
@@ -503,8 +512,9 @@ static int gemm_colmajor_c(cudaStream_t s, bool lower_only, size_t m, size_t n, 
     p.ldc = (long long)ldc; p.C = c; p.alpha = alpha; p.beta = beta; p.lower_only = lower_only ? 1 : 0;
     p.splits = 1; p.kb_per_split = (int)ceil_div(k, BK); p.split_stride = 0;
     if (lower_only) {
-        if (m != n) { set_error("gemm: lower_only needs a square C"); return NA_EINVAL; }
-        p.num_tiles = (int)((long long)p.tiles_m * (p.tiles_m + 1) / 2);
+        if (m < n) { set_error("gemm: lower_only needs C with rows >= cols"); return NA_EINVAL; }
+        const long long T = p.tiles_m, Tn = p.tiles_n;
+        p.num_tiles = (int)(Tn * T - Tn * (Tn - 1) / 2);
     } else {
         if ((long long)p.tiles_m * p.tiles_n > 0x7fffffffLL) { set_error("gemm: too many tiles"); return NA_EINVAL; }
         p.num_tiles = p.tiles_m * p.tiles_n;

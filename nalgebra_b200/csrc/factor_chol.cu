@@ -6,6 +6,8 @@
 // /root/reference/src/linalg/solve.rs.  The reference runs unblocked Level-1 loops; here the
 // O(n^3) work is restructured as recursive panel + TRSM + SYRK so that it runs on the DMMA GEMM
 // engine.  Parity is therefore on results (residuals, failure column), not on operation order.
+#include <algorithm>
+
 #include "common.cuh"
 #include "kernels.cuh"
 
@@ -98,6 +100,86 @@ static int chol_rec(const CholCtx& c, size_t j0, size_t n) {
     return chol_rec(c, j0 + n1, n2);
 }
 
+// ------------------------------------------------------------------------------------------------
+// Large n: right-looking blocked Cholesky with one-step look-ahead on two streams.
+//
+//   panel(j)   : columns [j, j+nb): inner right-looking loop over 128-blocks -- POTF2+TRTRI leaf,
+//                TRSM as one GEMM with the leaf's inverse, lower-trapezoid GEMM on the rest of the panel.
+//   la(j)      : update of the NEXT panel's columns with panel j (trapezoid GEMM, K = nb), whole GPU.
+//   bulk(j)    : update of everything right of the next panel with panel j (lower-only GEMM, K = nb).
+//
+// bulk(j) runs on a second stream on (SMs - Rp) CTAs while panel(j+nb) runs on the caller's stream on
+// at most Rp CTAs, so the latency-bound panel is hidden behind the compute-bound update; the GEMM
+// kernels are persistent (one CTA per SM), which is why the split is expressed as grid limits.
+// ------------------------------------------------------------------------------------------------
+constexpr size_t CHOL_NB = 512;
+
+static int chol_panel(const CholCtx& c, cudaStream_t sp, size_t n, size_t j, size_t jb, int sm_limit, double* tmp, size_t ldt) {
+    for (size_t i = 0; i < jb; i += IBs) {
+        const size_t cc = j + i, w = std::min(IBs, jb - i);
+        double* acc = c.a + cc + cc * c.lda;
+        double* inv = c.inv + (cc / IBs) * IBs * IBs;
+        NAB_TRY(potf2(sp, acc, c.lda, (int)w, c.use_sub, c.sub, cc, c.fail, inv));
+        const size_t r = n - cc - w;
+        if (r == 0) continue;
+        double* a21 = acc + w;
+        set_gemm_sm_limit(sm_limit);
+        // A21 <- A21 * inv(L)^T  (out of place, then copied back)
+        int st = dgemm_device(sp, false, r, w, w, 1.0, a21, 1, (ptrdiff_t)c.lda, inv, (ptrdiff_t)IBs, 1, 0.0, tmp, 1, (ptrdiff_t)ldt);
+        if (st == NA_OK) st = copy_strided(sp, a21, 1, (ptrdiff_t)c.lda, tmp, 1, (ptrdiff_t)ldt, r, w);
+        const size_t pw = j + jb - cc - w;               // remaining columns of this panel
+        if (st == NA_OK && pw > 0)
+            st = dgemm_device(sp, true, r, w, pw, -1.0, a21, 1, (ptrdiff_t)c.lda, a21, (ptrdiff_t)c.lda, 1, 1.0,
+                              acc + w + w * c.lda, 1, (ptrdiff_t)c.lda);
+        set_gemm_sm_limit(0);
+        NAB_TRY(st);
+    }
+    return NA_OK;
+}
+
+static int chol_lookahead(const CholCtx& c, size_t n) {
+    cudaStream_t sp = c.s, su = nullptr;
+    cudaEvent_t ev_p = nullptr, ev_u = nullptr;
+    NAB_CUDA(cudaStreamCreateWithFlags(&su, cudaStreamNonBlocking));
+    NAB_CUDA(cudaEventCreateWithFlags(&ev_p, cudaEventDisableTiming));
+    NAB_CUDA(cudaEventCreateWithFlags(&ev_u, cudaEventDisableTiming));
+    Scratch tmp;
+    const size_t ldt = round_up(n, 2);
+    int st = tmp.alloc(ldt * IBs * sizeof(double), sp);
+    const int sms = ctx().sm_count;
+    bool bulk_pending = false;
+    if (st == NA_OK) st = chol_panel(c, sp, n, 0, std::min(CHOL_NB, n), 0, tmp.as<double>(), ldt);
+    for (size_t j = 0; st == NA_OK && j + CHOL_NB < n; j += CHOL_NB) {
+        const size_t jb = CHOL_NB, jn = j + jb, jbn = std::min(CHOL_NB, n - jn);
+        const double* pj = c.a + j * c.lda;               // panel j: columns [j, j+jb)
+        // la(j): next panel's columns, rows jn.., needs bulk(j - nb) finished on those columns
+        if (bulk_pending) { cudaStreamWaitEvent(sp, ev_u, 0); }
+        st = dgemm_device(sp, true, n - jn, jb, jbn, -1.0, pj + jn, 1, (ptrdiff_t)c.lda, pj + jn, (ptrdiff_t)c.lda, 1, 1.0,
+                          c.a + jn + jn * c.lda, 1, (ptrdiff_t)c.lda);
+        if (st != NA_OK) break;
+        cudaEventRecord(ev_p, sp);
+        const size_t jr = jn + jbn, rr = n - jr;          // bulk region: rows/cols [jr, n)
+        int rp = 0;
+        if (rr > 0) {
+            rp = (int)((double)sms * 2.0 * CHOL_NB / ((double)(n - jn) + 2.0 * CHOL_NB));
+            rp = std::max(16, std::min(rp, sms - 28));
+            cudaStreamWaitEvent(su, ev_p, 0);
+            set_gemm_sm_limit(sms - rp);
+            st = dgemm_device(su, true, rr, jb, rr, -1.0, pj + jr, 1, (ptrdiff_t)c.lda, pj + jr, (ptrdiff_t)c.lda, 1, 1.0,
+                              c.a + jr + jr * c.lda, 1, (ptrdiff_t)c.lda);
+            set_gemm_sm_limit(0);
+            if (st != NA_OK) break;
+            cudaEventRecord(ev_u, su);
+            bulk_pending = true;
+        }
+        st = chol_panel(c, sp, n, jn, jbn, rp, tmp.as<double>(), ldt);
+    }
+    if (bulk_pending) cudaStreamWaitEvent(sp, ev_u, 0);
+    cudaStreamSynchronize(su);
+    cudaEventDestroy(ev_p); cudaEventDestroy(ev_u); cudaStreamDestroy(su);
+    return st;
+}
+
 int cholesky_device(cudaStream_t s, size_t n, double* a, size_t lda, int use_sub, double sub, size_t* fail_col) {
     if (n == 0) return NA_OK;
     if (lda < n) { set_error("cholesky: lda < n"); return NA_EINVAL; }
@@ -106,7 +188,8 @@ int cholesky_device(cudaStream_t s, size_t n, double* a, size_t lda, int use_sub
     NAB_TRY(flag.alloc(sizeof(unsigned long long), s));
     NAB_CUDA(cudaMemsetAsync(flag.p, 0xff, sizeof(unsigned long long), s));
     CholCtx c{s, a, lda, use_sub, sub, inv.as<double>(), flag.as<unsigned long long>()};
-    NAB_TRY(chol_rec(c, 0, n));
+    if (n <= 2 * CHOL_NB) NAB_TRY(chol_rec(c, 0, n));
+    else NAB_TRY(chol_lookahead(c, n));
     unsigned long long h = 0;
     NAB_CUDA(cudaMemcpyAsync(&h, flag.p, sizeof(h), cudaMemcpyDeviceToHost, s));
     NAB_CUDA(cudaStreamSynchronize(s));

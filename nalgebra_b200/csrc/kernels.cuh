@@ -11,6 +11,7 @@ namespace nab {
 int dgemm_device(cudaStream_t s, bool lower_only, size_t m, size_t k, size_t n, double alpha,
                  const double* a, ptrdiff_t rsa, ptrdiff_t csa, const double* b, ptrdiff_t rsb, ptrdiff_t csb,
                  double beta, double* c, ptrdiff_t rsc, ptrdiff_t csc);
+void set_gemm_sm_limit(int limit);   // 0 = all SMs; thread local
 int pack_strided(cudaStream_t s, double* dst, size_t ldd, const double* src, ptrdiff_t rs, ptrdiff_t cs, size_t rows, size_t cols);
 int scatter_strided(cudaStream_t s, double* dst, ptrdiff_t rs, ptrdiff_t cs, const double* src, size_t lds, size_t rows, size_t cols);
 int scale_strided(cudaStream_t s, double* c, ptrdiff_t rs, ptrdiff_t cs, size_t rows, size_t cols, double beta);

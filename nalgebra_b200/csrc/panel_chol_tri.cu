@@ -24,38 +24,44 @@ struct Tile16 {
 // X <- inverse of the n x n lower-triangular matrix held in sL (ld 128, diagonal included unless
 // unit).  Forward substitution on the identity, right-looking: for step j, row j of X is scaled by
 // 1/L[j,j] and eliminated from the rows below.  Result left in `x` (register tile).
-__device__ __forceinline__ void tile_trtri_lower(const double* __restrict__ sL, double* __restrict__ rowbuf /*[2][128]*/,
+__device__ __forceinline__ void tile_trtri_lower(const double* __restrict__ sL, double* __restrict__ rowbuf /*[3][128]*/,
                                                  int n, bool unit, Tile16& x, int tx, int ty) {
 #pragma unroll
     for (int a = 0; a < 8; ++a)
 #pragma unroll
         for (int b = 0; b < 8; ++b) x.r[a][b] = (tx + 16 * a == ty + 16 * b) ? 1.0 : 0.0;
-    for (int j = 0; j < n; ++j) {
-        double* rb = rowbuf + (j & 1) * 128;
-        if (tx == (j & 15)) {                       // owners of row j of X
-            const int a = j >> 4;
-            const double rd = unit ? 1.0 : 1.0 / sL[j + j * 128];
+    double* rdiag = rowbuf + 256;                   // reciprocal diagonal, computed once, in parallel
+    {
+        const int t = tx + 16 * ty;
+        if (t < n) rdiag[t] = unit ? 1.0 : 1.0 / sL[t + t * 128];
+    }
+    __syncthreads();
 #pragma unroll
-            for (int b = 0; b < 8; ++b) {
-                double v = 0.0;
+    for (int blk = 0; blk < 8; ++blk) {             // blk = j / 16 is a compile-time constant: static register indexing
+        for (int jj = 0; jj < 16; ++jj) {
+            const int j = blk * 16 + jj;
+            if (j >= n) break;
+            double* rb = rowbuf + (j & 1) * 128;
+            if (tx == jj) {                             // owners of row j of X
+                const double rd = rdiag[j];
 #pragma unroll
-                for (int aa = 0; aa < 8; ++aa) if (aa == a) v = x.r[aa][b];
-                v *= rd;
-#pragma unroll
-                for (int aa = 0; aa < 8; ++aa) if (aa == a) x.r[aa][b] = v;
-                rb[ty + 16 * b] = v;
+                for (int b = 0; b < 8; ++b) {
+                    const double v = x.r[blk][b] * rd;
+                    x.r[blk][b] = v;
+                    rb[ty + 16 * b] = v;
+                }
             }
+            __syncthreads();
+            double lcol[8], xrow[8];
+#pragma unroll
+            for (int a = 0; a < 8; ++a) { const int i = tx + 16 * a; lcol[a] = (i > j && i < n) ? sL[i + j * 128] : 0.0; }
+#pragma unroll
+            for (int b = 0; b < 8; ++b) { const int k = ty + 16 * b; xrow[b] = (k <= j) ? rb[k] : 0.0; }
+#pragma unroll
+            for (int a = 0; a < 8; ++a)
+#pragma unroll
+                for (int b = 0; b < 8; ++b) x.r[a][b] -= lcol[a] * xrow[b];
         }
-        __syncthreads();
-        double lcol[8], xrow[8];
-#pragma unroll
-        for (int a = 0; a < 8; ++a) { const int i = tx + 16 * a; lcol[a] = (i > j && i < n) ? sL[i + j * 128] : 0.0; }
-#pragma unroll
-        for (int b = 0; b < 8; ++b) { const int k = ty + 16 * b; xrow[b] = (k <= j) ? rb[k] : 0.0; }
-#pragma unroll
-        for (int a = 0; a < 8; ++a)
-#pragma unroll
-            for (int b = 0; b < 8; ++b) x.r[a][b] -= lcol[a] * xrow[b];
     }
 }
 
@@ -79,48 +85,43 @@ potf2_trtri_kernel(double* __restrict__ a, long long lda, int n, int use_sub, do
             const int i = tx + 16 * aa, k = ty + 16 * b;
             t.r[aa][b] = (i < n && k < n && i >= k) ? a[i + k * lda] : 0.0;
         }
-    for (int j = 0; j < n; ++j) {
-        if (ty == (j & 15)) {                       // owners of column j: half a warp (lanes 16*(ty&1)..+15)
-            const int b = j >> 4;
-            double colv[8];
 #pragma unroll
-            for (int aa = 0; aa < 8; ++aa) {
-                double v = 0.0;
+    for (int blk = 0; blk < 8; ++blk) {             // blk = j / 16 is a compile-time constant: static register indexing
+        for (int jj = 0; jj < 16; ++jj) {
+            const int j = blk * 16 + jj;
+            if (j >= n) break;
+            if (ty == jj) {                             // owners of column j: half a warp (lanes 16*(ty&1)..+15)
+                // diagonal element lives in lane tx == jj, slot [blk][blk]
+                double d = __shfl_sync(0xffffu << (tid & 16), t.r[blk][blk], jj + (tid & 16), 32);
+                bool ok = d > 0.0;                      // false for NaN and for <= 0
+                if (!ok && use_sub && sub > 0.0) { d = sub; ok = true; }
+                if (!ok) {
+                    if (tx == 0) atomicMin(fail_col, (unsigned long long)(col0 + j));
+                    d = 1.0;                            // keep going on garbage; the driver reports NOT_PD
+                }
+                // diagonal = sqrt(pivot) exactly; the column is scaled by the reciprocal (the reference
+                // divides by sqrt(pivot): same to ~1 ulp, without 8 serial FP64 divisions per thread)
+                const double sd = sqrt(d);
+                const double rsd = 1.0 / sd;
 #pragma unroll
-                for (int bb = 0; bb < 8; ++bb) if (bb == b) v = t.r[aa][bb];
-                colv[aa] = v;
+                for (int aa = 0; aa < 8; ++aa) {
+                    const int i = tx + 16 * aa;
+                    const double v = (i == j) ? sd : (i > j ? t.r[aa][blk] * rsd : 0.0);
+                    sL[i + j * 128] = v;
+                    t.r[aa][blk] = v;
+                }
             }
-            // diagonal element lives in lane tx == j%16, slot a == j/16
-            double d = 0.0;
+            __syncthreads();
+            double ci[8], ck[8];
 #pragma unroll
-            for (int aa = 0; aa < 8; ++aa) if (aa == (j >> 4)) d = colv[aa];
-            d = __shfl_sync(0xffffu << (tid & 16), d, (j & 15) + (tid & 16), 32);   // only this half-warp is converged here
-            bool ok = d > 0.0;                      // false for NaN and for <= 0
-            if (!ok && use_sub && sub > 0.0) { d = sub; ok = true; }
-            if (!ok) {
-                if (tx == 0) atomicMin(fail_col, (unsigned long long)(col0 + j));
-                d = 1.0;                            // keep going on garbage; the driver reports NOT_PD
-            }
-            const double sd = sqrt(d);
+            for (int aa = 0; aa < 8; ++aa) { const int i = tx + 16 * aa; ci[aa] = (i > j) ? sL[i + j * 128] : 0.0; }
 #pragma unroll
-            for (int aa = 0; aa < 8; ++aa) {
-                const int i = tx + 16 * aa;
-                double v = (i == j) ? sd : (i > j ? colv[aa] / sd : 0.0);
-                sL[i + j * 128] = v;
+            for (int b = 0; b < 8; ++b) { const int k = ty + 16 * b; ck[b] = (k > j) ? sL[k + j * 128] : 0.0; }
 #pragma unroll
-                for (int bb = 0; bb < 8; ++bb) if (bb == b) t.r[aa][bb] = v;
-            }
+            for (int aa = 0; aa < 8; ++aa)
+#pragma unroll
+                for (int b = 0; b < 8; ++b) t.r[aa][b] -= ci[aa] * ck[b];   // entries with i < k are never stored
         }
-        __syncthreads();
-        double ci[8], ck[8];
-#pragma unroll
-        for (int aa = 0; aa < 8; ++aa) { const int i = tx + 16 * aa; ci[aa] = (i > j) ? sL[i + j * 128] : 0.0; }
-#pragma unroll
-        for (int b = 0; b < 8; ++b) { const int k = ty + 16 * b; ck[b] = (k > j) ? sL[k + j * 128] : 0.0; }
-#pragma unroll
-        for (int aa = 0; aa < 8; ++aa)
-#pragma unroll
-            for (int b = 0; b < 8; ++b) t.r[aa][b] -= ci[aa] * ck[b];   // entries with i < k are never stored
     }
     // store L (lower triangle only)
 #pragma unroll
@@ -147,7 +148,7 @@ potf2_trtri_kernel(double* __restrict__ a, long long lda, int n, int use_sub, do
 int potf2(cudaStream_t st, double* a, size_t lda, int n, int use_sub, double sub, size_t col0, unsigned long long* fail_col,
           double* inv_out) {
     static std::once_flag once;
-    const int smem = (128 * 128 + 256) * 8;
+    const int smem = (128 * 128 + 384) * 8;
     std::call_once(once, [smem] { cudaFuncSetAttribute(potf2_trtri_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); });
     potf2_trtri_kernel<<<1, 256, smem, st>>>(a, (long long)lda, n, use_sub, sub, (long long)col0, fail_col, inv_out);
     NAB_LAUNCH_CHECK();
@@ -200,7 +201,7 @@ int trtri_blocks(cudaStream_t st, const double* t, ptrdiff_t rs, ptrdiff_t cs, s
                  const double* diag_abs, double* out) {
     if (n == 0) return NA_OK;
     static std::once_flag once;
-    const int smem = (IB * IB + 256) * 8;
+    const int smem = (IB * IB + 384) * 8;
     std::call_once(once, [smem] { cudaFuncSetAttribute(trtri_blocks_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); });
     const int nblk = (int)ceil_div(n, IB);
     trtri_blocks_kernel<<<nblk, 256, smem, st>>>(t, rs, cs, (long long)n, eff_lower ? 1 : 0, unit ? 1 : 0, diag_abs, out);
