@@ -7,6 +7,7 @@
 // O(n^3) work is restructured as recursive panel + TRSM + SYRK so that it runs on the DMMA GEMM
 // engine.  Parity is therefore on results (residuals, failure column), not on operation order.
 #include <algorithm>
+#include <cstdlib>
 
 #include "common.cuh"
 #include "kernels.cuh"
@@ -112,7 +113,15 @@ static int chol_rec(const CholCtx& c, size_t j0, size_t n) {
 // at most Rp CTAs, so the latency-bound panel is hidden behind the compute-bound update; the GEMM
 // kernels are persistent (one CTA per SM), which is why the split is expressed as grid limits.
 // ------------------------------------------------------------------------------------------------
-constexpr size_t CHOL_NB = 512;
+static size_t chol_nb() {
+    static size_t v = [] { const char* e = getenv("NAB_CHOL_NB"); size_t x = e ? (size_t)atoi(e) : 512; return x >= 128 ? x / 128 * 128 : 512; }();
+    return v;
+}
+static int chol_rp_override() {
+    static int v = [] { const char* e = getenv("NAB_CHOL_RP"); return e ? atoi(e) : 0; }();
+    return v;
+}
+#define CHOL_NB (chol_nb())
 
 static int chol_panel(const CholCtx& c, cudaStream_t sp, size_t n, size_t j, size_t jb, int sm_limit, double* tmp, size_t ldt) {
     for (size_t i = 0; i < jb; i += IBs) {
@@ -163,6 +172,7 @@ static int chol_lookahead(const CholCtx& c, size_t n) {
         if (rr > 0) {
             rp = (int)((double)sms * 2.0 * CHOL_NB / ((double)(n - jn) + 2.0 * CHOL_NB));
             rp = std::max(16, std::min(rp, sms - 28));
+            if (chol_rp_override() > 0) rp = chol_rp_override();
             cudaStreamWaitEvent(su, ev_p, 0);
             set_gemm_sm_limit(sms - rp);
             st = dgemm_device(su, true, rr, jb, rr, -1.0, pj + jr, 1, (ptrdiff_t)c.lda, pj + jr, (ptrdiff_t)c.lda, 1, 1.0,

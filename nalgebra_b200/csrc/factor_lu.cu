@@ -21,6 +21,7 @@ struct LuCtx {
     int* ipiv;                // device, absolute pivot rows
     int* iota;                // device, 0..mn-1
     void* ws_getf2; void* ws_perm;
+    int* seq_state;           // host counter of exchange sequence numbers used in ws_getf2
 };
 
 static int lu_apply_swaps(const LuCtx& c, size_t k0, size_t K, double* cols, size_t ncols) {
@@ -32,7 +33,7 @@ static int lu_apply_swaps(const LuCtx& c, size_t k0, size_t K, double* cols, siz
 static int lu_rec(const LuCtx& c, size_t j0, size_t nc) {
     if (nc == 0) return NA_OK;
     double* ajj = c.a + j0 + j0 * c.lda;
-    if (nc <= c.W) return getf2_panel(c.s, ajj, c.lda, c.M - j0, nc, j0, c.ipiv, c.ws_getf2);
+    if (nc <= c.W) return getf2_panel(c.s, ajj, c.lda, c.M - j0, nc, j0, c.ipiv, c.ws_getf2, c.seq_state);
     size_t n1 = round_up(nc / 2, c.W);
     if (n1 >= nc) n1 = nc - c.W;
     const size_t n2 = nc - n1;
@@ -68,10 +69,12 @@ int lu_device(cudaStream_t s, size_t M, size_t N, double* a, size_t lda, size_t*
     NAB_TRY(ipiv.alloc(mn * sizeof(int), s));
     NAB_TRY(iota.alloc(mn * sizeof(int), s));
     NAB_TRY(wsg.alloc(getf2_workspace_bytes(), s));
+    NAB_CUDA(cudaMemsetAsync(wsg.p, 0, getf2_workspace_bytes(), s));
+    int seq_state = 0;
     NAB_TRY(wsp.alloc(rowperm_workspace_bytes(M), s));
     NAB_TRY(iota_int(s, iota.as<int>(), mn, 0));
     NAB_TRY(iota_int(s, ipiv.as<int>(), mn, 0));
-    LuCtx c{s, a, lda, M, lu_leaf_width(M), ipiv.as<int>(), iota.as<int>(), wsg.p, wsp.p};
+    LuCtx c{s, a, lda, M, lu_leaf_width(M), ipiv.as<int>(), iota.as<int>(), wsg.p, wsp.p, &seq_state};
     NAB_TRY(lu_rec(c, 0, mn));
     if (N > mn) {   // wide matrix: the columns right of the square part
         double* ar = a + mn * lda;

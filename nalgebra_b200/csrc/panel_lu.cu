@@ -30,12 +30,30 @@ struct Getf2Params {
     int rp;                        // rows per CTA (multiple of 32)
     int j0;                        // global row/col offset of the panel (for ipiv values)
     int* ipiv;                     // ipiv[j0 + c] = global pivot row of column c
-    double* cand_val;              // [2][G]      |candidate|
-    int* cand_row;                 // [2][G]      candidate row (panel-relative)
-    double* cand_vals;             // [2][G][w]   the candidate's row of the panel
-    double* rowc;                  // [2][w]      current row c, published by its owner
-    unsigned int* counter;         // grid barrier, zeroed before launch
+    double2* xch;                  // [2][G][w + 2] (value, seq) pairs: |candidate|, candidate row, candidate's row values
+    double2* rowc;                 // [2][w]        (value, seq) pairs: current row c, published by its owner
+    int seq0;                      // sequence numbers already consumed in this workspace
 };
+
+// (value, seq) travel in one 16-byte word: a reader that sees the expected seq has the value.
+__device__ __forceinline__ void lu_st_pair(double2* p, double v, double seq) {
+    asm volatile("st.global.v2.f64 [%0], {%1, %2};" ::"l"(p), "d"(v), "d"(seq) : "memory");
+}
+__device__ __forceinline__ double lu_ld_pair(const double2* p, double seq) {
+    double x, y;
+    do {
+        asm volatile("ld.volatile.global.v2.f64 {%0, %1}, [%2];" : "=d"(x), "=d"(y) : "l"(p) : "memory");
+    } while (y != seq);
+    return x;
+}
+
+__device__ __forceinline__ void lu_ld_pair_raw(const double2* p, double& x, double& y) {
+    asm volatile("ld.volatile.global.v2.f64 {%0, %1}, [%2];" : "=d"(x), "=d"(y) : "l"(p) : "memory");
+}
+// candidate header: (|value|, seq << 32 | row) in one 16-byte word
+__device__ __forceinline__ double pack_seq_row(int seq, int row) {
+    return __longlong_as_double(((long long)seq << 32) | (unsigned int)row);
+}
 
 // candidate ordering of icamax: larger value wins; on equal values the lower row wins.
 __device__ __forceinline__ bool cand_better(double v1, int r1, double v2, int r2) {
@@ -47,11 +65,18 @@ __device__ __forceinline__ double pivot_key(double x, bool first) {
     return (v != v) ? (first ? __longlong_as_double(0x7ff0000000000000LL) : -1.0) : v;
 }
 
+__device__ long long g_getf2_prof[16];
+#ifdef NAB_GETF2_PROF   // per-phase cycle counters of CTA 0 / thread 0 (tools/lu_timing.py), off in the product build
+#define PROF(i) do { if (tid == 0 && cta == 0) { const long long t_ = clock64(); g_getf2_prof[i] += t_ - t_prev; t_prev = t_; } } while (0)
+#else
+#define PROF(i) do { (void)t_prev; } while (0)
+#endif
+
 __global__ void __launch_bounds__(256, 1) getf2_coop_kernel(const Getf2Params p) {
     extern __shared__ double sm[];
     const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, warp = tid >> 5;
     const int G = gridDim.x, cta = blockIdx.x;
-    const int w = p.w, rp = p.rp;
+    const int w = p.w, rp = p.rp, SL = w + 2;
     const int r_begin = cta * rp;
     const int nrows = max(0, min(rp, p.m - r_begin));
     double* s = sm;                        // [w][rp] column-major chunk
@@ -60,6 +85,7 @@ __global__ void __launch_bounds__(256, 1) getf2_coop_kernel(const Getf2Params p)
     __shared__ double red_v[8];
     __shared__ int red_r[8], red_w[8];
     __shared__ int s_lrow;
+    __shared__ double s_lval;
 
     for (int c = 0; c < w; ++c)
         for (int r = tid; r < nrows; r += nt) s[r + c * rp] = p.a[(long long)(r_begin + r) + (long long)c * p.lda];
@@ -74,10 +100,14 @@ __global__ void __launch_bounds__(256, 1) getf2_coop_kernel(const Getf2Params p)
     }
 
     const int ncol = min(w, p.m);
-    unsigned int bar_target = 0;
+    long long t_prev = clock64();
     for (int c = 0; c < ncol; ++c) {
         const int par = c & 1;
-        // ---- A. local winner ----
+        PROF(0);
+        const int iseq = p.seq0 + c + 1;
+        const double seq = (double)iseq;
+        double2* myslot = p.xch + ((size_t)par * G + cta) * SL;
+        // ---- A. local winner, published together with its whole row (no barrier, no fence) ----
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) {
             const double ov = __shfl_xor_sync(0xffffffffu, bv, o);
@@ -95,39 +125,38 @@ __global__ void __launch_bounds__(256, 1) getf2_coop_kernel(const Getf2Params p)
                 if (cand_better(ov, orow, v, r)) { v = ov; r = orow; }
             }
             if (lane == 0) {
-                p.cand_val[par * G + cta] = v;
-                p.cand_row[par * G + cta] = r;
-                s_lrow = r;
+                if (G > 1) lu_st_pair(myslot + 0, v, pack_seq_row(iseq, r));
+                s_lrow = r; s_lval = v;
             }
         }
         __syncthreads();
+        PROF(1);
+        int grow, gcta;
+        if (G == 1) {
+            // the whole panel lives in this CTA: everything stays in shared memory
+            grow = s_lrow; gcta = 0;
+            if (grow != 0x7fffffff)
+                for (int cc = tid; cc < w; cc += nt) { prow[cc] = s[grow + cc * rp]; crow[cc] = s[c + cc * rp]; }
+            __syncthreads();
+        } else {
         {
             const int lr = s_lrow;
-            if (lr != 0x7fffffff) {
-                double* dst = p.cand_vals + ((size_t)par * G + cta) * w;
-                for (int cc = tid; cc < w; cc += nt) dst[cc] = s[(lr - r_begin) + cc * rp];
-            }
+            if (lr != 0x7fffffff)
+                for (int cc = tid; cc < w; cc += nt) lu_st_pair(myslot + 2 + cc, s[(lr - r_begin) + cc * rp], seq);
             if (c >= r_begin && c < r_begin + nrows)
-                for (int cc = tid; cc < w; cc += nt) p.rowc[par * w + cc] = s[(c - r_begin) + cc * rp];
+                for (int cc = tid; cc < w; cc += nt) lu_st_pair(p.rowc + par * w + cc, s[(c - r_begin) + cc * rp], seq);
         }
-        // ---- B. grid barrier ----
-        bar_target += (unsigned int)G;
-        __syncthreads();
-        if (tid == 0) {
-            __threadfence();
-            atomicAdd(p.counter, 1u);
-            while (*((volatile unsigned int*)p.counter) < bar_target) {
-            }
-            __threadfence();
-        }
-        __syncthreads();
-        // ---- C. every CTA reduces the G candidates identically ----
-        double gv = -2.0; int grow = 0x7fffffff, gcta = -1;
+        // ---- B/C. every CTA reads all G candidate headers (one 16-byte word each, polled on its
+        //           sequence number) and reduces them identically ----
+        double gv = -2.0; grow = 0x7fffffff; gcta = -1;
         for (int i = tid; i < G; i += nt) {
-            const double sv = ((const volatile double*)p.cand_val)[par * G + i];
-            const int sr = ((const volatile int*)p.cand_row)[par * G + i];
+            const double2* slot = p.xch + ((size_t)par * G + i) * SL;
+            double sv, packed;
+            do { lu_ld_pair_raw(slot, sv, packed); } while ((int)(__double_as_longlong(packed) >> 32) != iseq);
+            const int sr = (int)(__double_as_longlong(packed) & 0xffffffffLL);
             if (cand_better(sv, sr, gv, grow)) { gv = sv; grow = sr; gcta = i; }
         }
+        PROF(2);
         const int nw_used = min(8, (G + 31) / 32);
         if (warp < nw_used) {
 #pragma unroll
@@ -143,13 +172,23 @@ __global__ void __launch_bounds__(256, 1) getf2_coop_kernel(const Getf2Params p)
         gv = red_v[0]; grow = red_r[0]; gcta = red_w[0];
         for (int i = 1; i < nw_used; ++i)
             if (cand_better(red_v[i], red_r[i], gv, grow)) { gv = red_v[i]; grow = red_r[i]; gcta = red_w[i]; }
-        // ---- D. pivot row and old row c ----
+        (void)gv;
+        PROF(3);
+        // ---- D. pivot row (the winner's published row) and old row c: both polls in flight together ----
         {
-            const volatile double* wv = p.cand_vals + ((size_t)par * G + gcta) * w;
-            const volatile double* rc = p.rowc + par * w;
-            for (int cc = tid; cc < w; cc += nt) { prow[cc] = wv[cc]; crow[cc] = rc[cc]; }
+            const double2* wv = p.xch + ((size_t)par * G + gcta) * SL + 2;
+            const double2* rc = p.rowc + par * w;
+            for (int cc = tid; cc < w; cc += nt) {
+                double a0, s0, a1, s1;
+                lu_ld_pair_raw(wv + cc, a0, s0); lu_ld_pair_raw(rc + cc, a1, s1);
+                while (s0 != seq) lu_ld_pair_raw(wv + cc, a0, s0);
+                while (s1 != seq) lu_ld_pair_raw(rc + cc, a1, s1);
+                prow[cc] = a0; crow[cc] = a1;
+            }
         }
         __syncthreads();
+        }   // G > 1
+        PROF(4);
         const double pivot = prow[c];
         const bool elim = pivot != 0.0;                  // lu.rs:107-110: an all-zero column is skipped
         if (cta == 0 && tid == 0) p.ipiv[p.j0 + c] = p.j0 + (elim ? grow : c);
@@ -161,48 +200,80 @@ __global__ void __launch_bounds__(256, 1) getf2_coop_kernel(const Getf2Params p)
             if (own_c) for (int cc = tid; cc < w; cc += nt) s[(c - r_begin) + cc * rp] = prow[cc];
             if (own_g || own_c) __syncthreads();
         }
-        // ---- F. scale by the reciprocal pivot, rank-1 update (unfused mul/add like the reference),
-        //         and pick up the candidates of column c+1 on the way ----
-        const double inv = 1.0 / pivot;
+        // ---- F. scale by the reciprocal pivot, then the rank-1 update (unfused mul/add like the reference)
+        //         on a 2D thread mapping (64 row lanes x 4 column groups) so that every thread has
+        //         independent work in flight; the candidates of column c+1 are picked up on the way ----
+        PROF(5);
+        const double inv = __drcp_rn(pivot);             // IEEE-rounded 1/diag, as gauss_step computes it
+        if (elim) {
+            for (int r = tid; r < nrows; r += nt)
+                if (r_begin + r > c) s[r + c * rp] = __dmul_rn(s[r + c * rp], inv);
+            __syncthreads();
+        }
+        PROF(6);
         bv = -1.0; br = 0x7fffffff;
-        for (int r = tid; r < nrows; r += nt) {
-            const int gr = r_begin + r;
-            if (gr <= c) continue;
-            if (elim) {
-                const double l = __dmul_rn(s[r + c * rp], inv);
-                s[r + c * rp] = l;
-                for (int cc = c + 1; cc < w; ++cc)
-                    s[r + cc * rp] = __dadd_rn(__dmul_rn(-prow[cc], l), s[r + cc * rp]);
-            }
-            if (c + 1 < w) {
-                const double v = pivot_key(s[r + (c + 1) * rp], gr == c + 1);
-                if (cand_better(v, gr, bv, br)) { bv = v; br = gr; }
+        {
+            // warp `warp` owns the columns cc = c+1+warp (mod 8); a lane owns rows lane, lane+32, ... in
+            // chunks of 8: the 8 multipliers stay in registers and the 8 row updates are independent.
+            const int rlo = max(0, c + 1 - r_begin);              // first local row below the pivot row
+            const double* lc = s + (size_t)c * rp;
+            for (int rb = (rlo / 256) * 256; rb < nrows; rb += 256) {
+                double l[8];
+                bool ok[8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const int r = rb + lane + 32 * i;
+                    ok[i] = r >= rlo && r < nrows;
+                    l[i] = ok[i] ? lc[r] : 0.0;
+                }
+                for (int cc = c + 1 + warp; cc < w; cc += 8) {
+                    double* col = s + (size_t)cc * rp;
+                    const double pv = -prow[cc];
+                    double v[8];
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) v[i] = ok[i] ? col[rb + lane + 32 * i] : 0.0;
+                    if (elim) {
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) v[i] = __dadd_rn(__dmul_rn(pv, l[i]), v[i]);
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) if (ok[i]) col[rb + lane + 32 * i] = v[i];
+                    }
+                    if (cc == c + 1) {                            // next pivot column: pick up its candidates
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) {
+                            if (!ok[i]) continue;
+                            const int gr = r_begin + rb + lane + 32 * i;
+                            const double key = pivot_key(v[i], gr == c + 1);
+                            if (cand_better(key, gr, bv, br)) { bv = key; br = gr; }
+                        }
+                    }
+                    if (!elim) break;                             // nothing to eliminate: only the candidate scan
+                }
             }
         }
+        __syncthreads();
+        PROF(7);
     }
     __syncthreads();
     for (int c = 0; c < w; ++c)
         for (int r = tid; r < nrows; r += nt) p.a[(long long)(r_begin + r) + (long long)c * p.lda] = s[r + c * rp];
 }
 
-// Factors the m x w panel at A[j0.., j0..j0+w).  ws: device workspace from getf2_workspace_bytes().
+// Factors the m x w panel at A[j0.., j0..j0+w).  ws: zero-initialised device workspace of
+// getf2_workspace_bytes(); *seq_state (host) carries the sequence numbers consumed so far in it.
 constexpr size_t kGetf2MaxCtas = 160;
-size_t getf2_workspace_bytes() {
-    return 256 + 2 * kGetf2MaxCtas * sizeof(double) + 2 * kGetf2MaxCtas * sizeof(int) +
-           (2 * kGetf2MaxCtas * kLuPanel + 2 * kLuPanel) * sizeof(double);
-}
+size_t getf2_workspace_bytes() { return (2 * kGetf2MaxCtas * (kLuPanel + 2) + 2 * kLuPanel) * sizeof(double2); }
 
-int getf2_panel(cudaStream_t st, double* a_panel, size_t lda, size_t m, size_t w, size_t j0, int* ipiv, void* ws) {
+int getf2_panel(cudaStream_t st, double* a_panel, size_t lda, size_t m, size_t w, size_t j0, int* ipiv, void* ws, int* seq_state) {
     if (m == 0 || w == 0) return NA_OK;
     if (w > (size_t)kLuPanel) { set_error("getf2: panel too wide"); return NA_EINVAL; }
     const int sms = ctx().sm_count;
     const size_t smem_budget = 200 * 1024;
-    // rows per CTA: as few CTAs as fit (fewer barrier participants), but at least 64 rows each
     size_t rp_max = (smem_budget - 2 * w * 8) / (w * 8);
     rp_max = rp_max / 32 * 32;
     size_t G = ceil_div(m, rp_max);
     if (G > (size_t)sms) { set_error("getf2: panel of %zu x %zu rows does not fit %d SMs of shared memory", m, w, sms); return NA_EINVAL; }
-    // spread rows evenly over G CTAs, but use more CTAs (up to 64) when rows are plentiful
+    // spread rows evenly; use more CTAs (up to 64) when rows are plentiful
     size_t G_pref = std::min<size_t>(std::min<size_t>(64, (size_t)sms), ceil_div(m, (size_t)128));
     if (G_pref > G) G = G_pref;
     size_t rp = round_up(ceil_div(m, G), 32);
@@ -212,13 +283,10 @@ int getf2_panel(cudaStream_t st, double* a_panel, size_t lda, size_t m, size_t w
     std::call_once(once, [] { cudaFuncSetAttribute(getf2_coop_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024); });
     Getf2Params p;
     p.a = a_panel; p.lda = (long long)lda; p.m = (int)m; p.w = (int)w; p.rp = (int)rp; p.j0 = (int)j0; p.ipiv = ipiv;
-    char* wsp = static_cast<char*>(ws);
-    p.counter = reinterpret_cast<unsigned int*>(wsp);
-    p.cand_val = reinterpret_cast<double*>(wsp + 256);
-    p.cand_vals = p.cand_val + 2 * kGetf2MaxCtas;
-    p.rowc = p.cand_vals + 2 * kGetf2MaxCtas * kLuPanel;
-    p.cand_row = reinterpret_cast<int*>(p.rowc + 2 * kLuPanel);
-    NAB_CUDA(cudaMemsetAsync(p.counter, 0, sizeof(unsigned int), st));
+    p.xch = static_cast<double2*>(ws);
+    p.rowc = p.xch + 2 * kGetf2MaxCtas * (kLuPanel + 2);
+    p.seq0 = *seq_state;
+    *seq_state += (int)w + 2 + ((w & 1) ? 1 : 0);      // keep the parity of seq0 even so buffers alternate cleanly
     void* args[] = {(void*)&p};
     NAB_CUDA(cudaLaunchCooperativeKernel((void*)getf2_coop_kernel, dim3((unsigned)G), dim3(256), args, smem, st));
     count_launch();
@@ -346,3 +414,9 @@ int iota_int(cudaStream_t st, int* p, size_t n, int offset) {
 }
 
 }  // namespace nab
+
+extern "C" __attribute__((visibility("default"))) int na_debug_getf2_prof(long long* out, int reset) {
+    cudaMemcpyFromSymbol(out, nab::g_getf2_prof, sizeof(long long) * 16);
+    if (reset) { long long z[16] = {0}; cudaMemcpyToSymbol(nab::g_getf2_prof, z, sizeof(z)); }
+    return 0;
+}
