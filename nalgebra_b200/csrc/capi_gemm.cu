@@ -77,6 +77,70 @@ static int check_view(const char* name, const void* p, ptrdiff_t rs, ptrdiff_t c
     return NA_OK;
 }
 
+// ------------------------------------------------------------------------------------------------
+// Pipelined host-pointer GEMM for large column-major operands: C is cut into a gr x gc grid of
+// chunks visited in snake order, so that each chunk needs at most one new row block of A or column
+// block of B.  H2D copies (stream h2d), chunk GEMMs (stream cmp) and D2H copies of finished chunks
+// (stream d2h) overlap; only the first A/B pieces and the last C chunk are exposed.
+// ------------------------------------------------------------------------------------------------
+static int dgemm_host_pipelined(size_t m, size_t k, size_t n, double alpha, const double* a, size_t lda,
+                                const double* b, size_t ldb, double beta, double* c, size_t ldc) {
+    Context& cx = ctx();
+    cudaStream_t cmp = cx.stream, h2d = cx.stream2, d2h = nullptr;
+    NAB_CUDA(cudaStreamCreateWithFlags(&d2h, cudaStreamNonBlocking));
+    const size_t gr = m >= 8192 ? 4 : 2, gc = n >= 8192 ? 4 : 2;
+    const size_t mc = round_up(ceil_div(m, gr), 128), nc = round_up(ceil_div(n, gc), 128);
+    const size_t nbr = ceil_div(m, mc), nbc = ceil_div(n, nc);
+    Scratch da, db, dc;
+    const size_t ldda = round_up(m, 2), lddb = round_up(k, 2), lddc = round_up(m, 2);
+    int st = da.alloc(ldda * k * 8, cmp);
+    if (st == NA_OK) st = db.alloc(lddb * n * 8, cmp);
+    if (st == NA_OK) st = dc.alloc(lddc * n * 8, cmp);
+    std::vector<cudaEvent_t> ev_a(nbr, nullptr), ev_b(nbc, nullptr), ev_c(nbr * nbc, nullptr), ev_cin(nbr * nbc, nullptr);
+    cudaEvent_t ev_alloc = nullptr;
+    auto mk = [](cudaEvent_t& e) { return cudaEventCreateWithFlags(&e, cudaEventDisableTiming); };
+    if (st == NA_OK) {
+        mk(ev_alloc); cudaEventRecord(ev_alloc, cmp);
+        cudaStreamWaitEvent(h2d, ev_alloc, 0); cudaStreamWaitEvent(d2h, ev_alloc, 0);
+    }
+    std::vector<bool> a_up(nbr, false), b_up(nbc, false);
+    for (size_t step = 0; st == NA_OK && step < nbr * nbc; ++step) {
+        const size_t bi = step / nbc, jj = step % nbc, bj = (bi % 2 == 0) ? jj : nbc - 1 - jj;   // snake order
+        const size_t r0 = bi * mc, rows = std::min(mc, m - r0), c0 = bj * nc, cols = std::min(nc, n - c0);
+        if (!a_up[bi]) {
+            if (cudaMemcpy2DAsync(da.as<double>() + r0, ldda * 8, a + r0, lda * 8, rows * 8, k, cudaMemcpyHostToDevice, h2d) != cudaSuccess) { st = NA_ECUDA; break; }
+            mk(ev_a[bi]); cudaEventRecord(ev_a[bi], h2d); a_up[bi] = true;
+        }
+        if (!b_up[bj]) {
+            if (cudaMemcpy2DAsync(db.as<double>() + c0 * lddb, lddb * 8, b + c0 * ldb, ldb * 8, k * 8, cols, cudaMemcpyHostToDevice, h2d) != cudaSuccess) { st = NA_ECUDA; break; }
+            mk(ev_b[bj]); cudaEventRecord(ev_b[bj], h2d); b_up[bj] = true;
+        }
+        double* dcc = dc.as<double>() + r0 + c0 * lddc;
+        if (beta != 0.0) {      // C is only read (and therefore only uploaded) when beta != 0
+            if (cudaMemcpy2DAsync(dcc, lddc * 8, c + r0 + c0 * ldc, ldc * 8, rows * 8, cols, cudaMemcpyHostToDevice, h2d) != cudaSuccess) { st = NA_ECUDA; break; }
+            mk(ev_cin[step]); cudaEventRecord(ev_cin[step], h2d);
+            cudaStreamWaitEvent(cmp, ev_cin[step], 0);
+        }
+        cudaStreamWaitEvent(cmp, ev_a[bi], 0);
+        cudaStreamWaitEvent(cmp, ev_b[bj], 0);
+        st = dgemm_device(cmp, false, rows, k, cols, alpha, da.as<double>() + r0, 1, (ptrdiff_t)ldda,
+                          db.as<double>() + c0 * lddb, 1, (ptrdiff_t)lddb, beta, dcc, 1, (ptrdiff_t)lddc);
+        if (st != NA_OK) break;
+        mk(ev_c[step]); cudaEventRecord(ev_c[step], cmp);
+        cudaStreamWaitEvent(d2h, ev_c[step], 0);
+        if (cudaMemcpy2DAsync(c + r0 + c0 * ldc, ldc * 8, dcc, lddc * 8, rows * 8, cols, cudaMemcpyDeviceToHost, d2h) != cudaSuccess) { st = NA_ECUDA; break; }
+    }
+    cudaError_t e1 = cudaStreamSynchronize(d2h), e2 = cudaStreamSynchronize(h2d), e3 = cudaStreamSynchronize(cmp);
+    for (auto* v : {&ev_a, &ev_b, &ev_c, &ev_cin}) for (cudaEvent_t e : *v) if (e) cudaEventDestroy(e);
+    if (ev_alloc) cudaEventDestroy(ev_alloc);
+    cudaStreamDestroy(d2h);
+    if (st != NA_OK) { if (st == NA_ECUDA) set_error("pipelined gemm: CUDA copy failed (%s)", cudaGetErrorString(cudaGetLastError())); return st; }
+    if (e1 != cudaSuccess) return cuda_fail(e1, "pipelined gemm d2h", __FILE__, __LINE__);
+    if (e2 != cudaSuccess) return cuda_fail(e2, "pipelined gemm h2d", __FILE__, __LINE__);
+    if (e3 != cudaSuccess) return cuda_fail(e3, "pipelined gemm compute", __FILE__, __LINE__);
+    return NA_OK;
+}
+
 }  // namespace nab
 
 extern "C" {
@@ -105,6 +169,10 @@ int na_dgemm(size_t m, size_t k, size_t n, double alpha, const double* a, ptrdif
         NAB_TRY(scale_strided(s, sc.buf.as<double>(), sc.rs, sc.cs, m, n, beta));
         return stage_out(s, sc, c, rsc, csc, m, n);
     }
+    // large plain column-major operands (VecStorage): overlap the PCIe copies with the compute
+    if (rsa == 1 && rsb == 1 && rsc == 1 && m >= 2048 && n >= 2048 && k >= 512 &&
+        csa >= (ptrdiff_t)m && csb >= (ptrdiff_t)k && csc >= (ptrdiff_t)m)
+        return dgemm_host_pipelined(m, k, n, alpha, a, (size_t)csa, b, (size_t)csb, beta, c, (size_t)csc);
     Staged sa, sb, sc;
     NAB_TRY(stage_in(s, sa, a, rsa, csa, m, k, true));
     NAB_TRY(stage_in(s, sb, b, rsb, csb, k, n, true));
