@@ -7,6 +7,7 @@
 // half), so all O(n^3) work is GEMM/TRSM on the DMMA engine and the leaves are the cooperative
 // GETF2 panel kernel.  Whole rows are swapped, so the packed result has the reference's layout
 // (identical to LAPACK getrf).  Everything stays on the device: no host pivoting.
+#include <algorithm>
 #include <vector>
 
 #include "common.cuh"
@@ -51,6 +52,75 @@ static int lu_rec(const LuCtx& c, size_t j0, size_t nc) {
     return lu_apply_swaps(c, j0 + n1, std::min(n2, c.M - j0 - n1), c.a + j0 * c.lda, n1);
 }
 
+// ------------------------------------------------------------------------------------------------
+// Large square-ish matrices: right-looking outer blocks of LU_NB columns with one-step look-ahead.
+//   panel(j)  : lu_rec on columns [j, j+nb) (leaves of 64 columns -> the cooperative GETF2 needs
+//               <= 43 SMs), on the caller's stream, GEMMs limited to `rp` CTAs;
+//   la(j)     : row swaps + TRSM + GEMM of panel j on the NEXT panel's columns, whole GPU;
+//   bulk(j)   : the same on all remaining columns (and the row swaps on the columns left of the
+//               panel), on a second stream with the remaining SMs, concurrent with panel(j + nb).
+// ------------------------------------------------------------------------------------------------
+constexpr size_t LU_NB = 512;
+
+static int lu_right_update(const LuCtx& c, cudaStream_t st, size_t j, size_t jb, size_t x0, size_t nx, const void* ws_outer) {
+    if (nx == 0) return NA_OK;
+    double* ax = c.a + x0 * c.lda;                      // column x0, row 0
+    NAB_TRY(rowperm_apply(st, ax, c.lda, nx, std::min(2 * jb, c.M), ws_outer, c.M));
+    NAB_TRY(trsm_left(st, true, true, jb, c.a + j + j * c.lda, 1, (ptrdiff_t)c.lda, nullptr, nullptr, ax + j, 1, (ptrdiff_t)c.lda, nx));
+    const size_t m2 = c.M - j - jb;
+    if (m2 > 0)
+        NAB_TRY(dgemm_device(st, false, m2, jb, nx, -1.0, c.a + (j + jb) + j * c.lda, 1, (ptrdiff_t)c.lda, ax + j, 1, (ptrdiff_t)c.lda,
+                             1.0, ax + j + jb, 1, (ptrdiff_t)c.lda));
+    return NA_OK;
+}
+
+static int lu_lookahead(LuCtx c, size_t N, size_t mn) {
+    cudaStream_t sp = c.s, su = nullptr;
+    cudaEvent_t ev_p = nullptr, ev_u = nullptr;
+    NAB_CUDA(cudaStreamCreateWithFlags(&su, cudaStreamNonBlocking));
+    NAB_CUDA(cudaEventCreateWithFlags(&ev_p, cudaEventDisableTiming));
+    NAB_CUDA(cudaEventCreateWithFlags(&ev_u, cudaEventDisableTiming));
+    Scratch wso[2];
+    int st = wso[0].alloc(rowperm_workspace_bytes(c.M), sp);
+    if (st == NA_OK) st = wso[1].alloc(rowperm_workspace_bytes(c.M), sp);
+    const int sms = ctx().sm_count;
+    const int g_getf2 = (int)ceil_div(c.M, (size_t)384) + 2;          // CTAs the 64-wide GETF2 leaf needs at full height
+    bool bulk_pending = false;
+    int par = 0;
+    if (st == NA_OK) st = lu_rec(c, 0, std::min(LU_NB, mn));
+    for (size_t j = 0; st == NA_OK; j += LU_NB) {
+        const size_t jb = std::min(LU_NB, mn - j), jn = j + jb;
+        const size_t jbn = jn < mn ? std::min(LU_NB, mn - jn) : 0;
+        st = rowperm_build(sp, c.iota + j, c.ipiv + j, jb, 1, c.M, wso[par].p);
+        if (st != NA_OK) break;
+        cudaEventRecord(ev_p, sp);
+        // la(j): the next panel's columns, whole GPU (needs bulk(j - nb) finished on them)
+        if (bulk_pending) cudaStreamWaitEvent(sp, ev_u, 0);
+        st = lu_right_update(c, sp, j, jb, jn, jbn, wso[par].p);
+        if (st != NA_OK) break;
+        // bulk(j) on the second stream: left swaps + everything right of the next panel
+        int rp = std::max(g_getf2, std::min(sms / 2, (int)((double)sms * 3.0 * LU_NB / ((double)(c.M - jn) + 3.0 * LU_NB))));
+        cudaStreamWaitEvent(su, ev_p, 0);
+        set_gemm_sm_limit(jbn ? sms - rp : 0);
+        st = rowperm_apply(su, c.a, c.lda, j, std::min(2 * jb, c.M), wso[par].p, c.M);
+        if (st == NA_OK) st = lu_right_update(c, su, j, jb, jn + jbn, N - (jn + jbn), wso[par].p);
+        set_gemm_sm_limit(0);
+        if (st != NA_OK) break;
+        cudaEventRecord(ev_u, su);
+        bulk_pending = true;
+        if (jbn == 0) break;
+        // panel(j + nb) on the caller's stream, concurrently with bulk(j)
+        set_gemm_sm_limit(rp);
+        st = lu_rec(c, jn, jbn);
+        set_gemm_sm_limit(0);
+        par ^= 1;
+    }
+    if (bulk_pending) cudaStreamWaitEvent(sp, ev_u, 0);
+    cudaStreamSynchronize(su);
+    cudaEventDestroy(ev_p); cudaEventDestroy(ev_u); cudaStreamDestroy(su);
+    return st;
+}
+
 static size_t lu_leaf_width(size_t M) {
     if (M <= 28000) return 128;
     if (M <= 56000) return 64;
@@ -75,8 +145,14 @@ int lu_device(cudaStream_t s, size_t M, size_t N, double* a, size_t lda, size_t*
     NAB_TRY(iota_int(s, iota.as<int>(), mn, 0));
     NAB_TRY(iota_int(s, ipiv.as<int>(), mn, 0));
     LuCtx c{s, a, lda, M, lu_leaf_width(M), ipiv.as<int>(), iota.as<int>(), wsg.p, wsp.p, &seq_state};
-    NAB_TRY(lu_rec(c, 0, mn));
-    if (N > mn) {   // wide matrix: the columns right of the square part
+    const bool lookahead = mn >= 4 * LU_NB && M <= 20000;
+    if (lookahead) {
+        c.W = 64;
+        NAB_TRY(lu_lookahead(c, N, mn));
+    } else {
+        NAB_TRY(lu_rec(c, 0, mn));
+    }
+    if (N > mn && !lookahead) {   // wide matrix: the columns right of the square part
         double* ar = a + mn * lda;
         NAB_TRY(lu_apply_swaps(c, 0, mn, ar, N - mn));
         NAB_TRY(trsm_left(s, true, true, mn, a, 1, (ptrdiff_t)lda, nullptr, nullptr, ar, 1, (ptrdiff_t)lda, N - mn));
