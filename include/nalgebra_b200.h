@@ -164,6 +164,25 @@ NAB_API int na_tri_solve_f64(int lower, int trans, int unit_diag, size_t n, cons
 NAB_API int na_tri_solve_f64_dev(int lower, int trans, int unit_diag, size_t n, const double* t, size_t ldt,
                          double* b, size_t ldb, size_t nrhs, void* stream);
 
+/* ---- building blocks of the multi-GPU (1D block-cyclic) factorizations, device pointers ------ */
+/* General triangular solve with many right-hand sides, in place on B (m x n, ldb):
+ *   side_right = 0:  op(T) X = B  (T is m x m)      side_right = 1:  X op(T) = B  (T is n x n)
+ * lower / trans / unit_diag as in na_tri_solve_f64.  No singularity check (the blocked drivers'
+ * *_unchecked use, src/linalg/solve.rs:488-580). */
+NAB_API int na_trsm_f64_dev(int side_right, int lower, int trans, int unit_diag, size_t m, size_t n,
+                            const double* t, size_t ldt, double* b, size_t ldb, void* stream);
+/* C <- alpha*A*B + beta*C restricted to the lower trapezoid (row >= col) of the m x n (m >= n)
+ * column-major C: the SYRK-shaped trailing update of Cholesky (cholesky.rs:226-235 never touches the
+ * strict upper triangle, and neither does this). */
+NAB_API int na_dgemm_lower_dev(size_t m, size_t k, size_t n, double alpha,
+                               const double* a, ptrdiff_t rsa, ptrdiff_t csa,
+                               const double* b, ptrdiff_t rsb, ptrdiff_t csb,
+                               double beta, double* c, size_t ldc, void* stream);
+/* The block [row0, +nrows) x [col0, +ncols) of the n x n SPD test matrix (B + B^T)/2 + n*I,
+ * B(i,j) = rand01(seed, i + j*n)  (Cfg 3 (ii)). */
+NAB_API int na_fill_spd_block_dev(double* a, size_t nrows, size_t ncols, size_t lda, uint64_t seed,
+                                  size_t row0, size_t col0, size_t n, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

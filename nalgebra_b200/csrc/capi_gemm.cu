@@ -193,4 +193,10 @@ int na_fill_uniform_block_dev(double* a, size_t nrows, size_t ncols, size_t lda,
     return fill_uniform(static_cast<cudaStream_t>(stream), a, nrows, ncols, lda, seed, row0, col0, global_rows);
 }
 
+int na_fill_spd_block_dev(double* a, size_t nrows, size_t ncols, size_t lda, uint64_t seed,
+                          size_t row0, size_t col0, size_t n, void* stream) {
+    NAB_TRY(ensure_init());
+    return fill_spd(static_cast<cudaStream_t>(stream), a, nrows, ncols, lda, seed, row0, col0, n);
+}
+
 }  // extern "C"

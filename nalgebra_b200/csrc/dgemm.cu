@@ -379,6 +379,26 @@ int copy_strided(cudaStream_t s, double* dst, ptrdiff_t rsd, ptrdiff_t csd, cons
     return NA_OK;
 }
 
+// (B + B^T)/2 + n*I for the block [row0,+nrows) x [col0,+ncols), B(i,j) = rand01(seed, i + j*n)
+__global__ void fill_spd_kernel(double* __restrict__ a, long long nrows, long long ncols, long long lda, uint64_t seed,
+                                long long row0, long long col0, long long n) {
+    const long long total = nrows * ncols;
+    for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+        const long long r = idx % nrows, c = idx / nrows, gi = row0 + r, gj = col0 + c;
+        const uint64_t k = (seed + 1) * 0x9E3779B97F4A7C15ULL;
+        const double bij = (double)(mix64((uint64_t)(gi + gj * n) + k) >> 11) * (1.0 / 9007199254740992.0);
+        const double bji = (double)(mix64((uint64_t)(gj + gi * n) + k) >> 11) * (1.0 / 9007199254740992.0);
+        a[r + c * lda] = (bij + bji) * 0.5 + (gi == gj ? (double)n : 0.0);
+    }
+}
+int fill_spd(cudaStream_t s, double* a, size_t nrows, size_t ncols, size_t lda, uint64_t seed, size_t row0, size_t col0, size_t n) {
+    if (nrows == 0 || ncols == 0) return NA_OK;
+    int blocks = (int)std::min<size_t>(ceil_div(nrows * ncols, 256), (size_t)ctx().sm_count * 16);
+    fill_spd_kernel<<<blocks, 256, 0, s>>>(a, (long long)nrows, (long long)ncols, (long long)lda, seed, (long long)row0, (long long)col0, (long long)n);
+    NAB_LAUNCH_CHECK();
+    return NA_OK;
+}
+
 int pack_strided(cudaStream_t s, double* dst, size_t ldd, const double* src, ptrdiff_t rs, ptrdiff_t cs, size_t rows, size_t cols) {
     if (rows == 0 || cols == 0) return NA_OK;
     dim3 grid((unsigned)ceil_div(rows, 32), (unsigned)ceil_div(cols, 32)), block(32, 8);

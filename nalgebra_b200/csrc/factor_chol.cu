@@ -304,6 +304,33 @@ int na_tri_solve_f64_dev(int lower, int trans, int unit_diag, size_t n, const do
     return trsm_left(s, eff_lower, unit_diag != 0, n, t, rsm, csm, nullptr, nullptr, b, 1, (ptrdiff_t)ldb, nrhs);
 }
 
+int na_trsm_f64_dev(int side_right, int lower, int trans, int unit_diag, size_t m, size_t n,
+                    const double* t, size_t ldt, double* b, size_t ldb, void* stream) {
+    NAB_TRY(ensure_init());
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    if (m == 0 || n == 0) return NA_OK;
+    const size_t nt = side_right ? n : m;
+    if (!t || !b || ldt < nt || ldb < m) { set_error("trsm: bad arguments"); return NA_EINVAL; }
+    if (!side_right) {
+        const bool eff_lower = (lower != 0) != (trans != 0);
+        const ptrdiff_t rsm = trans ? (ptrdiff_t)ldt : 1, csm = trans ? 1 : (ptrdiff_t)ldt;
+        return trsm_left(s, eff_lower, unit_diag != 0, m, t, rsm, csm, nullptr, nullptr, b, 1, (ptrdiff_t)ldb, n);
+    }
+    // X op(T) = B  <=>  op(T)^T X^T = B^T: a left solve on the transposed view of B
+    const bool mt = trans == 0;                         // M = op(T)^T is T^T when op = T, and T when op = T^T
+    const bool eff_lower = (lower != 0) != mt;
+    const ptrdiff_t rsm = mt ? (ptrdiff_t)ldt : 1, csm = mt ? 1 : (ptrdiff_t)ldt;
+    return trsm_left(s, eff_lower, unit_diag != 0, n, t, rsm, csm, nullptr, nullptr, b, (ptrdiff_t)ldb, 1, m);
+}
+
+int na_dgemm_lower_dev(size_t m, size_t k, size_t n, double alpha, const double* a, ptrdiff_t rsa, ptrdiff_t csa,
+                       const double* b, ptrdiff_t rsb, ptrdiff_t csb, double beta, double* c, size_t ldc, void* stream) {
+    NAB_TRY(ensure_init());
+    if (m < n) { set_error("gemm_lower: needs m >= n"); return NA_EINVAL; }
+    if (k == 0) { set_error("gemm_lower: k == 0 is not supported"); return NA_EINVAL; }
+    return dgemm_device(static_cast<cudaStream_t>(stream), true, m, k, n, alpha, a, rsa, csa, b, rsb, csb, beta, c, 1, (ptrdiff_t)ldc);
+}
+
 int na_tri_solve_f64(int lower, int trans, int unit_diag, size_t n, const double* t, size_t ldt,
                      double* b, size_t ldb, size_t nrhs) {
     NAB_TRY(ensure_init());

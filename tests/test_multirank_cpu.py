@@ -52,3 +52,76 @@ def test_sharded_gemm_two_ranks(tmp_path, oracle):
     oracle.gemm(1.0, a, b, 0.0, ref)
     assert np.abs(full - ref).max() <= 4 * n * np.finfo(np.float64).eps * np.linalg.norm(a) * np.linalg.norm(b)
     assert abs(np.load(tmp_path / "chk.npy")[0] - ref.sum()) <= 1e-9 * abs(ref.sum())
+
+
+# ---------------------------------------------------------------------------------------------------
+# block-cyclic distributed Cholesky: ownership / look-ahead / broadcast logic on CPU (gloo, world 2 and 3)
+# with the oracle plugged in as the local arithmetic
+# ---------------------------------------------------------------------------------------------------
+class _OracleOps:
+    """Same interface as nalgebra_b200.distributed.DeviceOps, CPU tensors + the oracle (checker side)."""
+
+    def __init__(self):
+        import ctypes as C
+        import oracle as O
+        self.C, self.O = C, O
+
+    def _np(self, ptr, count):
+        return np.frombuffer((self.C.c_double * count).from_address(ptr), dtype=np.float64)
+
+    def _mat(self, ptr, rows, cols, ld):
+        flat = self._np(ptr, ld * (cols - 1) + rows)
+        return np.lib.stride_tricks.as_strided(flat, shape=(rows, cols), strides=(8, 8 * ld))
+
+    def empty(self, numel):
+        return torch.zeros(numel, dtype=torch.float64)
+
+    def fill_spd(self, ptr, nrows, ncols, ld, seed, row0, col0, n):
+        i = (np.arange(row0, row0 + nrows)[:, None]).astype(np.uint64); j = (np.arange(col0, col0 + ncols)[None, :]).astype(np.uint64)
+        bij = self.O.rand01(seed, (i + j * np.uint64(n)).ravel()).reshape(nrows, ncols)
+        bji = self.O.rand01(seed, (j + i * np.uint64(n)).ravel()).reshape(nrows, ncols)
+        self._mat(ptr, nrows, ncols, ld)[...] = (bij + bji) * 0.5 + n * (i == j)
+
+    def potrf(self, ptr, w, ld):
+        fail = self.C.c_size_t(0)
+        return self.O.lib().na_oracle_cholesky_f64(w, ptr, ld, 0, 0.0, self.C.addressof(fail))
+
+    def trsm_right_lower_trans(self, m, w, t_ptr, ldt, b_ptr, ldb):
+        import scipy.linalg as sl
+        t = np.tril(self._mat(t_ptr, w, w, ldt)); b = self._mat(b_ptr, m, w, ldb)
+        b[...] = sl.solve_triangular(t, b.T, lower=True).T
+
+    def syrk_lower_update(self, m, k, n, p_ptr, ldp, c_ptr, ldc):
+        p = self._mat(p_ptr, m, k, ldp); c = self._mat(c_ptr, m, n, ldc)
+        upd = p @ p[:n, :].T
+        mask = np.arange(m)[:, None] >= np.arange(n)[None, :]
+        c[mask] -= upd[mask]
+
+
+def _chol_worker(rank, world, port, n, nb, out_dir, lookahead):
+    sys.path.insert(0, ROOT)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from nalgebra_b200.distributed import ColumnBlockCyclic, cholesky_block_cyclic
+    A = ColumnBlockCyclic(n, nb, rank, world, _OracleOps())
+    A.fill_spd(5)
+    st = cholesky_block_cyclic(A, lookahead=lookahead)
+    full = A.gather_to(0)
+    if rank == 0:
+        np.save(os.path.join(out_dir, f"l_{world}_{int(lookahead)}.npy"), full.numpy())
+        np.save(os.path.join(out_dir, f"st_{world}_{int(lookahead)}.npy"), np.array([st]))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_block_cyclic_cholesky_logic(tmp_path, oracle):
+    n, nb = 100, 16                      # 7 blocks, the last one narrow
+    spd = oracle.spd_wellcond(n, 5)
+    lref = np.tril(oracle.cholesky(spd))
+    for world, port in ((2, 29621), (3, 29622)):
+        mp.spawn(_chol_worker, args=(world, port, n, nb, str(tmp_path), True), nprocs=world, join=True)
+        got = np.load(tmp_path / f"l_{world}_1.npy")
+        assert np.load(tmp_path / f"st_{world}_1.npy")[0] == 0
+        assert np.abs(np.tril(got) - lref).max() <= 1e-12 * np.abs(lref).max()
+        assert np.array_equal(np.triu(got, 1), np.triu(spd, 1))          # strict upper never touched
