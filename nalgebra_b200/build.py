@@ -23,7 +23,7 @@ NVCC_FLAGS = [
     "-O3", "-lineinfo", "-std=c++17",
     "-Xcompiler", "-fPIC,-fvisibility=hidden",
     "-Xptxas", "-v",
-]
+] + os.environ.get("NAB_EXTRA_NVCC_FLAGS", "").split()
 
 
 def _sources():

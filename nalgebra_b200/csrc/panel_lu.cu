@@ -72,6 +72,15 @@ __device__ long long g_getf2_prof[16];
 #define PROF(i) do { (void)t_prev; } while (0)
 #endif
 
+// Software-pipelined column loop.  For column c every CTA
+//   1. receives the candidates of column c (headers -> identical reduction in every CTA -> the
+//      winner's published row = pivot row, and the old row c),
+//   2. swaps, scales column c by the reciprocal pivot,
+//   3. updates ONLY column c+1, finds its local pivot candidate and publishes it at once -- together
+//      with that candidate's row (and row c+1), whose not-yet-updated entries are produced on the fly
+//      with exactly the arithmetic step 4 will apply to them --
+//   4. and only then applies the rank-1 update to columns c+2.. : the all-to-all exchange of column
+//      c+1 travels through L2 while this bulk update runs.
 __global__ void __launch_bounds__(256, 1) getf2_coop_kernel(const Getf2Params p) {
     extern __shared__ double sm[];
     const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, warp = tid >> 5;
@@ -85,29 +94,15 @@ __global__ void __launch_bounds__(256, 1) getf2_coop_kernel(const Getf2Params p)
     __shared__ double red_v[8];
     __shared__ int red_r[8], red_w[8];
     __shared__ int s_lrow;
-    __shared__ double s_lval;
 
     for (int c = 0; c < w; ++c)
         for (int r = tid; r < nrows; r += nt) s[r + c * rp] = p.a[(long long)(r_begin + r) + (long long)c * p.lda];
     __syncthreads();
-
-    // candidates of column 0
-    double bv = -1.0; int br = 0x7fffffff;
-    for (int r = tid; r < nrows; r += nt) {
-        const int gr = r_begin + r;
-        const double v = pivot_key(s[r], gr == 0);
-        if (cand_better(v, gr, bv, br)) { bv = v; br = gr; }
-    }
-
     const int ncol = min(w, p.m);
     long long t_prev = clock64();
-    for (int c = 0; c < ncol; ++c) {
-        const int par = c & 1;
-        PROF(0);
-        const int iseq = p.seq0 + c + 1;
-        const double seq = (double)iseq;
-        double2* myslot = p.xch + ((size_t)par * G + cta) * SL;
-        // ---- A. local winner, published together with its whole row (no barrier, no fence) ----
+
+    // Local winner of (bv, br) over the CTA -> s_lrow; publishes the header of column `col`.
+    auto reduce_and_publish_header = [&](double bv, int br, int col) {
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) {
             const double ov = __shfl_xor_sync(0xffffffffu, bv, o);
@@ -125,57 +120,71 @@ __global__ void __launch_bounds__(256, 1) getf2_coop_kernel(const Getf2Params p)
                 if (cand_better(ov, orow, v, r)) { v = ov; r = orow; }
             }
             if (lane == 0) {
-                if (G > 1) lu_st_pair(myslot + 0, v, pack_seq_row(iseq, r));
-                s_lrow = r; s_lval = v;
+                if (G > 1) lu_st_pair(p.xch + ((size_t)(col & 1) * G + cta) * SL, v, pack_seq_row(p.seq0 + col + 1, r));
+                s_lrow = r;
             }
         }
         __syncthreads();
-        PROF(1);
+    };
+
+    // ---- prologue: candidates of column 0 (no pending update) ----
+    {
+        double bv = -1.0; int br = 0x7fffffff;
+        for (int r = tid; r < nrows; r += nt) {
+            const int gr = r_begin + r;
+            const double v = pivot_key(s[r], gr == 0);
+            if (cand_better(v, gr, bv, br)) { bv = v; br = gr; }
+        }
+        reduce_and_publish_header(bv, br, 0);
+        if (G > 1) {
+            const double seq = (double)(p.seq0 + 1);
+            const int lr = s_lrow;
+            double2* myslot = p.xch + (size_t)cta * SL;
+            if (lr != 0x7fffffff)
+                for (int cc = tid; cc < w; cc += nt) lu_st_pair(myslot + 2 + cc, s[(lr - r_begin) + cc * rp], seq);
+            if (r_begin == 0 && nrows > 0)
+                for (int cc = tid; cc < w; cc += nt) lu_st_pair(p.rowc + cc, s[cc * rp], seq);
+        }
+    }
+
+    for (int c = 0; c < ncol; ++c) {
+        const int par = c & 1;
+        const int iseq = p.seq0 + c + 1;
+        const double seq = (double)iseq;
+        PROF(0);
+        // ---- 1. receive column c ----
         int grow, gcta;
         if (G == 1) {
-            // the whole panel lives in this CTA: everything stays in shared memory
             grow = s_lrow; gcta = 0;
             if (grow != 0x7fffffff)
                 for (int cc = tid; cc < w; cc += nt) { prow[cc] = s[grow + cc * rp]; crow[cc] = s[c + cc * rp]; }
             __syncthreads();
         } else {
-        {
-            const int lr = s_lrow;
-            if (lr != 0x7fffffff)
-                for (int cc = tid; cc < w; cc += nt) lu_st_pair(myslot + 2 + cc, s[(lr - r_begin) + cc * rp], seq);
-            if (c >= r_begin && c < r_begin + nrows)
-                for (int cc = tid; cc < w; cc += nt) lu_st_pair(p.rowc + par * w + cc, s[(c - r_begin) + cc * rp], seq);
-        }
-        // ---- B/C. every CTA reads all G candidate headers (one 16-byte word each, polled on its
-        //           sequence number) and reduces them identically ----
-        double gv = -2.0; grow = 0x7fffffff; gcta = -1;
-        for (int i = tid; i < G; i += nt) {
-            const double2* slot = p.xch + ((size_t)par * G + i) * SL;
-            double sv, packed;
-            do { lu_ld_pair_raw(slot, sv, packed); } while ((int)(__double_as_longlong(packed) >> 32) != iseq);
-            const int sr = (int)(__double_as_longlong(packed) & 0xffffffffLL);
-            if (cand_better(sv, sr, gv, grow)) { gv = sv; grow = sr; gcta = i; }
-        }
-        PROF(2);
-        const int nw_used = min(8, (G + 31) / 32);
-        if (warp < nw_used) {
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) {
-                const double ov = __shfl_xor_sync(0xffffffffu, gv, o);
-                const int orow = __shfl_xor_sync(0xffffffffu, grow, o);
-                const int ow = __shfl_xor_sync(0xffffffffu, gcta, o);
-                if (cand_better(ov, orow, gv, grow)) { gv = ov; grow = orow; gcta = ow; }
+            double gv = -2.0; grow = 0x7fffffff; gcta = -1;
+            for (int i = tid; i < G; i += nt) {
+                const double2* slot = p.xch + ((size_t)par * G + i) * SL;
+                double sv, packed;
+                do { lu_ld_pair_raw(slot, sv, packed); } while ((int)(__double_as_longlong(packed) >> 32) != iseq);
+                const int sr = (int)(__double_as_longlong(packed) & 0xffffffffLL);
+                if (cand_better(sv, sr, gv, grow)) { gv = sv; grow = sr; gcta = i; }
             }
-            if (lane == 0) { red_v[warp] = gv; red_r[warp] = grow; red_w[warp] = gcta; }
-        }
-        __syncthreads();
-        gv = red_v[0]; grow = red_r[0]; gcta = red_w[0];
-        for (int i = 1; i < nw_used; ++i)
-            if (cand_better(red_v[i], red_r[i], gv, grow)) { gv = red_v[i]; grow = red_r[i]; gcta = red_w[i]; }
-        (void)gv;
-        PROF(3);
-        // ---- D. pivot row (the winner's published row) and old row c: both polls in flight together ----
-        {
+            PROF(1);
+            const int nw_used = min(8, (G + 31) / 32);
+            if (warp < nw_used) {
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) {
+                    const double ov = __shfl_xor_sync(0xffffffffu, gv, o);
+                    const int orow = __shfl_xor_sync(0xffffffffu, grow, o);
+                    const int ow = __shfl_xor_sync(0xffffffffu, gcta, o);
+                    if (cand_better(ov, orow, gv, grow)) { gv = ov; grow = orow; gcta = ow; }
+                }
+                if (lane == 0) { red_v[warp] = gv; red_r[warp] = grow; red_w[warp] = gcta; }
+            }
+            __syncthreads();
+            gv = red_v[0]; grow = red_r[0]; gcta = red_w[0];
+            for (int i = 1; i < nw_used; ++i)
+                if (cand_better(red_v[i], red_r[i], gv, grow)) { gv = red_v[i]; grow = red_r[i]; gcta = red_w[i]; }
+            PROF(2);
             const double2* wv = p.xch + ((size_t)par * G + gcta) * SL + 2;
             const double2* rc = p.rowc + par * w;
             for (int cc = tid; cc < w; cc += nt) {
@@ -185,14 +194,13 @@ __global__ void __launch_bounds__(256, 1) getf2_coop_kernel(const Getf2Params p)
                 while (s1 != seq) lu_ld_pair_raw(rc + cc, a1, s1);
                 prow[cc] = a0; crow[cc] = a1;
             }
+            __syncthreads();
         }
-        __syncthreads();
-        }   // G > 1
-        PROF(4);
+        PROF(3);
         const double pivot = prow[c];
         const bool elim = pivot != 0.0;                  // lu.rs:107-110: an all-zero column is skipped
         if (cta == 0 && tid == 0) p.ipiv[p.j0 + c] = p.j0 + (elim ? grow : c);
-        // ---- E. swap rows c <-> grow inside shared memory ----
+        // ---- 2. swap rows c <-> grow inside shared memory, scale column c ----
         if (elim && grow != c) {
             const bool own_g = grow >= r_begin && grow < r_begin + nrows;
             const bool own_c = c >= r_begin && c < r_begin + nrows;
@@ -200,23 +208,63 @@ __global__ void __launch_bounds__(256, 1) getf2_coop_kernel(const Getf2Params p)
             if (own_c) for (int cc = tid; cc < w; cc += nt) s[(c - r_begin) + cc * rp] = prow[cc];
             if (own_g || own_c) __syncthreads();
         }
-        // ---- F. scale by the reciprocal pivot, then the rank-1 update (unfused mul/add like the reference)
-        //         on a 2D thread mapping (64 row lanes x 4 column groups) so that every thread has
-        //         independent work in flight; the candidates of column c+1 are picked up on the way ----
-        PROF(5);
-        const double inv = __drcp_rn(pivot);             // IEEE-rounded 1/diag, as gauss_step computes it
+        const int rlo = max(0, c + 1 - r_begin);         // first local row below the pivot row
+        double* lc = s + (size_t)c * rp;
         if (elim) {
-            for (int r = tid; r < nrows; r += nt)
-                if (r_begin + r > c) s[r + c * rp] = __dmul_rn(s[r + c * rp], inv);
+            const double inv = __drcp_rn(pivot);         // IEEE-rounded 1/diag, as gauss_step computes it
+            for (int r = rlo + tid; r < nrows; r += nt) lc[r] = __dmul_rn(lc[r], inv);
             __syncthreads();
         }
-        PROF(6);
-        bv = -1.0; br = 0x7fffffff;
+        PROF(4);
+        if (c + 1 >= w) continue;                        // last column of the panel: nothing right of it
+        // ---- 3. column c+1 only: update, local candidate, publish header + candidate row + row c+1 ----
         {
-            // warp `warp` owns the columns cc = c+1+warp (mod 8); a lane owns rows lane, lane+32, ... in
-            // chunks of 8: the 8 multipliers stay in registers and the 8 row updates are independent.
-            const int rlo = max(0, c + 1 - r_begin);              // first local row below the pivot row
-            const double* lc = s + (size_t)c * rp;
+            double* col = s + (size_t)(c + 1) * rp;
+            const double pv = -prow[c + 1];
+            double bv = -1.0; int br = 0x7fffffff;
+            for (int r = rlo + tid; r < nrows; r += nt) {
+                double v = col[r];
+                if (elim) { v = __dadd_rn(__dmul_rn(pv, lc[r]), v); col[r] = v; }
+                const int gr = r_begin + r;
+                const double key = pivot_key(v, gr == c + 1);
+                if (cand_better(key, gr, bv, br)) { bv = key; br = gr; }
+            }
+            if (c + 1 < ncol) {
+                reduce_and_publish_header(bv, br, c + 1);
+                if (G > 1) {
+                    const double nseq = (double)(p.seq0 + c + 2);
+                    const int npar = (c + 1) & 1;
+                    const int lr = s_lrow;
+                    double2* myslot = p.xch + ((size_t)npar * G + cta) * SL;
+                    if (lr != 0x7fffffff) {
+                        const int lrl = lr - r_begin;
+                        const double ll = lc[lrl];
+                        for (int cc = tid; cc < w; cc += nt) {
+                            double v = s[lrl + cc * rp];
+                            if (elim && cc >= c + 2) v = __dadd_rn(__dmul_rn(-prow[cc], ll), v);    // what step 4 will store
+                            lu_st_pair(myslot + 2 + cc, v, nseq);
+                        }
+                    }
+                    if (c + 1 >= r_begin && c + 1 < r_begin + nrows) {
+                        const int rl = c + 1 - r_begin;
+                        const double ll = lc[rl];
+                        for (int cc = tid; cc < w; cc += nt) {
+                            double v = s[rl + cc * rp];
+                            if (elim && cc >= c + 2) v = __dadd_rn(__dmul_rn(-prow[cc], ll), v);
+                            lu_st_pair(p.rowc + npar * w + cc, v, nseq);
+                        }
+                    }
+                    __syncthreads();     // the rows above were read un-updated: step 4 may only start now
+                }
+            } else {
+                __syncthreads();
+            }
+        }
+        PROF(5);
+        // ---- 4. bulk rank-1 update of columns c+2.. (unfused mul/add like the reference): warp `warp`
+        //         owns the columns cc = c+2+warp (mod 8); a lane owns rows lane, lane+32, ... in chunks of
+        //         8 whose multipliers stay in registers; the 8 row updates are independent ----
+        if (elim) {
             for (int rb = (rlo / 256) * 256; rb < nrows; rb += 256) {
                 double l[8];
                 bool ok[8];
@@ -226,33 +274,21 @@ __global__ void __launch_bounds__(256, 1) getf2_coop_kernel(const Getf2Params p)
                     ok[i] = r >= rlo && r < nrows;
                     l[i] = ok[i] ? lc[r] : 0.0;
                 }
-                for (int cc = c + 1 + warp; cc < w; cc += 8) {
+                for (int cc = c + 2 + warp; cc < w; cc += 8) {
                     double* col = s + (size_t)cc * rp;
                     const double pv = -prow[cc];
                     double v[8];
 #pragma unroll
                     for (int i = 0; i < 8; ++i) v[i] = ok[i] ? col[rb + lane + 32 * i] : 0.0;
-                    if (elim) {
 #pragma unroll
-                        for (int i = 0; i < 8; ++i) v[i] = __dadd_rn(__dmul_rn(pv, l[i]), v[i]);
+                    for (int i = 0; i < 8; ++i) v[i] = __dadd_rn(__dmul_rn(pv, l[i]), v[i]);
 #pragma unroll
-                        for (int i = 0; i < 8; ++i) if (ok[i]) col[rb + lane + 32 * i] = v[i];
-                    }
-                    if (cc == c + 1) {                            // next pivot column: pick up its candidates
-#pragma unroll
-                        for (int i = 0; i < 8; ++i) {
-                            if (!ok[i]) continue;
-                            const int gr = r_begin + rb + lane + 32 * i;
-                            const double key = pivot_key(v[i], gr == c + 1);
-                            if (cand_better(key, gr, bv, br)) { bv = key; br = gr; }
-                        }
-                    }
-                    if (!elim) break;                             // nothing to eliminate: only the candidate scan
+                    for (int i = 0; i < 8; ++i) if (ok[i]) col[rb + lane + 32 * i] = v[i];
                 }
             }
         }
         __syncthreads();
-        PROF(7);
+        PROF(6);
     }
     __syncthreads();
     for (int c = 0; c < w; ++c)

@@ -18,7 +18,7 @@ def run(M, N, reps=10):
     print(f"lu {M:6d} x {N:4d}: {best*1e3:9.1f} us  launches {nl}  ({best*1e3/min(M,N):6.2f} us/column)")
     prof = (C.c_longlong * 16)(); L.na_debug_getf2_prof(prof, 1)
     cols = reps * min(M, N)
-    print("     cycles/column by phase [loop-top, A local argmax, C poll headers, C reduce, D rows, pivot/E swap, F1 scale, F2 update]:", [int(prof[i] / cols) for i in range(8)])
+    print("     cycles/column [top, 1 poll headers, 1 reduce, 1 rows, 2 swap+scale, 3 col c+1 + publish, 4 bulk update]:", [int(prof[i] / cols) for i in range(7)])
 L.na_debug_getf2_prof((C.c_longlong * 16)(), 1)
 for (M, N) in [(128, 128), (1024, 128), (16384, 128), (16384, 32)]:
     run(M, N)
