@@ -542,7 +542,9 @@ static int gemm_colmajor_c(cudaStream_t s, bool lower_only, size_t m, size_t n, 
         const int sms = ctx().sm_count;
         const int kblocks = (int)ceil_div(k, BK);
         if (p.num_tiles * 2 <= sms && kblocks >= 64) {
-            int splits = std::min(std::min(sms / p.num_tiles, kblocks / 32), 32);
+            // as many K-slices as there are idle SMs, but at least 16 k-blocks (256 deep) per slice
+            int splits = std::min(std::min(sms / p.num_tiles, kblocks / 16), 148);
+            while (splits > 1 && (size_t)splits * round_up(m, 2) * n * sizeof(double) > (512ull << 20)) --splits;
             if (splits > 1) {
                 const int kbs = (int)ceil_div((size_t)kblocks, (size_t)splits);
                 splits = (int)ceil_div((size_t)kblocks, (size_t)kbs);

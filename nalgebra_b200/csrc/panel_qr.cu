@@ -18,93 +18,148 @@
 namespace nab {
 
 // ------------------------------------------------------------------------------------------------
-// GEQR2: m x w panel (w <= 64), rows distributed over G co-resident CTAs, resident in shared
-// memory; two grid-wide exchanges per column (|x|^2 and alpha; then the w-c-1 dot products v^T a_j).
+// GEQR2: m x w panel (w <= 32), rows distributed over G co-resident CTAs, resident in shared memory;
+// ONE grid-wide exchange per column.
+//
+// For column c every CTA needs  alpha = a[c,c],  sigma = sum_{r>c} a[r,c]^2,  S_j = sum_{r>c} a[r,c]*a[r,j]
+// and the row a[c, j], j > c.  With those it forms the reflector (beta, tau, scale) and the products
+// v^T a_j = a[c,j] + scale*S_j locally.  The partial sums for column c+1 are accumulated in the SAME
+// pass that applies reflector c (column c+1 is updated first and kept in registers), reduced with a
+// butterfly reduce-scatter, and published together with row c+1 by its owner.
 //
 // The exchange is self-validating: every published double travels with a sequence number in the
 // same 16-byte word, so there is no separate barrier, fence or counter: readers poll the words they
-// need until the sequence number matches.  Two buffers (by exchange parity) are enough because a
-// CTA cannot publish exchange k+2 before every CTA has published k+1, i.e. finished reading k.
+// need until the sequence number matches.  Two buffers (by column parity) are enough because a CTA
+// cannot publish column c+2 before every CTA has published c+1, i.e. finished reading c.
 // ------------------------------------------------------------------------------------------------
 struct Geqr2Params {
     double* a; long long lda;
     int m, w, rp;
     double* tau;               // [w] out
-    double2* xch;              // [2][G][P] (value, seq) pairs, P = w + 1
-    int seq0;                  // sequence numbers already consumed in this buffer (buffers are reused across panels)
+    double2* xch;              // [2][G][32]  (partial sum, seq) pairs, slot j = column j (slot c = sigma)
+    double2* rowc;             // [2][32]     (a[c, j], seq) pairs published by the owner of row c
+    int seq0;                  // sequence numbers already consumed in this workspace
 };
 
 __device__ __forceinline__ void st_pair(double2* p, double v, double seq) {
     asm volatile("st.global.v2.f64 [%0], {%1, %2};" ::"l"(p), "d"(v), "d"(seq) : "memory");
 }
-__device__ __forceinline__ double2 ld_pair(const double2* p) {
-    double2 r;
-    asm volatile("ld.volatile.global.v2.f64 {%0, %1}, [%2];" : "=d"(r.x), "=d"(r.y) : "l"(p) : "memory");
-    return r;
+__device__ __forceinline__ void ld_pair_raw(const double2* p, double& x, double& y) {
+    asm volatile("ld.volatile.global.v2.f64 {%0, %1}, [%2];" : "=d"(x), "=d"(y) : "l"(p) : "memory");
 }
 
-// All CTAs publish `np` partial values (part[0..np)) and receive the sums over CTAs in tot[0..np)
-// (identical in every CTA: summed in CTA order).  stage: smem [G*np].
-__device__ __forceinline__ void exchange_sum(const Geqr2Params& p, int G, int cta, int P, int np, double seq, int buf,
-                                             const double* part, double* tot, double* stage) {
-    const int tid = threadIdx.x, nt = blockDim.x;
-    double2* base = p.xch + (size_t)buf * G * P;
-    for (int i = tid; i < np; i += nt) st_pair(base + (size_t)cta * P + i, part[i], seq);
-    for (int idx = tid; idx < G * np; idx += nt) {
-        const int g = idx / np, i = idx - g * np;
-        const double2* src = base + (size_t)g * P + i;
-        double2 v = ld_pair(src);
-        while (v.y != seq) v = ld_pair(src);
-        stage[idx] = v.x;
+// vals[0..31] per lane -> returns in every lane l the sum over the warp of vals[l] (butterfly
+// reduce-scatter: 31 shuffles instead of 160)
+__device__ __forceinline__ double warp_reduce_scatter32(double (&vals)[32], int lane) {
+#pragma unroll
+    for (int step = 16; step >= 1; step >>= 1) {
+        const bool hi = (lane & step) != 0;
+#pragma unroll
+        for (int i = 0; i < step; ++i) {
+            const double send = hi ? vals[i] : vals[i + step];
+            const double keep = hi ? vals[i + step] : vals[i];
+            vals[i] = keep + __shfl_xor_sync(0xffffffffu, send, step);
+        }
     }
-    __syncthreads();
-    for (int i = tid; i < np; i += nt) {
-        double s = 0.0;
-        for (int g = 0; g < G; ++g) s += stage[g * np + i];
-        tot[i] = s;
-    }
-    __syncthreads();
+    return vals[0];
 }
 
 __global__ void __launch_bounds__(256, 1) geqr2_coop_kernel(const Geqr2Params p) {
     extern __shared__ double sm[];
     const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, warp = tid >> 5;
     const int G = gridDim.x, cta = blockIdx.x;
-    const int w = p.w, rp = p.rp, P = w + 1;
+    const int w = p.w, rp = p.rp;
     const int r_begin = cta * rp;
     const int nrows = max(0, min(rp, p.m - r_begin));
     double* s = sm;                          // [w][rp]
-    double* part = s + (size_t)w * rp;       // [P]
-    double* tot = part + P;                  // [P]
-    double* wred = tot + P;                  // [8][P] per-warp partials
-    double* stage = wred + 8 * P;            // [G*P]
+    double* wred = s + (size_t)w * rp;       // [8][32] per-warp partial sums
+    double* tot = wred + 8 * 32;             // [32] totals T_j
+    double* rowv = tot + 32;                 // [32] row c values
+    double* dots = rowv + 32;                // [32] tau * (v^T a_j)
+    double* stage = dots + 32;               // [G][32]
 
     for (int c = 0; c < w; ++c)
         for (int r = tid; r < nrows; r += nt) s[r + c * rp] = p.a[(long long)(r_begin + r) + (long long)c * p.lda];
     __syncthreads();
-
     const int ncol = min(w, p.m);
-    int seq = p.seq0;
-    for (int c = 0; c < ncol; ++c) {
-        // ---- exchange 1: |x|^2 over rows >= c, and alpha = a[c,c] ----
-        double ss = 0.0;
-        for (int r = tid; r < nrows; r += nt)
-            if (r_begin + r >= c) { const double v = s[r + c * rp]; ss += v * v; }
+
+    // One pass over the local rows: applies reflector `c` (c < 0: nothing to apply) and accumulates, for
+    // the next column cn = c + 1, vals[j] = sum_{r > cn} x[r] * a[r, j] (j >= cn) with x = updated column cn.
+    auto pass = [&](int c, double scale, double tau_unused) {
+        (void)tau_unused;
+        const int cn = c + 1;
+        double vals[32];
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
-        if (lane == 0) wred[warp] = ss;
+        for (int j = 0; j < 32; ++j) vals[j] = 0.0;
+        for (int r = tid; r < nrows; r += nt) {
+            const int gr = r_begin + r;
+            if (gr < cn && !(gr == c)) continue;            // finished rows (R part) above the pivot row
+            double v = 0.0;
+            if (c >= 0) {
+                if (gr == c) v = 1.0;                        // v[c] = 1; the diagonal slot is set by the caller
+                else { v = s[r + c * rp] * scale; s[r + c * rp] = v; }
+            }
+            double x = 0.0;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+                if (j < cn || j >= w) continue;              // columns right of c only
+                double aj = s[r + j * rp];
+                if (c >= 0) { aj -= dots[j] * v; s[r + j * rp] = aj; }
+                if (j == cn) x = (gr > cn) ? aj : 0.0;       // rows below the next pivot row feed the sums
+                vals[j] += x * aj;
+            }
+        }
+        const double mine = warp_reduce_scatter32(vals, lane);
+        wred[warp * 32 + lane] = mine;
         __syncthreads();
-        if (tid == 0) {
-            double t = 0.0;
-            for (int i = 0; i < nt / 32; ++i) t += wred[i];
-            part[0] = t;
-            part[1] = (c >= r_begin && c < r_begin + nrows) ? s[(c - r_begin) + c * rp] : 0.0;
+        // cross-warp sum and publish: slot j = column j (slot cn = sigma), plus row cn from its owner
+        if (cn < ncol) {
+            const double seq = (double)(p.seq0 + cn + 1);
+            const int par = cn & 1;
+            if (tid < 32) {
+                double t = 0.0;
+#pragma unroll
+                for (int i = 0; i < 8; ++i) t += wred[i * 32 + tid];
+                if (tid >= cn && tid < w) st_pair(p.xch + ((size_t)par * G + cta) * 32 + tid, t, seq);
+            } else if (tid < 64) {
+                const int j = tid - 32;
+                if (cn >= r_begin && cn < r_begin + nrows && j >= cn && j < w) st_pair(p.rowc + par * 32 + j, s[(cn - r_begin) + j * rp], seq);
+            }
+        }
+    };
+
+    // receive column c: totals T_j (identical in every CTA: summed in CTA order) and row c
+    auto receive = [&](int c) {
+        const double seq = (double)(p.seq0 + c + 1);
+        const int par = c & 1;
+        const int np = w - c;                                   // slots c .. w-1
+        for (int idx = tid; idx < G * np; idx += nt) {
+            const int g = idx / np, j = c + (idx - g * np);
+            const double2* src = p.xch + ((size_t)par * G + g) * 32 + j;
+            double x, y;
+            do { ld_pair_raw(src, x, y); } while (y != seq);
+            stage[g * 32 + j] = x;
+        }
+        if (tid < np) {
+            double x, y;
+            const double2* src = p.rowc + par * 32 + c + tid;
+            do { ld_pair_raw(src, x, y); } while (y != seq);
+            rowv[c + tid] = x;
         }
         __syncthreads();
-        ++seq;
-        exchange_sum(p, G, cta, P, 2, (double)seq, seq & 1, part, tot, stage);
-        const double sq = tot[0], alpha = tot[1];
-        const double nrm = sqrt(sq);
+        if (tid < np) {
+            double t = 0.0;
+            for (int g = 0; g < G; ++g) t += stage[g * 32 + c + tid];
+            tot[c + tid] = t;
+        }
+        __syncthreads();
+    };
+
+    pass(-1, 0.0, 0.0);                                          // partial sums of column 0
+    for (int c = 0; c < ncol; ++c) {
+        receive(c);
+        const double alpha = rowv[c], sigma = tot[c];
+        const double nrm = sqrt(alpha * alpha + sigma);
         double beta = 0.0, tau = 0.0, scale = 0.0;
         if (nrm != 0.0) {                         // householder.rs:36: only an all-zero column is skipped
             beta = (alpha >= 0.0) ? -nrm : nrm;   // -sign(alpha)*|x|, sign(0) = +1 like simba's to_exp
@@ -112,51 +167,11 @@ __global__ void __launch_bounds__(256, 1) geqr2_coop_kernel(const Geqr2Params p)
             scale = 1.0 / (alpha - beta);
         }
         if (cta == 0 && tid == 0) p.tau[c] = tau;
-        // v = x * scale below the diagonal; the diagonal slot receives beta
-        for (int r = tid; r < nrows; r += nt) {
-            const int gr = r_begin + r;
-            if (gr > c) s[r + c * rp] *= scale;
-            else if (gr == c) s[r + c * rp] = beta;
-        }
+        __syncthreads();                          // everyone has read rowv/tot before dots is rewritten
+        if (tid < w && tid > c) dots[tid] = tau * (rowv[tid] + scale * tot[tid]);   // tau * v^T a_j
+        if (tid == 0 && c >= r_begin && c < r_begin + nrows) s[(c - r_begin) + c * rp] = beta;
         __syncthreads();
-        const int nrem = w - c - 1;
-        if (nrem == 0 || tau == 0.0) continue;    // uniform across CTAs
-        // ---- exchange 2: dots[j] = v^T a_j over rows >= c (v[c] = 1) ----
-        for (int j0 = 0; j0 < nrem; j0 += 8) {    // 8 columns at a time in registers
-            double acc[8];
-#pragma unroll
-            for (int jj = 0; jj < 8; ++jj) acc[jj] = 0.0;
-            for (int r = tid; r < nrows; r += nt) {
-                const int gr = r_begin + r;
-                if (gr < c) continue;
-                const double v = (gr == c) ? 1.0 : s[r + c * rp];
-#pragma unroll
-                for (int jj = 0; jj < 8; ++jj)
-                    if (j0 + jj < nrem) acc[jj] += v * s[r + (c + 1 + j0 + jj) * rp];
-            }
-#pragma unroll
-            for (int jj = 0; jj < 8; ++jj) {
-#pragma unroll
-                for (int o = 16; o > 0; o >>= 1) acc[jj] += __shfl_xor_sync(0xffffffffu, acc[jj], o);
-                if (lane == 0 && j0 + jj < nrem) wred[warp * P + j0 + jj] = acc[jj];
-            }
-        }
-        __syncthreads();
-        for (int j = tid; j < nrem; j += nt) {
-            double t = 0.0;
-            for (int i = 0; i < nt / 32; ++i) t += wred[i * P + j];
-            part[j] = t;
-        }
-        __syncthreads();
-        ++seq;
-        exchange_sum(p, G, cta, P, nrem, (double)seq, seq & 1, part, tot, stage);
-        // ---- a_j -= tau * dots[j] * v ----
-        for (int r = tid; r < nrows; r += nt) {
-            const int gr = r_begin + r;
-            if (gr < c) continue;
-            const double tv = tau * ((gr == c) ? 1.0 : s[r + c * rp]);
-            for (int j = 0; j < nrem; ++j) s[r + (c + 1 + j) * rp] -= tv * tot[j];
-        }
+        if (c + 1 < w || true) pass(c, scale, tau);
         __syncthreads();
     }
     for (int c = 0; c < w; ++c)
@@ -164,31 +179,31 @@ __global__ void __launch_bounds__(256, 1) geqr2_coop_kernel(const Geqr2Params p)
 }
 
 constexpr size_t kGeqr2MaxCtas = 160;
-size_t geqr2_workspace_bytes() { return 2 * kGeqr2MaxCtas * (kQrLeaf + 1) * sizeof(double2) + sizeof(int) * 4; }
+size_t geqr2_workspace_bytes() { return (2 * kGeqr2MaxCtas * 32 + 2 * 32) * sizeof(double2); }
 
-// *seq_state (host) carries the sequence numbers consumed so far in this workspace.
+// *seq_state (host) carries the sequence numbers consumed so far in this (zero-initialised) workspace.
 int geqr2_panel(cudaStream_t st, double* a_panel, size_t lda, size_t m, size_t w, double* tau, void* ws, int* seq_state) {
     if (m == 0 || w == 0) return NA_OK;
     if (w > (size_t)kQrLeaf) { set_error("geqr2: panel too wide"); return NA_EINVAL; }
     const int sms = ctx().sm_count;
-    const size_t P = w + 1;
-    // smem: w*rp + 2P + 8P + G*P doubles
+    // smem: w*rp + 8*32 + 3*32 + G*32 doubles
     size_t G = 1, rp = 0;
     for (;; ++G) {
         if (G > (size_t)std::min<int>(sms, (int)kGeqr2MaxCtas)) { set_error("geqr2: %zu x %zu panel does not fit in shared memory", m, w); return NA_EINVAL; }
         rp = round_up(ceil_div(m, G), 32);
-        const size_t bytes = (w * rp + 10 * P + G * P) * sizeof(double);
-        if (bytes <= 200 * 1024 && (rp <= 1024 || G * 2 > (size_t)sms)) break;   // prefer <= 1024 rows per CTA when SMs allow
+        const size_t bytes = (w * rp + 352 + G * 32) * sizeof(double);
+        if (bytes <= 200 * 1024 && (rp <= 768 || G * 2 > (size_t)sms)) break;   // prefer <= 768 rows per CTA when SMs allow
     }
     G = ceil_div(m, rp);
-    const size_t smem = (w * rp + 10 * P + G * P) * sizeof(double);
+    const size_t smem = (w * rp + 352 + G * 32) * sizeof(double);
     static std::once_flag once;
     std::call_once(once, [] { cudaFuncSetAttribute(geqr2_coop_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024); });
     Geqr2Params p;
     p.a = a_panel; p.lda = (long long)lda; p.m = (int)m; p.w = (int)w; p.rp = (int)rp; p.tau = tau;
     p.xch = static_cast<double2*>(ws);
+    p.rowc = p.xch + 2 * kGeqr2MaxCtas * 32;
     p.seq0 = *seq_state;
-    *seq_state += 2 * (int)w + 2;            // upper bound of the sequence numbers this panel uses (parity preserved)
+    *seq_state += (int)w + 2 + ((w & 1) ? 1 : 0);
     void* args[] = {(void*)&p};
     NAB_CUDA(cudaLaunchCooperativeKernel((void*)geqr2_coop_kernel, dim3((unsigned)G), dim3(256), args, smem, st));
     count_launch();
