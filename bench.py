@@ -185,12 +185,18 @@ def run_gpu(args):
             dist.barrier()
             torch.cuda.synchronize()
 
-    for _ in range(args.warmup):
-        step()
-    barrier()
-    launches0 = L.na_kernel_launches()
-    e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+    # the sampler starts before the warm-up (nvidia-smi needs ~0.2 s to produce its first line); only
+    # samples taken under load (SM clock above half of max) enter the summary
     with ClockSampler(local_rank) as clk:
+        for _ in range(args.warmup):
+            step()
+        barrier()
+        if ngpus > 1 and args.steps * 0.25 / ngpus < 0.5:      # short timed region: keep the GPU busy long enough to be sampled
+            for _ in range(max(3, int(0.6 / (0.25 / ngpus)))):
+                step()
+            barrier()
+        launches0 = L.na_kernel_launches()
+        e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
         e0.record()
         for _ in range(args.steps):
             step()
