@@ -161,6 +161,7 @@ def run_gpu(args):
     L = _capi.lib()
     _capi.check(L.na_init(local_rank))
     stream = torch.cuda.current_stream().cuda_stream
+    sm_count = torch.cuda.get_device_properties(dev).multi_processor_count
 
     N = args.n
     pr, pc = process_grid(ngpus)
@@ -168,16 +169,71 @@ def run_gpu(args):
     m_loc, n_loc = N // pr, N // pc
     row0, col0 = my_r * m_loc, my_c * n_loc
 
-    # inputs resident in HBM: this rank's row panel of A (m_loc x N) and column panel of B (N x n_loc)
-    A = torch.empty(m_loc * N, dtype=torch.float64, device=dev)
-    B = torch.empty(N * n_loc, dtype=torch.float64, device=dev)
+    # Inputs resident in HBM, block-distributed WITHOUT replication:
+    #   rank (r, c) owns the K-chunk c of the row panel A[r-rows, :]   (m_loc x N/pc, contiguous)
+    #   and the K-chunk r of the column panel B[:, c-cols]             (N/pr x n_loc, contiguous).
+    # A step assembles the panels over NVLink (one NCCL broadcast per foreign chunk, in the row /
+    # column sub-communicators, all issued up front) and accumulates C over K-pieces as they arrive,
+    # starting with the locally owned ones: the exchange overlaps the DMMA work.  (N = 1: no exchange.)
+    kca, kcb = N // pc, N // pr
+    A = torch.empty(m_loc * N, dtype=torch.float64, device=dev)                       # full row panel, ld = m_loc
+    Bc = [torch.empty(kcb * n_loc, dtype=torch.float64, device=dev) for _ in range(pr)]   # K-chunks of the column panel
     Cd = torch.empty(m_loc * n_loc, dtype=torch.float64, device=dev)
-    _capi.check(L.na_fill_uniform_block_dev(A.data_ptr(), m_loc, N, m_loc, 1, row0, 0, N, stream))
-    _capi.check(L.na_fill_uniform_block_dev(B.data_ptr(), N, n_loc, N, 2, 0, col0, N, stream))
+    a_chunks = [A[q * kca * m_loc:(q + 1) * kca * m_loc] for q in range(pc)]
+    _capi.check(L.na_fill_uniform_block_dev(a_chunks[my_c].data_ptr(), m_loc, kca, m_loc, 1, row0, my_c * kca, N, stream))
+    _capi.check(L.na_fill_uniform_block_dev(Bc[my_r].data_ptr(), kcb, n_loc, kcb, 2, my_r * kcb, col0, N, stream))
+    row_group = col_group = None
+    if world > 1:
+        for r in range(pr):
+            g = dist.new_group([r * pc + c for c in range(pc)])
+            if r == my_r:
+                row_group = g
+        for c in range(pc):
+            g = dist.new_group([r * pc + c for r in range(pr)])
+            if c == my_c:
+                col_group = g
+    kp = min(kca, kcb, 2048 if world > 1 else N)   # K-piece of one GEMM call (small pieces: only the first runs on a reduced grid)
+    pieces = sorted(range(N // kp), key=lambda t: (not ((t * kp) // kca == my_c and (t * kp) // kcb == my_r),
+                                                   not ((t * kp) // kca == my_c or (t * kp) // kcb == my_r), t))
+
+    def gemm_piece(t, first):
+        k0 = t * kp
+        qa, qb = k0 // kca, k0 // kcb
+        a_ptr = a_chunks[qa].data_ptr() + 8 * (k0 - qa * kca) * m_loc
+        b_ptr = Bc[qb].data_ptr() + 8 * (k0 - qb * kcb)
+        _capi.check(L.na_dgemm_dev(m_loc, kp, n_loc, 1.0, a_ptr, 1, m_loc, b_ptr, 1, kcb, 0.0 if first else 1.0,
+                                   Cd.data_ptr(), 1, m_loc, stream))
 
     def step():
-        _capi.check(L.na_dgemm_dev(m_loc, N, n_loc, 1.0, A.data_ptr(), 1, m_loc, B.data_ptr(), 1, N, 0.0,
-                                   Cd.data_ptr(), 1, m_loc, stream))
+        wa, wb = {}, {}
+        if world > 1:
+            # every member of a sub-communicator takes part in every broadcast (the owner as the source)
+            if pc > 1:
+                for q in range(pc):
+                    h = dist.broadcast(a_chunks[q], src=my_r * pc + q, group=row_group, async_op=True)
+                    if q != my_c:
+                        wa[q] = h
+            if pr > 1:
+                for q in range(pr):
+                    h = dist.broadcast(Bc[q], src=q * pc + my_c, group=col_group, async_op=True)
+                    if q != my_r:
+                        wb[q] = h
+        for i, t in enumerate(pieces):
+            qa, qb = (t * kp) // kca, (t * kp) // kcb
+            if qa in wa:
+                wa.pop(qa).wait()
+            if qb in wb:
+                wb.pop(qb).wait()
+            # while chunks are still in flight, leave SMs to NCCL's copy kernels (the GEMM is persistent)
+            L.na_set_gemm_sm_limit(sm_count - 20 if (i == 0 and (wa or wb)) else 0)
+            gemm_piece(t, i == 0)
+        L.na_set_gemm_sm_limit(0)
+
+    def step_replicated():
+        """Panels already assembled (what `step` leaves in A / Bc): compute only, one call per B chunk."""
+        for q in range(pr):
+            _capi.check(L.na_dgemm_dev(m_loc, kcb, n_loc, 1.0, A.data_ptr() + 8 * q * kcb * m_loc, 1, m_loc,
+                                       Bc[q].data_ptr(), 1, kcb, 0.0 if q == 0 else 1.0, Cd.data_ptr(), 1, m_loc, stream))
 
     def barrier():
         torch.cuda.synchronize()
@@ -212,8 +268,19 @@ def run_gpu(args):
     value = flops / (ms_step * 1e-3) / 1e9
     clocks = clk.summary()
 
-    # per-kernel duration for the roofline: one launch per step on this rank
-    kernel_ms = ms_total / args.steps
+    # roofline of the dominant kernel: compute-only launches (panels assembled), CUDA events on the launching stream
+    nk = len(pieces) if ngpus > 1 else 1
+    if ngpus > 1:
+        step_replicated(); torch.cuda.synchronize()
+        k0e = torch.cuda.Event(enable_timing=True); k1e = torch.cuda.Event(enable_timing=True)
+        k0e.record()
+        for _ in range(args.steps):
+            step_replicated()
+        k1e.record(); torch.cuda.synchronize()
+        kernel_ms = k0e.elapsed_time(k1e) / args.steps
+        nk = pr
+    else:
+        kernel_ms = ms_total / args.steps
     achieved = (flops / ngpus) / (kernel_ms * 1e-3) / 1e12
     traffic = None
     try:   # DRAM bytes of one launch from the committed `ncu --set full` capture (same workload only)
@@ -230,7 +297,10 @@ def run_gpu(args):
         hA = torch.empty(m_loc * N, dtype=torch.float64).pin_memory()
         hB = torch.empty(N * n_loc, dtype=torch.float64).pin_memory()
         hC = torch.empty(m_loc * n_loc, dtype=torch.float64).pin_memory()
-        hA.copy_(A); hB.copy_(B)
+        hA.copy_(A)                                                     # assembled row panel (ld = m_loc)
+        hBv = hB.view(n_loc, N)                                         # column-major N x n_loc
+        for q in range(pr):
+            hBv[:, q * kcb:(q + 1) * kcb].copy_(Bc[q].view(n_loc, kcb))
         torch.cuda.synchronize()
 
         def e2e_step():
@@ -300,12 +370,17 @@ def run_gpu(args):
             "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": f"DMatrix<f64> GEMM {N}x{N}x{N} (C = A*B), uniform [0,1) inputs (BASELINE.json configs[1])",
                        "process_grid": f"{pr}x{pc}", "per_gpu_tile": f"{m_loc}x{n_loc}x{N}",
+                       "distribution": ("single GPU" if ngpus == 1 else
+                                        f"A and B block-distributed without replication; per step each rank receives {pc - 1} A K-chunks "
+                                        f"({(pc - 1) * kca * m_loc * 8 / 1e9:.2f} GB) and {pr - 1} B K-chunks ({(pr - 1) * kcb * n_loc * 8 / 1e9:.2f} GB) "
+                                        "over NVLink (NCCL broadcasts in row/column sub-communicators) overlapped with the K-chunked GEMM"),
                        "l2": "inputs (>=1.6 GB per GPU) exceed the 126 MB L2; no explicit flush",
                        "pct_of_fp64_peak": 100.0 * value / 1e3 / (FP64_PEAK_TFLOPS * ngpus)},
             "roofline": {"bound": "tensor", "achieved": achieved, "peak": FP64_PEAK_TFLOPS, "unit": "TFLOP/s",
                          "frac": achieved / FP64_PEAK_TFLOPS, "traffic": traffic,
                          "kernel": "dgemm_tma_dmma_kernel", "peak_source": "measured: tools/fp64_peak.cu DMMA chain on this pool's B200 (profiles/fp64_peak_r01.md); MEASURED_PEAKS.json has no FP64 entry",
-                         "algorithmic_flops_per_launch": flops / ngpus},
+                         "algorithmic_flops_per_launch": flops / ngpus / nk, "launches_per_step": nk,
+                         "compute_only_ms_per_step": kernel_ms},
             "clocks": clocks, "gpu_launches": int(launches),
         }
         if e2e:

@@ -164,6 +164,11 @@ NAB_API int na_tri_solve_f64(int lower, int trans, int unit_diag, size_t n, cons
 NAB_API int na_tri_solve_f64_dev(int lower, int trans, int unit_diag, size_t n, const double* t, size_t ldt,
                          double* b, size_t ldb, size_t nrhs, void* stream);
 
+/* Upper bound on the CTAs (= SMs: the GEMM kernels are persistent, one CTA per SM) that GEMM launches
+ * issued by the CALLING THREAD may use; 0 restores "all SMs".  Lets a caller keep SMs free for work on
+ * other streams (NCCL copy kernels while panels are staged over NVLink, a concurrent panel kernel). */
+NAB_API int na_set_gemm_sm_limit(int max_ctas);
+
 /* ---- building blocks of the multi-GPU (1D block-cyclic) factorizations, device pointers ------ */
 /* General triangular solve with many right-hand sides, in place on B (m x n, ldb):
  *   side_right = 0:  op(T) X = B  (T is m x m)      side_right = 1:  X op(T) = B  (T is n x n)

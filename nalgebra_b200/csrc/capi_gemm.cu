@@ -193,6 +193,12 @@ int na_fill_uniform_block_dev(double* a, size_t nrows, size_t ncols, size_t lda,
     return fill_uniform(static_cast<cudaStream_t>(stream), a, nrows, ncols, lda, seed, row0, col0, global_rows);
 }
 
+int na_set_gemm_sm_limit(int max_ctas) {
+    if (max_ctas < 0) { set_error("na_set_gemm_sm_limit: negative limit"); return NA_EINVAL; }
+    set_gemm_sm_limit(max_ctas);
+    return NA_OK;
+}
+
 int na_fill_spd_block_dev(double* a, size_t nrows, size_t ncols, size_t lda, uint64_t seed,
                           size_t row0, size_t col0, size_t n, void* stream) {
     NAB_TRY(ensure_init());

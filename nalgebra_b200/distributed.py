@@ -53,6 +53,11 @@ class DeviceOps:
     def trsm_right_lower_trans(self, m: int, w: int, t_ptr: int, ldt: int, b_ptr: int, ldb: int):
         _capi.check(self.lib.na_trsm_f64_dev(1, 1, 1, 0, m, w, t_ptr, ldt, b_ptr, ldb, self._stream()))
 
+    def reserve_sms(self, n_reserved: int):
+        """Keep `n_reserved` SMs free of (persistent) GEMM CTAs, e.g. for NCCL's copy kernels; 0 = none."""
+        sms = torch.cuda.get_device_properties(self.device).multi_processor_count
+        _capi.check(self.lib.na_set_gemm_sm_limit(sms - n_reserved if n_reserved > 0 else 0))
+
     def syrk_lower_update(self, m: int, k: int, n: int, p_ptr: int, ldp: int, c_ptr: int, ldc: int):
         """C (m x n lower trapezoid) -= P[0:m, :] * P[0:n, :]^T."""
         _capi.check(self.lib.na_dgemm_lower_dev(m, k, n, -1.0, p_ptr, 1, ldp, p_ptr, ldp, 1, 1.0, c_ptr, ldc, self._stream()))
@@ -164,8 +169,12 @@ def cholesky_block_cyclic(A: ColumnBlockCyclic, group=None, lookahead: bool = Tr
                     pending = (bcast(nxt, nbuf), 1 - bi)
             else:
                 pending = (bcast(nxt, nbuf), 1 - bi)
+        if use_side and hasattr(ops, "reserve_sms"):
+            ops.reserve_sms(16)            # the next panel's broadcast is in flight: leave SMs to NCCL
         for b in mine:
             update_block(b, k, buf)
+        if use_side and hasattr(ops, "reserve_sms"):
+            ops.reserve_sms(0)
         if use_side:
             torch.cuda.current_stream(A.data.device).wait_stream(side)
     if A.data.is_cuda:
