@@ -169,12 +169,8 @@ def cholesky_block_cyclic(A: ColumnBlockCyclic, group=None, lookahead: bool = Tr
                     pending = (bcast(nxt, nbuf), 1 - bi)
             else:
                 pending = (bcast(nxt, nbuf), 1 - bi)
-        if use_side and hasattr(ops, "reserve_sms"):
-            ops.reserve_sms(16)            # the next panel's broadcast is in flight: leave SMs to NCCL
         for b in mine:
             update_block(b, k, buf)
-        if use_side and hasattr(ops, "reserve_sms"):
-            ops.reserve_sms(0)
         if use_side:
             torch.cuda.current_stream(A.data.device).wait_stream(side)
     if A.data.is_cuda:
