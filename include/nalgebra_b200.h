@@ -176,6 +176,11 @@ NAB_API int na_set_gemm_sm_limit(int max_ctas);
  * *_unchecked use, src/linalg/solve.rs:488-580). */
 NAB_API int na_trsm_f64_dev(int side_right, int lower, int trans, int unit_diag, size_t m, size_t n,
                             const double* t, size_t ldt, double* b, size_t ldb, void* stream);
+/* PermutationSequence::permute_rows / inv_permute_rows (src/linalg/permutation_sequence.rs:97-116) on a
+ * device matrix: applies the swaps (swaps[2s], swaps[2s+1]), s < nswaps (HOST array, application order;
+ * inverse != 0 applies them in reverse) to the rows of the nrows x ncols column-major matrix `a`. */
+NAB_API int na_permute_rows_f64_dev(size_t nrows, double* a, size_t lda, size_t ncols,
+                                    const size_t* swaps, size_t nswaps, int inverse, void* stream);
 /* C <- alpha*A*B + beta*C restricted to the lower trapezoid (row >= col) of the m x n (m >= n)
  * column-major C: the SYRK-shaped trailing update of Cholesky (cholesky.rs:226-235 never touches the
  * strict upper triangle, and neither does this). */

@@ -56,6 +56,7 @@ SIGNATURES = {
     "na_qr_solve_f64": (_int, [_sz, _p, _sz, _p, _p, _sz, _sz]),
     "na_set_gemm_sm_limit": (_int, [_int]),
     "na_trsm_f64_dev": (_int, [_int, _int, _int, _int, _sz, _sz, _p, _sz, _p, _sz, _p]),
+    "na_permute_rows_f64_dev": (_int, [_sz, _p, _sz, _sz, _p, _sz, _int, _p]),
     "na_dgemm_lower_dev": (_int, _GEMM64[:-2] + [_sz, _p]),
     "na_fill_spd_block_dev": (_int, [_p, _sz, _sz, _sz, _u64, _sz, _sz, _sz, _p]),
     "na_tri_solve_f64": (_int, [_int, _int, _int, _sz, _p, _sz, _p, _sz, _sz]),

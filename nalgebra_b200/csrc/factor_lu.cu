@@ -228,6 +228,28 @@ int na_lu_f64(size_t m, size_t n, double* a, size_t lda, size_t* swaps, size_t* 
     return NA_OK;
 }
 
+int na_permute_rows_f64_dev(size_t nrows, double* a, size_t lda, size_t ncols, const size_t* swaps, size_t nswaps,
+                            int inverse, void* stream) {
+    NAB_TRY(ensure_init());
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    if (nrows == 0 || ncols == 0 || nswaps == 0) return NA_OK;
+    if (!a || !swaps || lda < nrows || nrows > 0x7fffff00ull) { set_error("permute_rows: bad arguments"); return NA_EINVAL; }
+    std::vector<int> h(2 * nswaps);
+    for (size_t i = 0; i < nswaps; ++i) {
+        const size_t src = inverse ? nswaps - 1 - i : i;
+        if (swaps[2 * src] >= nrows || swaps[2 * src + 1] >= nrows) { set_error("permute_rows: swap index out of range"); return NA_EINVAL; }
+        h[2 * i] = (int)swaps[2 * src]; h[2 * i + 1] = (int)swaps[2 * src + 1];
+    }
+    Scratch dsw, wsp;
+    NAB_TRY(dsw.alloc(2 * nswaps * sizeof(int), s));
+    NAB_TRY(wsp.alloc(rowperm_workspace_bytes(nrows), s));
+    NAB_CUDA(cudaMemcpyAsync(dsw.p, h.data(), 2 * nswaps * sizeof(int), cudaMemcpyHostToDevice, s));
+    NAB_TRY(rowperm_build(s, dsw.as<int>(), dsw.as<int>() + 1, nswaps, 2, nrows, wsp.p));
+    NAB_TRY(rowperm_apply(s, a, lda, ncols, std::min(2 * nswaps, nrows), wsp.p, nrows));
+    NAB_CUDA(cudaStreamSynchronize(s));   // h must outlive the copy
+    return NA_OK;
+}
+
 int na_lu_solve_f64_dev(size_t n, const double* lu, size_t lda, const size_t* swaps, size_t nswaps,
                         double* b, size_t ldb, size_t nrhs, void* stream) {
     NAB_TRY(ensure_init());

@@ -58,6 +58,27 @@ class DeviceOps:
         sms = torch.cuda.get_device_properties(self.device).multi_processor_count
         _capi.check(self.lib.na_set_gemm_sm_limit(sms - n_reserved if n_reserved > 0 else 0))
 
+    def lu_panel(self, ptr: int, m: int, w: int, ld: int):
+        """LU::new on the m x w panel in place; returns the swaps as a list of (i, i2) panel-relative pairs."""
+        mn = min(m, w)
+        swaps = (C.c_size_t * (2 * max(mn, 1)))()
+        ns = C.c_size_t(0)
+        _capi.check(self.lib.na_lu_f64_dev(m, w, ptr, ld, swaps, C.addressof(ns), self._stream()))
+        return [(swaps[2 * i], swaps[2 * i + 1]) for i in range(ns.value)]
+
+    def permute_rows(self, ptr: int, nrows: int, ld: int, ncols: int, pairs):
+        if not pairs or ncols == 0:
+            return
+        arr = (C.c_size_t * (2 * len(pairs)))(*[v for p in pairs for v in p])
+        _capi.check(self.lib.na_permute_rows_f64_dev(nrows, ptr, ld, ncols, arr, len(pairs), 0, self._stream()))
+
+    def trsm_left_unit_lower(self, m: int, n: int, t_ptr: int, ldt: int, b_ptr: int, ldb: int):
+        _capi.check(self.lib.na_trsm_f64_dev(0, 1, 0, 1, m, n, t_ptr, ldt, b_ptr, ldb, self._stream()))
+
+    def gemm_update(self, m: int, k: int, n: int, a_ptr: int, lda: int, b_ptr: int, ldb: int, c_ptr: int, ldc: int):
+        """C -= A * B."""
+        _capi.check(self.lib.na_dgemm_dev(m, k, n, -1.0, a_ptr, 1, lda, b_ptr, 1, ldb, 1.0, c_ptr, 1, ldc, self._stream()))
+
     def syrk_lower_update(self, m: int, k: int, n: int, p_ptr: int, ldp: int, c_ptr: int, ldc: int):
         """C (m x n lower trapezoid) -= P[0:m, :] * P[0:n, :]^T."""
         _capi.check(self.lib.na_dgemm_lower_dev(m, k, n, -1.0, p_ptr, 1, ldp, p_ptr, ldp, 1, 1.0, c_ptr, ldc, self._stream()))
@@ -176,3 +197,97 @@ def cholesky_block_cyclic(A: ColumnBlockCyclic, group=None, lookahead: bool = Tr
     if A.data.is_cuda:
         torch.cuda.synchronize(A.data.device)
     return status
+
+
+def lu_block_cyclic(A: ColumnBlockCyclic, group=None, lookahead: bool = True):
+    """In-place LU with partial pivoting of the distributed matrix (LU::new semantics: whole rows are
+    swapped, packed L\\U layout).  Returns the PermutationSequence pairs [(i, i2), ...] (global row
+    indices, application order), identical on every rank.
+
+    Step k: owner(k) factors its (n - k*nb) x nb panel locally -- in a 1D column layout the panel is
+    local, so there is no cross-GPU pivot search --, broadcasts the panel and its pivot pairs; every rank
+    applies the row swaps to all its other columns, solves U12 = L11^-1 A12 on its trailing columns and
+    updates them with one GEMM (local block columns right of k are contiguous in local storage)."""
+    n, nb, rank, world, ops = A.n, A.nb, A.rank, A.world, A.ops
+    bufs = [ops.empty(n * nb), ops.empty(n * nb)]
+    use_side = lookahead and A.data.is_cuda and world > 1
+    side = torch.cuda.Stream(device=A.data.device) if use_side else None
+    piv_cap = 2 * nb + 1
+    pivs = [torch.zeros(piv_cap, dtype=torch.int64, device=A.data.device) for _ in range(2)]
+    all_pairs = []
+
+    def factor_and_pack(k: int, buf, piv):
+        r0, w = k * nb, A.width(k)
+        rows = n - r0
+        pairs = ops.lu_panel(A.ptr(r0, k), rows, w, n)
+        buf[: rows * w].view(w, rows).copy_(A.block_view(k, r0))
+        host = torch.zeros(piv_cap, dtype=torch.int64)
+        host[0] = len(pairs)
+        for i, (a, b) in enumerate(pairs):
+            host[1 + 2 * i] = a + r0
+            host[2 + 2 * i] = b + r0
+        piv.copy_(host)
+
+    def bcast(k: int, buf, piv):
+        if world == 1:
+            return []
+        r0, w = k * nb, A.width(k)
+        src = block_cyclic_owner(k, world)
+        return [dist.broadcast(buf[: (n - r0) * w], src=src, group=group, async_op=True),
+                dist.broadcast(piv, src=src, group=group, async_op=True)]
+
+    def local_range(b_lo: int, b_hi: int):
+        """(local column offset, number of columns) of the local blocks b with b_lo <= b < b_hi."""
+        blocks = [b for b in A.my_blocks if b_lo <= b < b_hi]
+        if not blocks:
+            return 0, 0
+        return A.col_off[blocks[0]], sum(A.width(b) for b in blocks)
+
+    def apply_panel(k: int, buf, pairs, b_lo: int, b_hi: int, swap_only: bool):
+        """Row swaps (+ TRSM + GEMM unless swap_only) of panel k on the local blocks in [b_lo, b_hi)."""
+        off, ncols = local_range(b_lo, b_hi)
+        if ncols == 0:
+            return
+        r0, w = k * nb, A.width(k)
+        rows = n - r0
+        base = A.data.data_ptr() + 8 * off * n
+        ops.permute_rows(base, n, n, ncols, pairs)
+        if swap_only:
+            return
+        ops.trsm_left_unit_lower(w, ncols, buf.data_ptr(), rows, base + 8 * r0, n)
+        if rows > w:
+            ops.gemm_update(rows - w, w, ncols, buf.data_ptr() + 8 * w, rows, base + 8 * r0, n, base + 8 * (r0 + w), n)
+
+    if block_cyclic_owner(0, world) == rank:
+        factor_and_pack(0, bufs[0], pivs[0])
+    pending = (bcast(0, bufs[0], pivs[0]), 0)
+    for k in range(A.nblocks):
+        works, bi = pending
+        for wk in works:
+            wk.wait()
+        buf, piv = bufs[bi], pivs[bi]
+        ph = piv.cpu()
+        pairs = [(int(ph[1 + 2 * i]), int(ph[2 + 2 * i])) for i in range(int(ph[0]))]
+        all_pairs.extend(pairs)
+        # the owner's panel block is already swapped; swap the local blocks left of k
+        apply_panel(k, buf, pairs, 0, k, True)
+        nxt = k + 1
+        lo = k + 1
+        if nxt < A.nblocks:
+            nbi = 1 - bi
+            if block_cyclic_owner(nxt, world) == rank:
+                apply_panel(k, buf, pairs, nxt, nxt + 1, False)      # look-ahead: the next panel's block first
+                factor_and_pack(nxt, bufs[nbi], pivs[nbi])
+                lo = nxt + 1
+            if use_side:
+                side.wait_stream(torch.cuda.current_stream(A.data.device))
+                with torch.cuda.stream(side):
+                    pending = (bcast(nxt, bufs[nbi], pivs[nbi]), nbi)
+            else:
+                pending = (bcast(nxt, bufs[nbi], pivs[nbi]), nbi)
+        apply_panel(k, buf, pairs, lo, A.nblocks, False)
+        if use_side:
+            torch.cuda.current_stream(A.data.device).wait_stream(side)
+    if A.data.is_cuda:
+        torch.cuda.synchronize(A.data.device)
+    return all_pairs

@@ -91,6 +91,28 @@ class _OracleOps:
         t = np.tril(self._mat(t_ptr, w, w, ldt)); b = self._mat(b_ptr, m, w, ldb)
         b[...] = sl.solve_triangular(t, b.T, lower=True).T
 
+    def lu_panel(self, ptr, m, w, ld):
+        mn = min(m, w)
+        swaps = (self.C.c_size_t * (2 * max(mn, 1)))(); ns = self.C.c_size_t(0)
+        self.O.lib().na_oracle_lu_f64(m, w, ptr, ld, swaps, self.C.addressof(ns))
+        return [(swaps[2 * i], swaps[2 * i + 1]) for i in range(ns.value)]
+
+    def permute_rows(self, ptr, nrows, ld, ncols, pairs):
+        if not pairs or ncols == 0:
+            return
+        a = self._mat(ptr, nrows, ncols, ld)
+        for i, j in pairs:
+            a[[i, j]] = a[[j, i]]
+
+    def trsm_left_unit_lower(self, m, n, t_ptr, ldt, b_ptr, ldb):
+        import scipy.linalg as sl
+        t = np.tril(self._mat(t_ptr, m, m, ldt), -1) + np.eye(m); b = self._mat(b_ptr, m, n, ldb)
+        b[...] = sl.solve_triangular(t, b, lower=True, unit_diagonal=True)
+
+    def gemm_update(self, m, k, n, a_ptr, lda, b_ptr, ldb, c_ptr, ldc):
+        a = self._mat(a_ptr, m, k, lda); b = self._mat(b_ptr, k, n, ldb); c = self._mat(c_ptr, m, n, ldc)
+        c -= a @ b
+
     def syrk_lower_update(self, m, k, n, p_ptr, ldp, c_ptr, ldc):
         p = self._mat(p_ptr, m, k, ldp); c = self._mat(c_ptr, m, n, ldc)
         upd = p @ p[:n, :].T
@@ -125,3 +147,36 @@ def test_block_cyclic_cholesky_logic(tmp_path, oracle):
         assert np.load(tmp_path / f"st_{world}_1.npy")[0] == 0
         assert np.abs(np.tril(got) - lref).max() <= 1e-12 * np.abs(lref).max()
         assert np.array_equal(np.triu(got, 1), np.triu(spd, 1))          # strict upper never touched
+
+
+def _lu_worker(rank, world, port, n, nb, out_dir):
+    sys.path.insert(0, ROOT)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    import oracle as O
+    from nalgebra_b200.distributed import ColumnBlockCyclic, lu_block_cyclic
+    ops = _OracleOps()
+    A = ColumnBlockCyclic(n, nb, rank, world, ops)
+    full0 = O.uniform(n, n, 6) - 0.3
+    for b in A.my_blocks:                                   # this rank's columns of the shared test matrix
+        w = A.width(b)
+        ops._mat(A.ptr(0, b), n, w, n)[...] = full0[:, b * nb: b * nb + w]
+    pairs = lu_block_cyclic(A)
+    full = A.gather_to(0)
+    if rank == 0:
+        np.save(os.path.join(out_dir, f"lu_{world}.npy"), full.numpy())
+        np.save(os.path.join(out_dir, f"sw_{world}.npy"), np.array(pairs, dtype=np.int64).reshape(-1, 2))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_block_cyclic_lu_logic(tmp_path, oracle):
+    n, nb = 100, 16
+    a = oracle.uniform(n, n, 6) - 0.3
+    lu_ref, sw_ref = oracle.lu(a)
+    for world, port in ((2, 29623), (3, 29624)):
+        mp.spawn(_lu_worker, args=(world, port, n, nb, str(tmp_path)), nprocs=world, join=True)
+        got = np.load(tmp_path / f"lu_{world}.npy"); sw = np.load(tmp_path / f"sw_{world}.npy")
+        assert np.array_equal(sw, sw_ref.astype(np.int64))                # PermutationSequence identical
+        assert np.abs(got - lu_ref).max() <= 1e-11
