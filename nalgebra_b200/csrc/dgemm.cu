@@ -223,6 +223,14 @@ dgemm_tma_dmma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
 
     int stage = 0;
     uint32_t phase = 0;
+    // Deferred release: the empty-barrier arrive for a stage is issued only after the NEXT stage's
+    // full-barrier wait.  ptxas sinks the last k-step's DMMAs below an arrive placed at the end of the
+    // iteration, which leaves that step's final LDS still in flight when the slot is handed back; under a
+    // backed-up LSU (beta != 0 epilogues of the sibling warps) the refill TMA then won the race about once
+    // per 1e8 stage reads and one A fragment of one warp came from the wrong k-block.  The spin-wait loop
+    // in between is a scheduling barrier: every DMMA of the previous stage (hence every LDS result) has
+    // issued before the arrive below.
+    int release_stage = -1;
     for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
         int tm, tn;
         const int tile = t / p.splits, split = t - tile * p.splits;
@@ -237,6 +245,7 @@ dgemm_tma_dmma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
 
         for (int kb = kb0; kb < kb1; ++kb) {
             ptx::mbar_wait(bar_base + 8 * stage, phase);
+            if (release_stage >= 0 && lane == 0) ptx::mbar_arrive(bar_base + 8 * (STAGES + release_stage));
             const uint8_t* sptr = smem_gen + stage * STAGE_BYTES;
 #pragma unroll
             for (int kk = 0; kk < 4; ++kk) {
@@ -250,31 +259,55 @@ dgemm_tma_dmma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
 #pragma unroll
                     for (int j = 0; j < NT; ++j) ptx::dmma884(acc[i][j][0], acc[i][j][1], a[i], b[j]);
             }
-            __syncwarp();
-            if (lane == 0) ptx::mbar_arrive(bar_base + 8 * (STAGES + stage));
+            release_stage = stage;
             if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
 
         // ---- epilogue: C = alpha*acc + beta*C (C untouched-before-write when beta == 0) ----
+        // The C reads are issued in batches of 32 independent loads BEFORE any store of the batch: with
+        // load/store interleaved per element every load waits for the previous store (possible aliasing)
+        // and the beta != 0 epilogue cost ~14 us per tile instead of ~1.
         const long long gm0 = (long long)tm * BM + row0, gn0 = (long long)tn * BN + col0;
         const bool use_beta = p.beta != 0.0;
+        double* cbase = p.C + (long long)split * p.split_stride;
+        long long rows[MT];
+        bool rok[MT];
 #pragma unroll
-        for (int j = 0; j < NT; ++j) {
+        for (int i = 0; i < MT; ++i) { rows[i] = gm0 + frag_row<A_KMAJOR>(i, g); rok[i] = rows[i] < p.M; }
 #pragma unroll
-            for (int e = 0; e < 2; ++e) {
-                const long long col = gn0 + frag_row<B_KMAJOR>(j, 2 * q + e);
-                if (col >= p.N) continue;
-                double* ccol = p.C + (long long)split * p.split_stride + col * p.ldc;
+        for (int jh = 0; jh < NT; jh += 2) {
+            double cv[2][2][MT];
+            long long cols[2][2];
+            bool cok[2][2];
 #pragma unroll
-                for (int i = 0; i < MT; ++i) {
-                    const long long row = gm0 + frag_row<A_KMAJOR>(i, g);
-                    if (row >= p.M) continue;
-                    if (p.lower_only && row < col) continue;
-                    double v = p.alpha * acc[i][j][e];
-                    if (use_beta) v += p.beta * ccol[row];
-                    ccol[row] = v;
+            for (int jj = 0; jj < 2; ++jj)
+#pragma unroll
+                for (int e = 0; e < 2; ++e) {
+                    cols[jj][e] = gn0 + frag_row<B_KMAJOR>(jh + jj, 2 * q + e);
+                    cok[jj][e] = cols[jj][e] < p.N;
                 }
+            if (use_beta) {
+#pragma unroll
+                for (int jj = 0; jj < 2; ++jj)
+#pragma unroll
+                    for (int e = 0; e < 2; ++e)
+#pragma unroll
+                        for (int i = 0; i < MT; ++i) {
+                            const bool ok = cok[jj][e] && rok[i] && !(p.lower_only && rows[i] < cols[jj][e]);
+                            cv[jj][e][i] = ok ? cbase[rows[i] + cols[jj][e] * p.ldc] : 0.0;
+                        }
             }
+#pragma unroll
+            for (int jj = 0; jj < 2; ++jj)
+#pragma unroll
+                for (int e = 0; e < 2; ++e)
+#pragma unroll
+                    for (int i = 0; i < MT; ++i) {
+                        const bool ok = cok[jj][e] && rok[i] && !(p.lower_only && rows[i] < cols[jj][e]);
+                        double v = p.alpha * acc[i][jh + jj][e];
+                        if (use_beta) v += p.beta * cv[jj][e][i];
+                        if (ok) cbase[rows[i] + cols[jj][e] * p.ldc] = v;
+                    }
         }
     }
 }

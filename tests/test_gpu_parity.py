@@ -165,6 +165,17 @@ def test_gemm_full_size_linearity_on_device(L):
     C2 = Cd.clone()
     _capi.check(L.na_dgemm_dev(n, n, n, 0.5, A.data_ptr(), 1, n, B.data_ptr(), 1, n, 0.5, C2.data_ptr(), 1, n, s))
     assert (C2 - Cd).abs().max().item() <= tol
+    # Regression (round 1): a shared-memory stage was handed back to the TMA producer while the last
+    # fragment load of the stage was still in flight; under beta != 0 epilogues about one warp tile per
+    # launch picked up 4 k-values of the wrong k-block (error ~1e-4 relative, far inside `tol`).  The kernel
+    # is deterministic, so repeated launches must agree bit for bit over the whole matrix, and the beta path
+    # must reproduce C to rounding (|C| ~ 4100, ulp ~ 9e-13).
+    for _ in range(6):
+        C3 = Cd.clone()
+        _capi.check(L.na_dgemm_dev(n, n, n, 0.5, A.data_ptr(), 1, n, B.data_ptr(), 1, n, 0.5, C3.data_ptr(), 1, n, s))
+        assert torch.equal(C3, C2)
+        assert (C3 - Cd).abs().max().item() <= 1e-8
+        del C3
 
 
 # ---- Cholesky --------------------------------------------------------------------------------------
