@@ -121,6 +121,12 @@ static int chol_rp_override() {
     static int v = [] { const char* e = getenv("NAB_CHOL_RP"); return e ? atoi(e) : 0; }();
     return v;
 }
+// Off by default: at N = 16384 the panel chain is as long as the bulk update in most steps, so part B would
+// mostly wait for the panel (measured 60.9 ms with the split vs 56.9 ms without).
+static bool chol_split() {
+    static bool v = [] { const char* e = getenv("NAB_CHOL_SPLIT"); return e ? atoi(e) != 0 : false; }();
+    return v;
+}
 #define CHOL_NB (chol_nb())
 
 static int chol_panel(const CholCtx& c, cudaStream_t sp, size_t n, size_t j, size_t jb, int sm_limit, double* tmp, size_t ldt) {
@@ -148,18 +154,20 @@ static int chol_panel(const CholCtx& c, cudaStream_t sp, size_t n, size_t j, siz
 
 static int chol_lookahead(const CholCtx& c, size_t n) {
     cudaStream_t sp = c.s, su = nullptr;
-    cudaEvent_t ev_p = nullptr, ev_u = nullptr;
+    cudaEvent_t ev_p = nullptr, ev_u = nullptr, ev_d = nullptr;
     NAB_CUDA(cudaStreamCreateWithFlags(&su, cudaStreamNonBlocking));
     NAB_CUDA(cudaEventCreateWithFlags(&ev_p, cudaEventDisableTiming));
     NAB_CUDA(cudaEventCreateWithFlags(&ev_u, cudaEventDisableTiming));
+    NAB_CUDA(cudaEventCreateWithFlags(&ev_d, cudaEventDisableTiming));
     Scratch tmp;
     const size_t ldt = round_up(n, 2);
     int st = tmp.alloc(ldt * IBs * sizeof(double), sp);
     const int sms = ctx().sm_count;
+    const size_t NB = CHOL_NB;
     bool bulk_pending = false;
-    if (st == NA_OK) st = chol_panel(c, sp, n, 0, std::min(CHOL_NB, n), 0, tmp.as<double>(), ldt);
-    for (size_t j = 0; st == NA_OK && j + CHOL_NB < n; j += CHOL_NB) {
-        const size_t jb = CHOL_NB, jn = j + jb, jbn = std::min(CHOL_NB, n - jn);
+    if (st == NA_OK) st = chol_panel(c, sp, n, 0, std::min(NB, n), 0, tmp.as<double>(), ldt);
+    for (size_t j = 0; st == NA_OK && j + NB < n; j += NB) {
+        const size_t jb = NB, jn = j + jb, jbn = std::min(NB, n - jn);
         const double* pj = c.a + j * c.lda;               // panel j: columns [j, j+jb)
         // la(j): next panel's columns, rows jn.., needs bulk(j - nb) finished on those columns
         if (bulk_pending) { cudaStreamWaitEvent(sp, ev_u, 0); }
@@ -169,24 +177,49 @@ static int chol_lookahead(const CholCtx& c, size_t n) {
         cudaEventRecord(ev_p, sp);
         const size_t jr = jn + jbn, rr = n - jr;          // bulk region: rows/cols [jr, n)
         int rp = 0;
+        size_t wa = 0;                                    // columns of the bulk region updated while the panel runs
         if (rr > 0) {
-            rp = (int)((double)sms * 2.0 * CHOL_NB / ((double)(n - jn) + 2.0 * CHOL_NB));
+            rp = (int)((double)sms * 2.0 * NB / ((double)(n - jn) + 2.0 * NB));
             rp = std::max(16, std::min(rp, sms - 28));
             if (chol_rp_override() > 0) rp = chol_rp_override();
+            // bulk(j) in two parts.  Part A (the leftmost `wa` columns) runs on sms - rp CTAs next to panel(j + nb);
+            // part B (the rest) starts when that panel is done and takes the whole GPU, so the rp SMs reserved
+            // for the latency-bound panel idle only while it actually runs.  wa from a simple time model:
+            // panel = leaves * 130 us + its own TRSM/SYRK flops on rp SMs; part A = the same time on sms - rp SMs.
+            const double m_p = (double)(n - jn), w_p = (double)jbn;
+            const double panel_flops = m_p * w_p * w_p;   // TRSM-as-GEMM + in-panel SYRK, ~ m * w^2
+            const double t_panel = (w_p / 128.0) * 130e-6 + panel_flops / (rp * kSmFlops);
+            const double target = t_panel * (sms - rp) * kSmFlops;
+            for (wa = IBs; wa < rr; wa += IBs) {
+                const double area = (double)wa * ((double)rr - 0.5 * (double)wa);
+                if (2.0 * (double)jb * area >= target) break;
+            }
+            if (wa + 2 * IBs >= rr || !chol_split()) wa = rr;
             cudaStreamWaitEvent(su, ev_p, 0);
             set_gemm_sm_limit(sms - rp);
-            st = dgemm_device(su, true, rr, jb, rr, -1.0, pj + jr, 1, (ptrdiff_t)c.lda, pj + jr, (ptrdiff_t)c.lda, 1, 1.0,
+            st = dgemm_device(su, true, rr, jb, wa, -1.0, pj + jr, 1, (ptrdiff_t)c.lda, pj + jr, (ptrdiff_t)c.lda, 1, 1.0,
                               c.a + jr + jr * c.lda, 1, (ptrdiff_t)c.lda);
             set_gemm_sm_limit(0);
             if (st != NA_OK) break;
+        }
+        st = chol_panel(c, sp, n, jn, jbn, rp, tmp.as<double>(), ldt);
+        if (st != NA_OK) break;
+        if (rr > 0) {
+            if (wa < rr) {
+                cudaEventRecord(ev_d, sp);
+                cudaStreamWaitEvent(su, ev_d, 0);
+                const size_t jq = jr + wa, rq = n - jq;
+                st = dgemm_device(su, true, rq, jb, rq, -1.0, pj + jq, 1, (ptrdiff_t)c.lda, pj + jq, (ptrdiff_t)c.lda, 1, 1.0,
+                                  c.a + jq + jq * c.lda, 1, (ptrdiff_t)c.lda);
+                if (st != NA_OK) break;
+            }
             cudaEventRecord(ev_u, su);
             bulk_pending = true;
         }
-        st = chol_panel(c, sp, n, jn, jbn, rp, tmp.as<double>(), ldt);
     }
     if (bulk_pending) cudaStreamWaitEvent(sp, ev_u, 0);
     cudaStreamSynchronize(su);
-    cudaEventDestroy(ev_p); cudaEventDestroy(ev_u); cudaStreamDestroy(su);
+    cudaEventDestroy(ev_p); cudaEventDestroy(ev_u); cudaEventDestroy(ev_d); cudaStreamDestroy(su);
     return st;
 }
 

@@ -8,6 +8,7 @@
 // GETF2 panel kernel.  Whole rows are swapped, so the packed result has the reference's layout
 // (identical to LAPACK getrf).  Everything stays on the device: no host pivoting.
 #include <algorithm>
+#include <cstdlib>
 #include <vector>
 
 #include "common.cuh"
@@ -62,11 +63,12 @@ static int lu_rec(const LuCtx& c, size_t j0, size_t nc) {
 // ------------------------------------------------------------------------------------------------
 constexpr size_t LU_NB = 512;
 
-static int lu_right_update(const LuCtx& c, cudaStream_t st, size_t j, size_t jb, size_t x0, size_t nx, const void* ws_outer) {
+static int lu_right_update(const LuCtx& c, cudaStream_t st, size_t j, size_t jb, size_t x0, size_t nx, const void* ws_outer,
+                           const double* inv_l11) {
     if (nx == 0) return NA_OK;
     double* ax = c.a + x0 * c.lda;                      // column x0, row 0
     NAB_TRY(rowperm_apply(st, ax, c.lda, nx, std::min(2 * jb, c.M), ws_outer, c.M));
-    NAB_TRY(trsm_left(st, true, true, jb, c.a + j + j * c.lda, 1, (ptrdiff_t)c.lda, nullptr, nullptr, ax + j, 1, (ptrdiff_t)c.lda, nx));
+    NAB_TRY(trsm_left(st, true, true, jb, c.a + j + j * c.lda, 1, (ptrdiff_t)c.lda, nullptr, inv_l11, ax + j, 1, (ptrdiff_t)c.lda, nx));
     const size_t m2 = c.M - j - jb;
     if (m2 > 0)
         NAB_TRY(dgemm_device(st, false, m2, jb, nx, -1.0, c.a + (j + jb) + j * c.lda, 1, (ptrdiff_t)c.lda, ax + j, 1, (ptrdiff_t)c.lda,
@@ -74,15 +76,24 @@ static int lu_right_update(const LuCtx& c, cudaStream_t st, size_t j, size_t jb,
     return NA_OK;
 }
 
+static bool lu_split() {
+    static bool v = [] { const char* e = getenv("NAB_LU_SPLIT"); return e ? atoi(e) != 0 : true; }();
+    return v;
+}
+
 static int lu_lookahead(LuCtx c, size_t N, size_t mn) {
     cudaStream_t sp = c.s, su = nullptr;
-    cudaEvent_t ev_p = nullptr, ev_u = nullptr;
+    cudaEvent_t ev_p = nullptr, ev_u = nullptr, ev_d = nullptr;
     NAB_CUDA(cudaStreamCreateWithFlags(&su, cudaStreamNonBlocking));
     NAB_CUDA(cudaEventCreateWithFlags(&ev_p, cudaEventDisableTiming));
     NAB_CUDA(cudaEventCreateWithFlags(&ev_u, cudaEventDisableTiming));
-    Scratch wso[2];
+    NAB_CUDA(cudaEventCreateWithFlags(&ev_d, cudaEventDisableTiming));
+    Scratch wso[2], invb[2];      // per-step permutation lists and inverses of L11's diagonal blocks, double-buffered
     int st = wso[0].alloc(rowperm_workspace_bytes(c.M), sp);
     if (st == NA_OK) st = wso[1].alloc(rowperm_workspace_bytes(c.M), sp);
+    const size_t inv_bytes = ceil_div(LU_NB, (size_t)kInvBlock) * kInvBlock * kInvBlock * sizeof(double);
+    if (st == NA_OK) st = invb[0].alloc(inv_bytes, sp);
+    if (st == NA_OK) st = invb[1].alloc(inv_bytes, sp);
     const int sms = ctx().sm_count;
     const int g_getf2 = (int)ceil_div(c.M, (size_t)384) + 2;          // CTAs the 64-wide GETF2 leaf needs at full height
     bool bulk_pending = false;
@@ -92,32 +103,51 @@ static int lu_lookahead(LuCtx c, size_t N, size_t mn) {
         const size_t jb = std::min(LU_NB, mn - j), jn = j + jb;
         const size_t jbn = jn < mn ? std::min(LU_NB, mn - jn) : 0;
         st = rowperm_build(sp, c.iota + j, c.ipiv + j, jb, 1, c.M, wso[par].p);
+        if (st == NA_OK) st = trtri_blocks(sp, c.a + j + j * c.lda, 1, (ptrdiff_t)c.lda, jb, true, true, nullptr, invb[par].as<double>());
         if (st != NA_OK) break;
         cudaEventRecord(ev_p, sp);
         // la(j): the next panel's columns, whole GPU (needs bulk(j - nb) finished on them)
         if (bulk_pending) cudaStreamWaitEvent(sp, ev_u, 0);
-        st = lu_right_update(c, sp, j, jb, jn, jbn, wso[par].p);
+        st = lu_right_update(c, sp, j, jb, jn, jbn, wso[par].p, invb[par].as<double>());
         if (st != NA_OK) break;
-        // bulk(j) on the second stream: left swaps + everything right of the next panel
-        int rp = std::max(g_getf2, std::min(sms / 2, (int)((double)sms * 3.0 * LU_NB / ((double)(c.M - jn) + 3.0 * LU_NB))));
+        // bulk(j) on the second stream: left swaps + everything right of the next panel, in two parts.
+        // Part A (the leftmost `wa` columns) runs on sms - rp CTAs next to panel(j + nb); part B (the rest)
+        // starts when that panel is done and takes the whole GPU: the rp SMs reserved for the latency-bound
+        // panel chain (~5.3 us per column whatever its height) idle only while the panel actually runs.
+        const int rp = std::max(g_getf2, std::min(sms / 2, (int)((double)sms * 3.0 * LU_NB / ((double)(c.M - jn) + 3.0 * LU_NB))));
+        const size_t x0 = jn + jbn, nx = N - x0, m2 = c.M - jn;
+        size_t wa = nx;
+        if (jbn && nx && m2 && lu_split()) {
+            const double t_panel = (double)jbn * 5.3e-6;
+            const double target = t_panel * (sms - rp) * kSmFlops;
+            wa = round_up((size_t)(target / (2.0 * (double)m2 * (double)jb)) + 1, 128);
+            if (wa + 256 >= nx) wa = nx;
+        }
         cudaStreamWaitEvent(su, ev_p, 0);
         set_gemm_sm_limit(jbn ? sms - rp : 0);
         st = rowperm_apply(su, c.a, c.lda, j, std::min(2 * jb, c.M), wso[par].p, c.M);
-        if (st == NA_OK) st = lu_right_update(c, su, j, jb, jn + jbn, N - (jn + jbn), wso[par].p);
+        if (st == NA_OK) st = lu_right_update(c, su, j, jb, x0, wa, wso[par].p, invb[par].as<double>());
         set_gemm_sm_limit(0);
         if (st != NA_OK) break;
-        cudaEventRecord(ev_u, su);
-        bulk_pending = true;
-        if (jbn == 0) break;
-        // panel(j + nb) on the caller's stream, concurrently with bulk(j)
+        if (jbn == 0) { cudaEventRecord(ev_u, su); bulk_pending = true; break; }
+        // panel(j + nb) on the caller's stream, concurrently with part A
         set_gemm_sm_limit(rp);
         st = lu_rec(c, jn, jbn);
         set_gemm_sm_limit(0);
+        if (st != NA_OK) break;
+        if (wa < nx) {
+            cudaEventRecord(ev_d, sp);
+            cudaStreamWaitEvent(su, ev_d, 0);
+            st = lu_right_update(c, su, j, jb, x0 + wa, nx - wa, wso[par].p, invb[par].as<double>());
+            if (st != NA_OK) break;
+        }
+        cudaEventRecord(ev_u, su);
+        bulk_pending = true;
         par ^= 1;
     }
     if (bulk_pending) cudaStreamWaitEvent(sp, ev_u, 0);
     cudaStreamSynchronize(su);
-    cudaEventDestroy(ev_p); cudaEventDestroy(ev_u); cudaStreamDestroy(su);
+    cudaEventDestroy(ev_p); cudaEventDestroy(ev_u); cudaEventDestroy(ev_d); cudaStreamDestroy(su);
     return st;
 }
 

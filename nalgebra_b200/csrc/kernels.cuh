@@ -13,6 +13,8 @@ int dgemm_device(cudaStream_t s, bool lower_only, size_t m, size_t k, size_t n, 
                  double beta, double* c, ptrdiff_t rsc, ptrdiff_t csc);
 int fill_spd(cudaStream_t s, double* a, size_t nrows, size_t ncols, size_t lda, uint64_t seed, size_t row0, size_t col0, size_t n);
 void set_gemm_sm_limit(int limit);   // 0 = all SMs; thread local
+// Per-SM throughput the look-ahead schedule models assume for K = nb update GEMMs (36.3 TFLOP/s / 148 SMs at ~90 %).
+constexpr double kSmFlops = 0.22e12;
 int pack_strided(cudaStream_t s, double* dst, size_t ldd, const double* src, ptrdiff_t rs, ptrdiff_t cs, size_t rows, size_t cols);
 int scatter_strided(cudaStream_t s, double* dst, ptrdiff_t rs, ptrdiff_t cs, const double* src, size_t lds, size_t rows, size_t cols);
 int scale_strided(cudaStream_t s, double* c, ptrdiff_t rs, ptrdiff_t cs, size_t rows, size_t cols, double beta);

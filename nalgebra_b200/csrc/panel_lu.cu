@@ -337,24 +337,43 @@ int getf2_panel(cudaStream_t st, double* a_panel, size_t lda, size_t m, size_t w
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(1024, 1)
 perm_from_swaps_kernel(const int* __restrict__ sa, const int* __restrict__ sb, int K, int sa_stride, int n,
-                       int* __restrict__ gperm, int use_global, int* __restrict__ dest, int* __restrict__ src, int* __restrict__ count) {
+                       int* __restrict__ gperm, int use_global, int swaps_in_smem,
+                       int* __restrict__ dest, int* __restrict__ src, int* __restrict__ count) {
     extern __shared__ int sperm[];
     int* perm = use_global ? gperm : sperm;
+    // The swap list is staged in shared memory (when it fits) so that the serial simulation below never
+    // waits on global memory; only the rows the list names are initialised and compacted (<= 2K of n).
+    int* sx = sperm + (use_global ? 0 : n);
+    int* sy = sx + K;
     const int tid = threadIdx.x, nt = blockDim.x;
-    for (int r = tid; r < n; r += nt) perm[r] = r;
     __shared__ int s_count;
     if (tid == 0) s_count = 0;
+    for (int s = tid; s < K; s += nt) {
+        const int x = sa[(size_t)s * sa_stride], y = sb[(size_t)s * sa_stride];
+        if (swaps_in_smem) { sx[s] = x; sy[s] = y; }
+        perm[x] = x; perm[y] = y;                  // racing writers store the same value
+    }
     __syncthreads();
     if (tid == 0) {
-        for (int s = 0; s < K; ++s) {
-            const int x = sa[(size_t)s * sa_stride], y = sb[(size_t)s * sa_stride];
-            if (x != y) { const int t = perm[x]; perm[x] = perm[y]; perm[y] = t; }
+        if (swaps_in_smem) {
+            for (int s = 0; s < K; ++s) {
+                const int x = sx[s], y = sy[s];
+                if (x != y) { const int t = perm[x]; perm[x] = perm[y]; perm[y] = t; }
+            }
+        } else {
+            for (int s = 0; s < K; ++s) {
+                const int x = sa[(size_t)s * sa_stride], y = sb[(size_t)s * sa_stride];
+                if (x != y) { const int t = perm[x]; perm[x] = perm[y]; perm[y] = t; }
+            }
         }
     }
     __syncthreads();
-    // compact the touched rows (order irrelevant)
-    for (int r = tid; r < n; r += nt) {
-        const int v = perm[r];
+    // compact the touched rows (order irrelevant); a row named several times is claimed once: the claim
+    // resets its entry to the identity, so later claimants see an untouched row
+    for (int s = tid; s < 2 * K; s += nt) {
+        const int h = s >= K ? 1 : 0, si = s - h * K;
+        const int r = swaps_in_smem ? (h ? sy[si] : sx[si]) : (h ? sb[(size_t)si * sa_stride] : sa[(size_t)si * sa_stride]);
+        const int v = atomicExch(&perm[r], r);
         if (v != r) { const int i = atomicAdd(&s_count, 1); dest[i] = r; src[i] = v; }
     }
     __syncthreads();
@@ -400,11 +419,15 @@ size_t rowperm_workspace_bytes(size_t n) { return (3 * n + 64) * sizeof(int); }
 int rowperm_build(cudaStream_t st, const int* sa, const int* sb, size_t K, size_t stride, size_t n, void* ws) {
     int* w = static_cast<int*>(ws);
     int* count = w; int* dest = w + 64; int* src = dest + n; int* gperm = src + n;
-    const bool use_global = n * sizeof(int) > 200 * 1024;
-    const size_t smem = use_global ? 0 : n * sizeof(int);
+    const size_t budget = 200 * 1024;
+    const bool use_global = n * sizeof(int) > budget;
+    const size_t perm_bytes = use_global ? 0 : n * sizeof(int);
+    const bool swaps_in_smem = perm_bytes + 2 * K * sizeof(int) <= budget;
+    const size_t smem = perm_bytes + (swaps_in_smem ? 2 * K * sizeof(int) : 0);
     static std::once_flag once;
     std::call_once(once, [] { cudaFuncSetAttribute(perm_from_swaps_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); });
-    perm_from_swaps_kernel<<<1, 1024, smem, st>>>(sa, sb, (int)K, (int)stride, (int)n, gperm, use_global ? 1 : 0, dest, src, count);
+    perm_from_swaps_kernel<<<1, 1024, smem, st>>>(sa, sb, (int)K, (int)stride, (int)n, gperm, use_global ? 1 : 0, swaps_in_smem ? 1 : 0,
+                                                   dest, src, count);
     NAB_LAUNCH_CHECK();
     return NA_OK;
 }
