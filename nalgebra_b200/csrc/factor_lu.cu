@@ -8,6 +8,7 @@
 // GETF2 panel kernel.  Whole rows are swapped, so the packed result has the reference's layout
 // (identical to LAPACK getrf).  Everything stays on the device: no host pivoting.
 #include <algorithm>
+#include <cstdio>
 #include <cstdlib>
 #include <vector>
 
@@ -24,6 +25,7 @@ struct LuCtx {
     int* iota;                // device, 0..mn-1
     void* ws_getf2; void* ws_perm;
     int* seq_state;           // host counter of exchange sequence numbers used in ws_getf2
+    int getf2_limit = 0;      // max CTAs of a GETF2 leaf (look-ahead: the SMs kept free of the bulk GEMM); 0 = no limit
 };
 
 static int lu_apply_swaps(const LuCtx& c, size_t k0, size_t K, double* cols, size_t ncols) {
@@ -35,15 +37,25 @@ static int lu_apply_swaps(const LuCtx& c, size_t k0, size_t K, double* cols, siz
 static int lu_rec(const LuCtx& c, size_t j0, size_t nc) {
     if (nc == 0) return NA_OK;
     double* ajj = c.a + j0 + j0 * c.lda;
-    if (nc <= c.W) return getf2_panel(c.s, ajj, c.lda, c.M - j0, nc, j0, c.ipiv, c.ws_getf2, c.seq_state);
+    if (nc <= c.W) return getf2_panel(c.s, ajj, c.lda, c.M - j0, nc, j0, c.ipiv, c.ws_getf2, c.seq_state, c.getf2_limit);
     size_t n1 = round_up(nc / 2, c.W);
     if (n1 >= nc) n1 = nc - c.W;
     const size_t n2 = nc - n1;
     NAB_TRY(lu_rec(c, j0, n1));
     double* a12 = ajj + n1 * c.lda;
     NAB_TRY(lu_apply_swaps(c, j0, n1, a12 - j0, n2));                         // whole rows: columns start at row 0
-    // U12 = L11^-1 * A12 (unit lower)
-    NAB_TRY(trsm_left(c.s, true, true, n1, ajj, 1, (ptrdiff_t)c.lda, nullptr, nullptr, a12, 1, (ptrdiff_t)c.lda, n2));
+    // U12 = L11^-1 * A12 (unit lower): direct substitution kernels for the narrow nodes of the panel recursion
+    // (n1 <= 128; 256 = two of them around one GEMM), blocked inverse-based TRSM above that
+    if (n1 <= 128) {
+        NAB_TRY(trsm_unit_lower_small(c.s, n1, ajj, c.lda, a12, c.lda, n2));
+    } else if (n1 <= 256) {
+        const size_t h = 128, r = n1 - h;
+        NAB_TRY(trsm_unit_lower_small(c.s, h, ajj, c.lda, a12, c.lda, n2));
+        NAB_TRY(dgemm_device(c.s, false, r, h, n2, -1.0, ajj + h, 1, (ptrdiff_t)c.lda, a12, 1, (ptrdiff_t)c.lda, 1.0, a12 + h, 1, (ptrdiff_t)c.lda));
+        NAB_TRY(trsm_unit_lower_small(c.s, r, ajj + h + h * c.lda, c.lda, a12 + h, c.lda, n2));
+    } else {
+        NAB_TRY(trsm_left(c.s, true, true, n1, ajj, 1, (ptrdiff_t)c.lda, nullptr, nullptr, a12, 1, (ptrdiff_t)c.lda, n2));
+    }
     // A22 -= A21 * U12
     const size_t m2 = c.M - j0 - n1;
     if (m2 > 0)
@@ -81,6 +93,32 @@ static bool lu_split() {
     return v;
 }
 
+// NAB_LU_TRACE=1: per-step timeline of the look-ahead schedule (CUDA events on both streams), printed to stderr.
+struct LuTrace {
+    bool on = false;
+    cudaEvent_t t0 = nullptr;
+    struct Rec { const char* what; size_t j; cudaEvent_t a, b; };
+    std::vector<Rec> recs;
+    LuTrace() { const char* e = getenv("NAB_LU_TRACE"); on = e && atoi(e) != 0; }
+    cudaEvent_t mark(cudaStream_t s) {
+        cudaEvent_t e = nullptr;
+        if (on) { cudaEventCreate(&e); cudaEventRecord(e, s); }
+        return e;
+    }
+    void add(const char* what, size_t j, cudaEvent_t a, cudaEvent_t b) { if (on) recs.push_back({what, j, a, b}); }
+    void dump() {
+        if (!on) return;
+        cudaDeviceSynchronize();
+        for (auto& r : recs) {
+            float s0 = 0, d = 0;
+            cudaEventElapsedTime(&s0, t0, r.a); cudaEventElapsedTime(&d, r.a, r.b);
+            fprintf(stderr, "lu_trace j=%6zu %-6s start %9.3f ms  dur %8.3f ms\n", r.j, r.what, s0, d);
+            cudaEventDestroy(r.a); cudaEventDestroy(r.b);
+        }
+        cudaEventDestroy(t0);
+    }
+};
+
 static int lu_lookahead(LuCtx c, size_t N, size_t mn) {
     cudaStream_t sp = c.s, su = nullptr;
     cudaEvent_t ev_p = nullptr, ev_u = nullptr, ev_d = nullptr;
@@ -98,18 +136,25 @@ static int lu_lookahead(LuCtx c, size_t N, size_t mn) {
     const int g_getf2 = (int)ceil_div(c.M, (size_t)384) + 2;          // CTAs the 64-wide GETF2 leaf needs at full height
     bool bulk_pending = false;
     int par = 0;
+    LuTrace tr;
+    tr.t0 = tr.mark(sp);
+    cudaEvent_t t_first = tr.mark(sp);
     if (st == NA_OK) st = lu_rec(c, 0, std::min(LU_NB, mn));
+    tr.add("panel", 0, t_first, tr.mark(sp));
     for (size_t j = 0; st == NA_OK; j += LU_NB) {
         const size_t jb = std::min(LU_NB, mn - j), jn = j + jb;
         const size_t jbn = jn < mn ? std::min(LU_NB, mn - jn) : 0;
         st = rowperm_build(sp, c.iota + j, c.ipiv + j, jb, 1, c.M, wso[par].p);
         if (st == NA_OK) st = trtri_blocks(sp, c.a + j + j * c.lda, 1, (ptrdiff_t)c.lda, jb, true, true, nullptr, invb[par].as<double>());
         if (st != NA_OK) break;
-        cudaEventRecord(ev_p, sp);
-        // la(j): the next panel's columns, whole GPU (needs bulk(j - nb) finished on them)
+        // la(j): the next panel's columns, whole GPU (needs bulk(j - nb) finished on them).  It is on the critical
+        // chain, so bulk(j) is released only after it: side by side with part A it ran on the rp free SMs only.
         if (bulk_pending) cudaStreamWaitEvent(sp, ev_u, 0);
+        cudaEvent_t t_la = tr.mark(sp);
         st = lu_right_update(c, sp, j, jb, jn, jbn, wso[par].p, invb[par].as<double>());
         if (st != NA_OK) break;
+        tr.add("la", j, t_la, tr.mark(sp));
+        cudaEventRecord(ev_p, sp);
         // bulk(j) on the second stream: left swaps + everything right of the next panel, in two parts.
         // Part A (the leftmost `wa` columns) runs on sms - rp CTAs next to panel(j + nb); part B (the rest)
         // starts when that panel is done and takes the whole GPU: the rp SMs reserved for the latency-bound
@@ -118,28 +163,36 @@ static int lu_lookahead(LuCtx c, size_t N, size_t mn) {
         const size_t x0 = jn + jbn, nx = N - x0, m2 = c.M - jn;
         size_t wa = nx;
         if (jbn && nx && m2 && lu_split()) {
-            const double t_panel = (double)jbn * 5.3e-6;
+            const double t_panel = (double)jbn * (4.5e-6 + 2.5e-6 * (double)m2 / 16384.0);   // measured 2.3 .. 4.0 ms per 512
             const double target = t_panel * (sms - rp) * kSmFlops;
             wa = round_up((size_t)(target / (2.0 * (double)m2 * (double)jb)) + 1, 128);
             if (wa + 256 >= nx) wa = nx;
         }
         cudaStreamWaitEvent(su, ev_p, 0);
+        cudaEvent_t t_a = tr.mark(su);
         set_gemm_sm_limit(jbn ? sms - rp : 0);
         st = rowperm_apply(su, c.a, c.lda, j, std::min(2 * jb, c.M), wso[par].p, c.M);
         if (st == NA_OK) st = lu_right_update(c, su, j, jb, x0, wa, wso[par].p, invb[par].as<double>());
         set_gemm_sm_limit(0);
         if (st != NA_OK) break;
+        tr.add("bulkA", j, t_a, tr.mark(su));
         if (jbn == 0) { cudaEventRecord(ev_u, su); bulk_pending = true; break; }
         // panel(j + nb) on the caller's stream, concurrently with part A
+        cudaEvent_t t_p = tr.mark(sp);
         set_gemm_sm_limit(rp);
+        c.getf2_limit = rp;
         st = lu_rec(c, jn, jbn);
+        c.getf2_limit = 0;
         set_gemm_sm_limit(0);
         if (st != NA_OK) break;
+        tr.add("panel", jn, t_p, tr.mark(sp));
         if (wa < nx) {
             cudaEventRecord(ev_d, sp);
             cudaStreamWaitEvent(su, ev_d, 0);
+            cudaEvent_t t_b = tr.mark(su);
             st = lu_right_update(c, su, j, jb, x0 + wa, nx - wa, wso[par].p, invb[par].as<double>());
             if (st != NA_OK) break;
+            tr.add("bulkB", j, t_b, tr.mark(su));
         }
         cudaEventRecord(ev_u, su);
         bulk_pending = true;
@@ -147,6 +200,7 @@ static int lu_lookahead(LuCtx c, size_t N, size_t mn) {
     }
     if (bulk_pending) cudaStreamWaitEvent(sp, ev_u, 0);
     cudaStreamSynchronize(su);
+    tr.dump();
     cudaEventDestroy(ev_p); cudaEventDestroy(ev_u); cudaEventDestroy(ev_d); cudaStreamDestroy(su);
     return st;
 }

@@ -37,11 +37,14 @@ int set_identity(cudaStream_t st, double* a, size_t lda, size_t rows, size_t col
 // ---- panel_lu.cu ---------------------------------------------------------------------------------
 constexpr int kLuPanel = 128;      // widest GETF2 leaf panel
 size_t getf2_workspace_bytes();
-int getf2_panel(cudaStream_t st, double* a_panel, size_t lda, size_t m, size_t w, size_t j0, int* ipiv, void* ws, int* seq_state);
+int getf2_panel(cudaStream_t st, double* a_panel, size_t lda, size_t m, size_t w, size_t j0, int* ipiv, void* ws, int* seq_state,
+                int cta_limit = 0);
 size_t rowperm_workspace_bytes(size_t n);
 int rowperm_build(cudaStream_t st, const int* sa, const int* sb, size_t K, size_t stride, size_t n, void* ws);
 int rowperm_apply(cudaStream_t st, double* a, size_t lda, size_t ncols, size_t max_touched, const void* ws, size_t n);
 int iota_int(cudaStream_t st, int* p, size_t n, int offset);
+// B (n1 x nrhs, column-major) <- L^-1 B, L = unit lower triangle of l (n1 <= 128); one launch, no inverse blocks
+int trsm_unit_lower_small(cudaStream_t st, size_t n1, const double* l, size_t ldl, double* b, size_t ldb, size_t nrhs);
 
 // ---- panel_qr.cu ---------------------------------------------------------------------------------
 constexpr int kQrLeaf = 32;        // GEQR2 leaf panel width

@@ -300,7 +300,8 @@ __global__ void __launch_bounds__(256, 1) getf2_coop_kernel(const Getf2Params p)
 constexpr size_t kGetf2MaxCtas = 160;
 size_t getf2_workspace_bytes() { return (2 * kGetf2MaxCtas * (kLuPanel + 2) + 2 * kLuPanel) * sizeof(double2); }
 
-int getf2_panel(cudaStream_t st, double* a_panel, size_t lda, size_t m, size_t w, size_t j0, int* ipiv, void* ws, int* seq_state) {
+int getf2_panel(cudaStream_t st, double* a_panel, size_t lda, size_t m, size_t w, size_t j0, int* ipiv, void* ws, int* seq_state,
+                int cta_limit) {
     if (m == 0 || w == 0) return NA_OK;
     if (w > (size_t)kLuPanel) { set_error("getf2: panel too wide"); return NA_EINVAL; }
     const int sms = ctx().sm_count;
@@ -311,6 +312,9 @@ int getf2_panel(cudaStream_t st, double* a_panel, size_t lda, size_t m, size_t w
     if (G > (size_t)sms) { set_error("getf2: panel of %zu x %zu rows does not fit %d SMs of shared memory", m, w, sms); return NA_EINVAL; }
     // spread rows evenly; use more CTAs (up to 64) when rows are plentiful
     size_t G_pref = std::min<size_t>(std::min<size_t>(64, (size_t)sms), ceil_div(m, (size_t)128));
+    // cta_limit: SMs the caller keeps free for this cooperative launch while a persistent GEMM holds the rest;
+    // a grid that does not fit would wait for that GEMM to finish (measured: 5.4 ms instead of 4.0 ms per panel)
+    if (cta_limit > 0) G_pref = std::min<size_t>(G_pref, (size_t)cta_limit);
     if (G_pref > G) G = G_pref;
     size_t rp = round_up(ceil_div(m, G), 32);
     G = ceil_div(m, rp);
@@ -458,6 +462,93 @@ int rowperm_apply(cudaStream_t st, double* a, size_t lda, size_t ncols, size_t m
         permute_rows_scatter_kernel<<<blocks, 256, 0, st>>>(a + c0 * lda, (long long)lda, dest, count, tmp.as<double>(), (long long)max_touched, (long long)nc);
         NAB_LAUNCH_CHECK();
     }
+    return NA_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Direct small TRSM for the LU panel recursion: B <- L^-1 B with L the n1 x n1 UNIT lower triangle
+// stored in `l` (n1 <= 128), B n1 x nrhs column-major, in place.  One thread owns one column of B and
+// keeps 64 of its entries in registers; L is read as shared-memory broadcasts.  Replaces the
+// TRTRI + GEMM + copy sequence (3 launches, 75-110 us) on the latency-critical panel chain by one
+// launch of a few microseconds.
+// ------------------------------------------------------------------------------------------------
+constexpr int kTrsmCols = 64;      // columns of B (threads) per CTA
+
+// x (64 registers) <- solve with the unit-lower 64 x 64 block in sl (column-major, ld 64; rows/cols >= nv
+// are identity padding).
+__device__ __forceinline__ void trsm64_regs(const double* __restrict__ sl, double (&x)[64]) {
+#pragma unroll
+    for (int k = 0; k < 63; ++k) {
+        const double xk = x[k];
+#pragma unroll
+        for (int i = k + 1; i < 64; ++i) x[i] = fma(-sl[i + k * 64], xk, x[i]);
+    }
+}
+
+__device__ __forceinline__ void load_l_block(double* sl, const double* __restrict__ l, long long ldl, int r0, int c0, int n1,
+                                             bool diag_block) {
+    // sl(i, k) = L(r0 + i, c0 + k); outside the matrix or (diag_block) on/above the diagonal: 0
+    for (int idx = threadIdx.x; idx < 64 * 64; idx += blockDim.x) {
+        const int i = idx & 63, k = idx >> 6;
+        const int r = r0 + i, c = c0 + k;
+        double v = 0.0;
+        if (r < n1 && c < n1 && (!diag_block || i > k)) v = l[r + (long long)c * ldl];
+        sl[i + k * 64] = v;
+    }
+}
+
+__global__ void __launch_bounds__(kTrsmCols) trsm_unit_lower_small_kernel(const double* __restrict__ l, long long ldl, int n1,
+                                                                         double* __restrict__ b, long long ldb, int nrhs) {
+    __shared__ double sl[64 * 64];
+    const int col = blockIdx.x * kTrsmCols + threadIdx.x;
+    const bool active = col < nrhs;
+    double* bc = b + (long long)(active ? col : 0) * ldb;
+    double x[64];
+    // ---- top block ----
+    load_l_block(sl, l, ldl, 0, 0, n1, true);
+#pragma unroll
+    for (int i = 0; i < 64; ++i) x[i] = (active && i < n1) ? bc[i] : 0.0;
+    __syncthreads();
+    trsm64_regs(sl, x);
+    if (active) {
+#pragma unroll
+        for (int i = 0; i < 64; ++i) if (i < n1) bc[i] = x[i];
+    }
+    if (n1 <= 64) return;
+    // ---- bottom rows: b_bot -= L21 * x_top (one entry at a time, x_top stays in registers) ----
+    __syncthreads();
+    load_l_block(sl, l, ldl, 64, 0, n1, false);
+    __syncthreads();
+    if (active) {
+        for (int i = 0; i < n1 - 64; ++i) {
+            double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+#pragma unroll
+            for (int k = 0; k < 64; k += 4) {
+                a0 = fma(sl[i + (k + 0) * 64], x[k + 0], a0);
+                a1 = fma(sl[i + (k + 1) * 64], x[k + 1], a1);
+                a2 = fma(sl[i + (k + 2) * 64], x[k + 2], a2);
+                a3 = fma(sl[i + (k + 3) * 64], x[k + 3], a3);
+            }
+            bc[64 + i] -= (a0 + a1) + (a2 + a3);
+        }
+    }
+    __syncthreads();
+    load_l_block(sl, l, ldl, 64, 64, n1, true);
+#pragma unroll
+    for (int i = 0; i < 64; ++i) x[i] = (active && 64 + i < n1) ? bc[64 + i] : 0.0;
+    __syncthreads();
+    trsm64_regs(sl, x);
+    if (active) {
+#pragma unroll
+        for (int i = 0; i < 64; ++i) if (64 + i < n1) bc[64 + i] = x[i];
+    }
+}
+
+int trsm_unit_lower_small(cudaStream_t st, size_t n1, const double* l, size_t ldl, double* b, size_t ldb, size_t nrhs) {
+    if (n1 == 0 || nrhs == 0) return NA_OK;
+    if (n1 > 128) { set_error("trsm_unit_lower_small: n1 > 128"); return NA_EINVAL; }
+    trsm_unit_lower_small_kernel<<<(unsigned)ceil_div(nrhs, (size_t)kTrsmCols), kTrsmCols, 0, st>>>(l, (long long)ldl, (int)n1, b, (long long)ldb, (int)nrhs);
+    NAB_LAUNCH_CHECK();
     return NA_OK;
 }
 
