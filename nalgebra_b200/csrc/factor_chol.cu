@@ -179,8 +179,20 @@ static int chol_lookahead(const CholCtx& c, size_t n) {
         int rp = 0;
         size_t wa = 0;                                    // columns of the bulk region updated while the panel runs
         if (rr > 0) {
-            rp = (int)((double)sms * 2.0 * NB / ((double)(n - jn) + 2.0 * NB));
-            rp = std::max(16, std::min(rp, sms - 28));
+            // SMs for the panel chain: balance panel(rp) against bulk(sms - rp) with a simple time model
+            // (4 leaves of ~100 us each + m*w^2 TRSM/SYRK flops at the K = 128 rate; bulk at the K = nb rate)
+            {
+                const double m_p = (double)(n - jn), w_p = (double)jbn;
+                const double bulk_flops = (double)jb * (double)rr * (double)rr;          // 2 * K * rr^2 / 2
+                double best = 1e30;
+                rp = 16;
+                for (int r = 16; r <= sms - 28; r += 4) {
+                    const double tp = (w_p / 128.0) * 100e-6 + m_p * w_p * w_p / (r * 0.15e12);
+                    const double tb = bulk_flops / ((sms - r) * kSmFlops);
+                    const double t = std::max(tp, tb);
+                    if (t < best) { best = t; rp = r; }
+                }
+            }
             if (chol_rp_override() > 0) rp = chol_rp_override();
             // bulk(j) in two parts.  Part A (the leftmost `wa` columns) runs on sms - rp CTAs next to panel(j + nb);
             // part B (the rest) starts when that panel is done and takes the whole GPU, so the rp SMs reserved

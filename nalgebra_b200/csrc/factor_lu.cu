@@ -159,11 +159,18 @@ static int lu_lookahead(LuCtx c, size_t N, size_t mn) {
         // Part A (the leftmost `wa` columns) runs on sms - rp CTAs next to panel(j + nb); part B (the rest)
         // starts when that panel is done and takes the whole GPU: the rp SMs reserved for the latency-bound
         // panel chain (~5.3 us per column whatever its height) idle only while the panel actually runs.
-        const int rp = std::max(g_getf2, std::min(sms / 2, (int)((double)sms * 3.0 * LU_NB / ((double)(c.M - jn) + 3.0 * LU_NB))));
         const size_t x0 = jn + jbn, nx = N - x0, m2 = c.M - jn;
+        const double t_panel = (double)jbn * (4.5e-6 + 2.5e-6 * (double)m2 / 16384.0);   // measured 2.3 .. 4.0 ms per 512
+        // SMs for the panel chain: what the 64-wide GETF2 leaf needs at this height (384 rows per CTA); more (the
+        // leaf then spreads its rows over more CTAs) once the whole bulk update fits beside the panel anyway.
+        int rp = std::min(g_getf2, (int)ceil_div(m2, (size_t)384) + 2);
+        {
+            const double bulk_flops = 2.0 * (double)m2 * (double)jb * (double)nx;
+            for (int r = rp; r <= std::min(72, sms / 2); r += 4)
+                if (bulk_flops / ((sms - r) * kSmFlops) <= t_panel) rp = r;
+        }
         size_t wa = nx;
         if (jbn && nx && m2 && lu_split()) {
-            const double t_panel = (double)jbn * (4.5e-6 + 2.5e-6 * (double)m2 / 16384.0);   // measured 2.3 .. 4.0 ms per 512
             const double target = t_panel * (sms - rp) * kSmFlops;
             wa = round_up((size_t)(target / (2.0 * (double)m2 * (double)jb)) + 1, 128);
             if (wa + 256 >= nx) wa = nx;

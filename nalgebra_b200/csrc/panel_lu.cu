@@ -7,6 +7,7 @@
 //   diag == 0 -> skip the column (no swap, no scaling)               (lu.rs:107-110)
 //   swap whole rows, multiply the column by 1/diag (reciprocal, lu.rs:344-349), rank-1 update.
 #include <algorithm>
+#include <cstdlib>
 
 #include "common.cuh"
 #include "kernels.cuh"
