@@ -537,8 +537,19 @@ __global__ void splitk_reduce_kernel(double* __restrict__ c, long long ldc, cons
     const long long total = m * n;
     for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
         const long long r = idx % m, col = idx / m;
+        // partial sums are added in split order (deterministic); 8 independent loads in flight per thread --
+        // one load per iteration made this kernel latency-bound (50 us for 148 splits of a 32 x 224 block)
+        const double* w0 = ws + r + col * ldw;
         double s = 0.0;
-        for (int k = 0; k < splits; ++k) s += ws[k * split_stride + r + col * ldw];
+        int k = 0;
+        for (; k + 8 <= splits; k += 8) {
+            double v8[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) v8[i] = w0[(long long)(k + i) * split_stride];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) s += v8[i];
+        }
+        for (; k < splits; ++k) s += w0[(long long)k * split_stride];
         double v = alpha * s;
         if (beta != 0.0) v += beta * c[r + col * ldc];
         c[r + col * ldc] = v;
@@ -574,9 +585,22 @@ static int gemm_colmajor_c(cudaStream_t s, bool lower_only, size_t m, size_t n, 
         // split-K for few-tile / deep-K shapes (V^T C in the blocked QR, Gram matrices)
         const int sms = ctx().sm_count;
         const int kblocks = (int)ceil_div(k, BK);
-        if (p.num_tiles * 2 <= sms && kblocks >= 64) {
-            // as many K-slices as there are idle SMs, but at least 16 k-blocks (256 deep) per slice
-            int splits = std::min(std::min(sms / p.num_tiles, kblocks / 16), 148);
+        auto wave_eff = [&](int sp) {
+            const long long items = (long long)p.num_tiles * sp;
+            return (double)items / (double)(ceil_div((size_t)items, (size_t)sms) * (size_t)sms);
+        };
+        if (kblocks >= 64 && wave_eff(1) < 0.8) {
+            // K-slices chosen for wave efficiency over the persistent grid (work items = tiles x slices are dealt
+            // round-robin to the CTAs): the fewest slices that fill >= 93 % of the last wave, else the best found;
+            // at least 16 k-blocks (256 deep) per slice.  (60 tiles: 2 slices = 81 %, 7 slices = 95 %.)
+            const int smax = std::min(kblocks / 16, 148);
+            int splits = 1;
+            double best = wave_eff(1);
+            for (int sp = 2; sp <= smax; ++sp) {
+                const double e = wave_eff(sp);
+                if (e > best + 1e-9) { best = e; splits = sp; }
+                if (best >= 0.93) break;
+            }
             while (splits > 1 && (size_t)splits * round_up(m, 2) * n * sizeof(double) > (512ull << 20)) --splits;
             if (splits > 1) {
                 const int kbs = (int)ceil_div((size_t)kblocks, (size_t)splits);

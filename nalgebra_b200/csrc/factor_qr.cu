@@ -36,7 +36,7 @@ static int build_s_from_v(cudaStream_t s, size_t mc, size_t w, const double* v, 
 }
 
 struct QrWork {
-    Scratch tau, vw, smat, wk, csign, ws_geqr2;
+    Scratch tau, vw, smat, wk, csign, ws_geqr2, ws_gram;
     size_t ldv = 0, lds = 0, ldw = 0;
     int seq_state = 0;
     int init(cudaStream_t s, size_t m, size_t ncols_max, size_t k) {
@@ -48,6 +48,8 @@ struct QrWork {
         NAB_TRY(csign.alloc((k + 2) * sizeof(double), s));
         NAB_TRY(ws_geqr2.alloc(geqr2_workspace_bytes(), s));
         NAB_CUDA(cudaMemsetAsync(ws_geqr2.p, 0, geqr2_workspace_bytes(), s));
+        NAB_TRY(ws_gram.alloc(extract_v_gram_workspace_bytes(), s));
+        NAB_CUDA(cudaMemsetAsync(ws_gram.p, 0, extract_v_gram_workspace_bytes(), s));
         return NA_OK;
     }
 };
@@ -71,8 +73,7 @@ int qr_device(cudaStream_t s, size_t m, size_t n, double* a, size_t lda, double*
             NAB_TRY(geqr2_panel(s, apanel, lda, ml, lw, tau + jl, w.ws_geqr2.p, &w.seq_state));
             const size_t nc = (j + jb) - (jl + lw);          // rest of the outer panel
             if (nc > 0) {
-                NAB_TRY(extract_v(s, vw, w.ldv, apanel, lda, ml, lw, tau + jl, 0));
-                NAB_TRY(build_s_from_v(s, ml, lw, vw, w.ldv, tau + jl, w.smat.as<double>(), w.lds));
+                NAB_TRY(extract_v_gram(s, vw, w.ldv, apanel, lda, ml, lw, tau + jl, w.smat.as<double>(), w.lds, w.ws_gram.p));
                 NAB_TRY(apply_block_reflector(s, ml, lw, vw, w.ldv, w.smat.as<double>(), w.lds, true,
                                               apanel + lw * lda, lda, nc, w.wk.as<double>(), w.ldw));
             }

@@ -52,6 +52,10 @@ size_t geqr2_workspace_bytes();
 int geqr2_panel(cudaStream_t st, double* a_panel, size_t lda, size_t m, size_t w, double* tau, void* ws, int* seq_state);
 int extract_v(cudaStream_t st, double* vw, size_t ldv, const double* a, size_t lda, size_t m, size_t w, const double* tau, int mode);
 int build_s(cudaStream_t st, double* g, size_t ldg, size_t w, const double* tau);
+// leaf panels (w <= 32): clean V into vw and S = triu(V^T V, 1) + diag(1/tau) into smat, one launch
+size_t extract_v_gram_workspace_bytes();
+int extract_v_gram(cudaStream_t st, double* vw, size_t ldv, const double* a, size_t lda, size_t m, size_t w, const double* tau,
+                   double* smat, size_t lds, void* ws);
 int tau_from_diag(cudaStream_t st, double* tau_out, const double* diag, size_t n);
 int qr_convert_to_nalgebra(cudaStream_t st, double* a, size_t lda, size_t m, size_t n, const double* tau, double* csign, double* diag);
 int qr_signs_from_diag(cudaStream_t st, const double* diag, size_t k, double* csign);
