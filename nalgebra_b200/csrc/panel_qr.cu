@@ -239,37 +239,46 @@ int extract_v(cudaStream_t st, double* vw, size_t ldv, const double* a, size_t l
 // ------------------------------------------------------------------------------------------------
 // Leaf panels (w <= 32): V extraction fused with the Gram matrix and S = T^-1 = triu(V^T V, 1) + diag(1/tau).
 // Replaces extract_v + a 32 x 32 x m split-K GEMM (a 128 x 128 tile padded 16x, 148 K-slices) + its
-// reduction + build_s (160 us per leaf) by one launch: each CTA cleans a slab of rows into vw, keeps it in
-// shared memory in chunks of 128 rows, accumulates its 32 x 32 partial Gram matrix (thread = one row i and
-// four columns j), and the last CTA to finish adds the partials in slab order (deterministic) and writes S.
+// reduction + build_s (160 us per leaf) by two small launches: each CTA cleans chunks of 128 rows into vw
+// (16 independent loads per thread in flight), keeps the chunk in shared memory, accumulates its 32 x 32
+// partial Gram matrix (thread = one row i and four columns j); gram_finish adds the partials in CTA order
+// (deterministic) and writes S.
 // ------------------------------------------------------------------------------------------------
-constexpr int kGramSlabs = 64;
+constexpr int kGramCtas = 148;
 __global__ void __launch_bounds__(256) extract_v_gram_kernel(double* __restrict__ vw, long long ldv, const double* __restrict__ a,
                                                              long long lda, long long m, int w, const double* __restrict__ tau,
-                                                             long long rows_per_slab, double* __restrict__ part,
-                                                             unsigned int* __restrict__ counter, double* __restrict__ smat, long long lds) {
+                                                             double* __restrict__ part) {
     __shared__ double tile[128 * 33];
     __shared__ double tau_s[32];
-    __shared__ bool s_last;
     const int tid = threadIdx.x, i = tid & 31, j0 = tid >> 5;
     if (tid < 32) tau_s[tid] = tid < w ? tau[tid] : 0.0;
     __syncthreads();
     double acc[4] = {0.0, 0.0, 0.0, 0.0};
-    const long long r_begin = (long long)blockIdx.x * rows_per_slab, r_end = min(m, r_begin + rows_per_slab);
-    for (long long c0 = r_begin; c0 < r_end; c0 += 128) {
-        const int nr = (int)min((long long)128, r_end - c0);
-        for (int idx = tid; idx < 128 * w; idx += 256) {
-            const int r = idx & 127, j = idx >> 7;
-            double v = 0.0;
-            if (r < nr) {
-                const long long gr = c0 + r;
-                if (tau_s[j] != 0.0) v = gr > j ? a[gr + j * lda] : (gr == j ? 1.0 : 0.0);
-                vw[gr + j * ldv] = v;
+    const long long nchunks = (m + 127) / 128;
+    for (long long ch = blockIdx.x; ch < nchunks; ch += gridDim.x) {
+        const long long c0 = ch * 128;
+        const int nr = (int)min((long long)128, m - c0);
+        // 16 independent loads per thread in flight (the chunk is 128 rows x 32 columns), then the stores
+        double v[16];
+#pragma unroll
+        for (int u = 0; u < 16; ++u) {
+            const int idx = tid + u * 256, r = idx & 127, j = idx >> 7;
+            const long long gr = c0 + r;
+            v[u] = (j < w && r < nr && gr > j && tau_s[j] != 0.0) ? a[gr + j * lda] : 0.0;
+        }
+#pragma unroll
+        for (int u = 0; u < 16; ++u) {
+            const int idx = tid + u * 256, r = idx & 127, j = idx >> 7;
+            const long long gr = c0 + r;
+            if (j < w) {
+                if (gr == j && tau_s[j] != 0.0) v[u] = 1.0;
+                if (r < nr) vw[gr + j * ldv] = v[u];
+                tile[r * 33 + j] = v[u];
             }
-            tile[r * 33 + j] = v;
         }
         __syncthreads();
         if (i < w) {
+#pragma unroll 4
             for (int r = 0; r < nr; ++r) {
                 const double vi = tile[r * 33 + i];
 #pragma unroll
@@ -280,40 +289,40 @@ __global__ void __launch_bounds__(256) extract_v_gram_kernel(double* __restrict_
     }
 #pragma unroll
     for (int k = 0; k < 4; ++k) part[(size_t)blockIdx.x * 1024 + i * 32 + j0 + 8 * k] = acc[k];
-    __threadfence();
-    __syncthreads();
-    if (tid == 0) s_last = atomicAdd(counter, 1u) == gridDim.x - 1;
-    __syncthreads();
-    if (!s_last) return;
-    __threadfence();
-    if (tid == 0) *counter = 0;                     // ready for the next leaf (stream order)
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-        const int j = j0 + 8 * k;
-        if (i >= w || j >= w) continue;
-        double v = 0.0;
-        if (i < j) {
-            const double* g0 = part + i * 32 + j;
-            for (unsigned g = 0; g < gridDim.x; ++g) v += __ldcg(g0 + (size_t)g * 1024);
-        } else if (i == j) {
-            v = (tau_s[j] != 0.0) ? 1.0 / tau_s[j] : 1.0;
-        }
-        smat[i + j * lds] = v;
-    }
 }
-size_t extract_v_gram_workspace_bytes() { return (size_t)kGramSlabs * 1024 * sizeof(double) + 256; }
-// ws: extract_v_gram_workspace_bytes(), its last 256 bytes zero-initialised once (the ticket counter).
+
+// S (w x w, ld lds) = triu(sum of the per-CTA partial Gram matrices, 1) + diag(1/tau); CTA order (deterministic).
+__global__ void __launch_bounds__(1024) gram_finish_kernel(double* __restrict__ smat, long long lds, int w, const double* __restrict__ tau,
+                                                           const double* __restrict__ part, int G) {
+    const int i = threadIdx.x & 31, j = threadIdx.x >> 5;
+    if (i >= w || j >= w) return;
+    double v = 0.0;
+    if (i < j) {
+        const double* g0 = part + i * 32 + j;
+        int g = 0;
+        for (; g + 8 <= G; g += 8) {
+            double t[8];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) t[k] = g0[(size_t)(g + k) * 1024];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) v += t[k];
+        }
+        for (; g < G; ++g) v += g0[(size_t)g * 1024];
+    } else if (i == j) {
+        v = (tau[j] != 0.0) ? 1.0 / tau[j] : 1.0;
+    }
+    smat[i + j * lds] = v;
+}
+size_t extract_v_gram_workspace_bytes() { return (size_t)kGramCtas * 1024 * sizeof(double); }
 int extract_v_gram(cudaStream_t st, double* vw, size_t ldv, const double* a, size_t lda, size_t m, size_t w, const double* tau,
                    double* smat, size_t lds, void* ws) {
     if (m == 0 || w == 0) return NA_OK;
     if (w > 32) { set_error("extract_v_gram: w > 32"); return NA_EINVAL; }
-    const size_t slabs = std::min<size_t>(kGramSlabs, ceil_div(m, (size_t)128));
-    const size_t rows_per = round_up(ceil_div(m, slabs), 128);
-    const unsigned grid = (unsigned)ceil_div(m, rows_per);
+    const unsigned grid = (unsigned)std::min<size_t>(std::min<size_t>(kGramCtas, (size_t)ctx().sm_count), ceil_div(m, (size_t)128));
     double* part = static_cast<double*>(ws);
-    unsigned int* counter = reinterpret_cast<unsigned int*>(part + (size_t)kGramSlabs * 1024);
-    extract_v_gram_kernel<<<grid, 256, 0, st>>>(vw, (long long)ldv, a, (long long)lda, (long long)m, (int)w, tau, (long long)rows_per,
-                                                part, counter, smat, (long long)lds);
+    extract_v_gram_kernel<<<grid, 256, 0, st>>>(vw, (long long)ldv, a, (long long)lda, (long long)m, (int)w, tau, part);
+    NAB_LAUNCH_CHECK();
+    gram_finish_kernel<<<1, 1024, 0, st>>>(smat, (long long)lds, (int)w, tau, part, (int)grid);
     NAB_LAUNCH_CHECK();
     return NA_OK;
 }
