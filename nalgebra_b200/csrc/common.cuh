@@ -10,7 +10,9 @@
 #include <cstdint>
 #include <cstdio>
 #include <cstring>
+#include <cstdlib>
 #include <mutex>
+#include <vector>
 
 #include "../../include/nalgebra_b200.h"
 
@@ -66,6 +68,35 @@ struct Scratch {
     int alloc(size_t bytes, cudaStream_t stream);
     ~Scratch();
     template <typename T> T* as() const { return static_cast<T*>(p); }
+};
+
+// ---- optional timelines ----------------------------------------------------------------------------
+// NAB_LU_TRACE=1 / NAB_CHOL_TRACE=1: start and duration of the phases of a blocked driver, taken with CUDA
+// events on the streams the work runs on, printed to stderr when the factorization is done.
+struct Timeline {
+    bool on = false;
+    const char* tag = "";
+    cudaEvent_t t0 = nullptr;
+    struct Rec { const char* what; size_t j; cudaEvent_t a, b; };
+    std::vector<Rec> recs;
+    Timeline(const char* env, const char* tag_) : tag(tag_) { const char* e = getenv(env); on = e && atoi(e) != 0; }
+    cudaEvent_t mark(cudaStream_t s) {
+        cudaEvent_t e = nullptr;
+        if (on) { cudaEventCreate(&e); cudaEventRecord(e, s); }
+        return e;
+    }
+    void start(cudaStream_t s) { t0 = mark(s); }
+    void add(const char* what, size_t j, cudaEvent_t a, cudaEvent_t b) { if (on) recs.push_back({what, j, a, b}); }
+    void dump() {
+        if (!on) return;
+        cudaDeviceSynchronize();
+        for (auto& r : recs) {
+            float s0 = 0, d = 0;
+            cudaEventElapsedTime(&s0, t0, r.a); cudaEventElapsedTime(&d, r.a, r.b);
+            fprintf(stderr, "%s j=%6zu %-7s start %9.3f ms  dur %8.3f ms\n", tag, r.j, r.what, s0, d);
+        }
+        recs.clear();      // diagnostic mode only: the events (shared between records) are left to the context
+    }
 };
 
 inline size_t ceil_div(size_t a, size_t b) { return (a + b - 1) / b; }

@@ -7,6 +7,7 @@
 // O(n^3) work is restructured as recursive panel + TRSM + SYRK so that it runs on the DMMA GEMM
 // engine.  Parity is therefore on results (residuals, failure column), not on operation order.
 #include <algorithm>
+#include <cstdio>
 #include <cstdlib>
 
 #include "common.cuh"
@@ -165,57 +166,69 @@ static int chol_lookahead(const CholCtx& c, size_t n) {
     const int sms = ctx().sm_count;
     const size_t NB = CHOL_NB;
     bool bulk_pending = false;
+    Timeline tr("NAB_CHOL_TRACE", "chol_trace");
+    tr.start(sp);
+    cudaEvent_t t_first = tr.mark(sp);
     if (st == NA_OK) st = chol_panel(c, sp, n, 0, std::min(NB, n), 0, tmp.as<double>(), ldt);
+    tr.add("panel", 0, t_first, tr.mark(sp));
     for (size_t j = 0; st == NA_OK && j + NB < n; j += NB) {
         const size_t jb = NB, jn = j + jb, jbn = std::min(NB, n - jn);
         const double* pj = c.a + j * c.lda;               // panel j: columns [j, j+jb)
         // la(j): next panel's columns, rows jn.., needs bulk(j - nb) finished on those columns
         if (bulk_pending) { cudaStreamWaitEvent(sp, ev_u, 0); }
+        cudaEvent_t t_la = tr.mark(sp);
         st = dgemm_device(sp, true, n - jn, jb, jbn, -1.0, pj + jn, 1, (ptrdiff_t)c.lda, pj + jn, (ptrdiff_t)c.lda, 1, 1.0,
                           c.a + jn + jn * c.lda, 1, (ptrdiff_t)c.lda);
         if (st != NA_OK) break;
+        tr.add("la", j, t_la, tr.mark(sp));
         cudaEventRecord(ev_p, sp);
         const size_t jr = jn + jbn, rr = n - jr;          // bulk region: rows/cols [jr, n)
         int rp = 0;
         size_t wa = 0;                                    // columns of the bulk region updated while the panel runs
         if (rr > 0) {
-            // SMs for the panel chain: balance panel(rp) against bulk(sms - rp) with a simple time model
-            // (4 leaves of ~100 us each + m*w^2 TRSM/SYRK flops at the K = 128 rate; bulk at the K = nb rate)
+            // SMs for the panel chain from a simple time model: panel(r) = 4 leaves of ~100 us + m*w^2 TRSM/SYRK
+            // flops at the K = 128 rate on r SMs; bulk at the K = nb rate.  Without the split the step costs
+            // max(panel(r), bulk(sms - r)); with it, part A (the leftmost `wa` columns) runs beside the panel on
+            // sms - r CTAs and part B takes the whole GPU when the panel is done: panel(r) + rest / sms.
+            const bool split = chol_split();
+            double t_panel = 0.0;
             {
                 const double m_p = (double)(n - jn), w_p = (double)jbn;
                 const double bulk_flops = (double)jb * (double)rr * (double)rr;          // 2 * K * rr^2 / 2
                 double best = 1e30;
                 rp = 16;
-                for (int r = 16; r <= sms - 28; r += 4) {
+                for (int r = split ? 8 : 16; r <= sms - 28; r += 4) {
                     const double tp = (w_p / 128.0) * 100e-6 + m_p * w_p * w_p / (r * 0.15e12);
                     const double tb = bulk_flops / ((sms - r) * kSmFlops);
-                    const double t = std::max(tp, tb);
-                    if (t < best) { best = t; rp = r; }
+                    const double rest = std::max(0.0, bulk_flops - tp * (sms - r) * kSmFlops);
+                    const double t = split ? tp + rest / (sms * kSmFlops) : std::max(tp, tb);
+                    if (t < best) { best = t; rp = r; t_panel = tp; }
                 }
             }
             if (chol_rp_override() > 0) rp = chol_rp_override();
-            // bulk(j) in two parts.  Part A (the leftmost `wa` columns) runs on sms - rp CTAs next to panel(j + nb);
-            // part B (the rest) starts when that panel is done and takes the whole GPU, so the rp SMs reserved
-            // for the latency-bound panel idle only while it actually runs.  wa from a simple time model:
-            // panel = leaves * 130 us + its own TRSM/SYRK flops on rp SMs; part A = the same time on sms - rp SMs.
-            const double m_p = (double)(n - jn), w_p = (double)jbn;
-            const double panel_flops = m_p * w_p * w_p;   // TRSM-as-GEMM + in-panel SYRK, ~ m * w^2
-            const double t_panel = (w_p / 128.0) * 130e-6 + panel_flops / (rp * kSmFlops);
-            const double target = t_panel * (sms - rp) * kSmFlops;
-            for (wa = IBs; wa < rr; wa += IBs) {
-                const double area = (double)wa * ((double)rr - 0.5 * (double)wa);
-                if (2.0 * (double)jb * area >= target) break;
+            wa = rr;
+            if (split) {
+                const double target = t_panel * (sms - rp) * kSmFlops;
+                for (wa = IBs; wa < rr; wa += IBs) {
+                    const double area = (double)wa * ((double)rr - 0.5 * (double)wa);
+                    if (2.0 * (double)jb * area >= target) break;
+                }
+                if (wa + 2 * IBs >= rr) wa = rr;
             }
-            if (wa + 2 * IBs >= rr || !chol_split()) wa = rr;
             cudaStreamWaitEvent(su, ev_p, 0);
+            cudaEvent_t t_a = tr.mark(su);
             set_gemm_sm_limit(sms - rp);
             st = dgemm_device(su, true, rr, jb, wa, -1.0, pj + jr, 1, (ptrdiff_t)c.lda, pj + jr, (ptrdiff_t)c.lda, 1, 1.0,
                               c.a + jr + jr * c.lda, 1, (ptrdiff_t)c.lda);
             set_gemm_sm_limit(0);
             if (st != NA_OK) break;
+            tr.add("bulkA", j, t_a, tr.mark(su));
         }
+        cudaEvent_t t_p = tr.mark(sp);
         st = chol_panel(c, sp, n, jn, jbn, rp, tmp.as<double>(), ldt);
         if (st != NA_OK) break;
+        tr.add("panel", jn, t_p, tr.mark(sp));
+        if (tr.on) fprintf(stderr, "chol_trace j=%6zu rp=%d wa=%zu rr=%zu\n", j, rp, wa, rr);
         if (rr > 0) {
             if (wa < rr) {
                 cudaEventRecord(ev_d, sp);
@@ -231,6 +244,7 @@ static int chol_lookahead(const CholCtx& c, size_t n) {
     }
     if (bulk_pending) cudaStreamWaitEvent(sp, ev_u, 0);
     cudaStreamSynchronize(su);
+    tr.dump();
     cudaEventDestroy(ev_p); cudaEventDestroy(ev_u); cudaEventDestroy(ev_d); cudaStreamDestroy(su);
     return st;
 }

@@ -26,6 +26,7 @@ struct LuCtx {
     void* ws_getf2; void* ws_perm;
     int* seq_state;           // host counter of exchange sequence numbers used in ws_getf2
     int getf2_limit = 0;      // max CTAs of a GETF2 leaf (look-ahead: the SMs kept free of the bulk GEMM); 0 = no limit
+    Timeline* tl = nullptr;   // optional per-node timeline of the panel recursion
 };
 
 static int lu_apply_swaps(const LuCtx& c, size_t k0, size_t K, double* cols, size_t ncols) {
@@ -37,13 +38,20 @@ static int lu_apply_swaps(const LuCtx& c, size_t k0, size_t K, double* cols, siz
 static int lu_rec(const LuCtx& c, size_t j0, size_t nc) {
     if (nc == 0) return NA_OK;
     double* ajj = c.a + j0 + j0 * c.lda;
-    if (nc <= c.W) return getf2_panel(c.s, ajj, c.lda, c.M - j0, nc, j0, c.ipiv, c.ws_getf2, c.seq_state, c.getf2_limit);
+    if (nc <= c.W) {
+        cudaEvent_t t = c.tl ? c.tl->mark(c.s) : nullptr;
+        NAB_TRY(getf2_panel(c.s, ajj, c.lda, c.M - j0, nc, j0, c.ipiv, c.ws_getf2, c.seq_state, c.getf2_limit));
+        if (c.tl) c.tl->add("getf2", j0, t, c.tl->mark(c.s));
+        return NA_OK;
+    }
     size_t n1 = round_up(nc / 2, c.W);
     if (n1 >= nc) n1 = nc - c.W;
     const size_t n2 = nc - n1;
     NAB_TRY(lu_rec(c, j0, n1));
     double* a12 = ajj + n1 * c.lda;
+    cudaEvent_t tn0 = c.tl ? c.tl->mark(c.s) : nullptr;
     NAB_TRY(lu_apply_swaps(c, j0, n1, a12 - j0, n2));                         // whole rows: columns start at row 0
+    cudaEvent_t tn1 = c.tl ? c.tl->mark(c.s) : nullptr;
     // U12 = L11^-1 * A12 (unit lower): direct substitution kernels for the narrow nodes of the panel recursion
     // (n1 <= 128; 256 = two of them around one GEMM), blocked inverse-based TRSM above that
     if (n1 <= 128) {
@@ -57,12 +65,20 @@ static int lu_rec(const LuCtx& c, size_t j0, size_t nc) {
         NAB_TRY(trsm_left(c.s, true, true, n1, ajj, 1, (ptrdiff_t)c.lda, nullptr, nullptr, a12, 1, (ptrdiff_t)c.lda, n2));
     }
     // A22 -= A21 * U12
+    cudaEvent_t tn2 = c.tl ? c.tl->mark(c.s) : nullptr;
     const size_t m2 = c.M - j0 - n1;
     if (m2 > 0)
         NAB_TRY(dgemm_device(c.s, false, m2, n1, n2, -1.0, ajj + n1, 1, (ptrdiff_t)c.lda, a12, 1, (ptrdiff_t)c.lda, 1.0,
                              a12 + n1, 1, (ptrdiff_t)c.lda));
+    if (c.tl) {
+        cudaEvent_t tn3 = c.tl->mark(c.s);
+        c.tl->add("n.swap", j0 + n1, tn0, tn1); c.tl->add("n.trsm", j0 + n1, tn1, tn2); c.tl->add("n.gemm", j0 + n1, tn2, tn3);
+    }
     NAB_TRY(lu_rec(c, j0 + n1, n2));
-    return lu_apply_swaps(c, j0 + n1, std::min(n2, c.M - j0 - n1), c.a + j0 * c.lda, n1);
+    cudaEvent_t tn4 = c.tl ? c.tl->mark(c.s) : nullptr;
+    NAB_TRY(lu_apply_swaps(c, j0 + n1, std::min(n2, c.M - j0 - n1), c.a + j0 * c.lda, n1));
+    if (c.tl) c.tl->add("n.swapL", j0 + n1, tn4, c.tl->mark(c.s));
+    return NA_OK;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -93,32 +109,6 @@ static bool lu_split() {
     return v;
 }
 
-// NAB_LU_TRACE=1: per-step timeline of the look-ahead schedule (CUDA events on both streams), printed to stderr.
-struct LuTrace {
-    bool on = false;
-    cudaEvent_t t0 = nullptr;
-    struct Rec { const char* what; size_t j; cudaEvent_t a, b; };
-    std::vector<Rec> recs;
-    LuTrace() { const char* e = getenv("NAB_LU_TRACE"); on = e && atoi(e) != 0; }
-    cudaEvent_t mark(cudaStream_t s) {
-        cudaEvent_t e = nullptr;
-        if (on) { cudaEventCreate(&e); cudaEventRecord(e, s); }
-        return e;
-    }
-    void add(const char* what, size_t j, cudaEvent_t a, cudaEvent_t b) { if (on) recs.push_back({what, j, a, b}); }
-    void dump() {
-        if (!on) return;
-        cudaDeviceSynchronize();
-        for (auto& r : recs) {
-            float s0 = 0, d = 0;
-            cudaEventElapsedTime(&s0, t0, r.a); cudaEventElapsedTime(&d, r.a, r.b);
-            fprintf(stderr, "lu_trace j=%6zu %-6s start %9.3f ms  dur %8.3f ms\n", r.j, r.what, s0, d);
-            cudaEventDestroy(r.a); cudaEventDestroy(r.b);
-        }
-        cudaEventDestroy(t0);
-    }
-};
-
 static int lu_lookahead(LuCtx c, size_t N, size_t mn) {
     cudaStream_t sp = c.s, su = nullptr;
     cudaEvent_t ev_p = nullptr, ev_u = nullptr, ev_d = nullptr;
@@ -136,8 +126,9 @@ static int lu_lookahead(LuCtx c, size_t N, size_t mn) {
     const int g_getf2 = (int)ceil_div(c.M, (size_t)384) + 2;          // CTAs the 64-wide GETF2 leaf needs at full height
     bool bulk_pending = false;
     int par = 0;
-    LuTrace tr;
-    tr.t0 = tr.mark(sp);
+    Timeline tr("NAB_LU_TRACE", "lu_trace");
+    tr.start(sp);
+    if (tr.on && getenv("NAB_LU_TRACE_NODES")) c.tl = &tr;
     cudaEvent_t t_first = tr.mark(sp);
     if (st == NA_OK) st = lu_rec(c, 0, std::min(LU_NB, mn));
     tr.add("panel", 0, t_first, tr.mark(sp));

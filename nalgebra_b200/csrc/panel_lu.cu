@@ -468,23 +468,13 @@ int rowperm_apply(cudaStream_t st, double* a, size_t lda, size_t ncols, size_t m
 
 // ------------------------------------------------------------------------------------------------
 // Direct small TRSM for the LU panel recursion: B <- L^-1 B with L the n1 x n1 UNIT lower triangle
-// stored in `l` (n1 <= 128), B n1 x nrhs column-major, in place.  One thread owns one column of B and
-// keeps 64 of its entries in registers; L is read as shared-memory broadcasts.  Replaces the
-// TRTRI + GEMM + copy sequence (3 launches, 75-110 us) on the latency-critical panel chain by one
-// launch of a few microseconds.
+// stored in `l` (n1 <= 128), B n1 x nrhs column-major, in place.  A CTA handles 64 columns of B with the
+// current 64 x 64 block of L in shared memory; every substitution step is spread over all 256 threads
+// (4 row groups x 64 columns), the entries of B stay in registers.  Replaces the TRTRI + GEMM + copy sequence (3 launches, 75-110 us) on the
+// latency-critical panel chain by one launch of a few microseconds.
 // ------------------------------------------------------------------------------------------------
-constexpr int kTrsmCols = 64;      // columns of B (threads) per CTA
-
-// x (64 registers) <- solve with the unit-lower 64 x 64 block in sl (column-major, ld 64; rows/cols >= nv
-// are identity padding).
-__device__ __forceinline__ void trsm64_regs(const double* __restrict__ sl, double (&x)[64]) {
-#pragma unroll
-    for (int k = 0; k < 63; ++k) {
-        const double xk = x[k];
-#pragma unroll
-        for (int i = k + 1; i < 64; ++i) x[i] = fma(-sl[i + k * 64], xk, x[i]);
-    }
-}
+constexpr int kTrsmCols = 64;      // columns of B per CTA
+constexpr int kTrsmLdb = 65;       // row stride of the B tiles in shared memory (odd: conflict-free column access)
 
 __device__ __forceinline__ void load_l_block(double* sl, const double* __restrict__ l, long long ldl, int r0, int c0, int n1,
                                              bool diag_block) {
@@ -497,58 +487,78 @@ __device__ __forceinline__ void load_l_block(double* sl, const double* __restric
         sl[i + k * 64] = v;
     }
 }
+// Forward substitution with the unit-lower 64 x 64 block sl on a 64-column tile of B.  Thread (c = tid % 64,
+// g = tid / 64) keeps rows g, g+4, ..., g+60 of column c in registers x[16]; at step k the owner of row k puts
+// x_k into xs[c] (shared), one barrier, and every thread applies L(i, k) * x_k to its rows below k.  The k loop
+// is fully unrolled so that all register indices are static.
+// (No __restrict__ on the shared-memory pointers: xs is rewritten by other threads between barriers, and with
+// restrict nvcc kept the value of an earlier step in a register across __syncthreads.)
+__device__ __forceinline__ void trsm64_regs(const double* sl, volatile double* xs, double (&x)[16], int c, int g) {
+#pragma unroll
+    for (int k = 0; k < 63; ++k) {
+        if (g == (k & 3)) xs[(k & 1) * 64 + c] = x[k >> 2];
+        __syncthreads();
+        const double xk = xs[(k & 1) * 64 + c];
+#pragma unroll
+        for (int t = 0; t < 16; ++t) {
+            if (4 * t + 3 <= k) continue;                    // rows 4t .. 4t+3 are all <= k: nothing to do (static)
+            const int i = g + 4 * t;
+            if (i > k) x[t] = fma(-sl[i + k * 64], xk, x[t]);
+        }
+    }
+}
 
-__global__ void __launch_bounds__(kTrsmCols) trsm_unit_lower_small_kernel(const double* __restrict__ l, long long ldl, int n1,
-                                                                         double* __restrict__ b, long long ldb, int nrhs) {
-    __shared__ double sl[64 * 64];
-    const int col = blockIdx.x * kTrsmCols + threadIdx.x;
+__global__ void __launch_bounds__(256) trsm_unit_lower_small_kernel(const double* __restrict__ l, long long ldl, int n1,
+                                                                   double* __restrict__ b, long long ldb, int nrhs) {
+    extern __shared__ double tsm[];
+    double* sl = tsm;                               // 64 x 64 block of L
+    double* xs = sl + 64 * 64;                      // x_k of the current step, double-buffered by step parity
+    double* xt = xs + 2 * 64;                       // solved top block (n1 > 64): xt[c * 65 + k]
+    const int c = threadIdx.x & 63, g = threadIdx.x >> 6;
+    const int col = blockIdx.x * kTrsmCols + c;
     const bool active = col < nrhs;
     double* bc = b + (long long)(active ? col : 0) * ldb;
-    double x[64];
-    // ---- top block ----
+    double x[16];
     load_l_block(sl, l, ldl, 0, 0, n1, true);
 #pragma unroll
-    for (int i = 0; i < 64; ++i) x[i] = (active && i < n1) ? bc[i] : 0.0;
+    for (int t = 0; t < 16; ++t) x[t] = (active && g + 4 * t < n1) ? bc[g + 4 * t] : 0.0;
     __syncthreads();
-    trsm64_regs(sl, x);
+    trsm64_regs(sl, xs, x, c, g);
     if (active) {
 #pragma unroll
-        for (int i = 0; i < 64; ++i) if (i < n1) bc[i] = x[i];
+        for (int t = 0; t < 16; ++t) if (g + 4 * t < n1) bc[g + 4 * t] = x[t];
     }
     if (n1 <= 64) return;
-    // ---- bottom rows: b_bot -= L21 * x_top (one entry at a time, x_top stays in registers) ----
+    // bottom rows: B_bot -= L21 * X_top, then the bottom-right triangle
+#pragma unroll
+    for (int t = 0; t < 16; ++t) xt[c * kTrsmLdb + g + 4 * t] = x[t];
     __syncthreads();
     load_l_block(sl, l, ldl, 64, 0, n1, false);
-    __syncthreads();
-    if (active) {
-        for (int i = 0; i < n1 - 64; ++i) {
-            double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
 #pragma unroll
-            for (int k = 0; k < 64; k += 4) {
-                a0 = fma(sl[i + (k + 0) * 64], x[k + 0], a0);
-                a1 = fma(sl[i + (k + 1) * 64], x[k + 1], a1);
-                a2 = fma(sl[i + (k + 2) * 64], x[k + 2], a2);
-                a3 = fma(sl[i + (k + 3) * 64], x[k + 3], a3);
-            }
-            bc[64 + i] -= (a0 + a1) + (a2 + a3);
-        }
+    for (int t = 0; t < 16; ++t) x[t] = (active && 64 + g + 4 * t < n1) ? bc[64 + g + 4 * t] : 0.0;
+    __syncthreads();
+    for (int k = 0; k < 64; ++k) {
+        const double xk = xt[c * kTrsmLdb + k];
+#pragma unroll
+        for (int t = 0; t < 16; ++t) x[t] = fma(-sl[g + 4 * t + k * 64], xk, x[t]);
     }
     __syncthreads();
     load_l_block(sl, l, ldl, 64, 64, n1, true);
-#pragma unroll
-    for (int i = 0; i < 64; ++i) x[i] = (active && 64 + i < n1) ? bc[64 + i] : 0.0;
     __syncthreads();
-    trsm64_regs(sl, x);
+    trsm64_regs(sl, xs, x, c, g);
     if (active) {
 #pragma unroll
-        for (int i = 0; i < 64; ++i) if (64 + i < n1) bc[64 + i] = x[i];
+        for (int t = 0; t < 16; ++t) if (64 + g + 4 * t < n1) bc[64 + g + 4 * t] = x[t];
     }
 }
 
 int trsm_unit_lower_small(cudaStream_t st, size_t n1, const double* l, size_t ldl, double* b, size_t ldb, size_t nrhs) {
     if (n1 == 0 || nrhs == 0) return NA_OK;
     if (n1 > 128) { set_error("trsm_unit_lower_small: n1 > 128"); return NA_EINVAL; }
-    trsm_unit_lower_small_kernel<<<(unsigned)ceil_div(nrhs, (size_t)kTrsmCols), kTrsmCols, 0, st>>>(l, (long long)ldl, (int)n1, b, (long long)ldb, (int)nrhs);
+    const size_t smem = (64 * 64 + 2 * 64 + 64 * kTrsmLdb) * sizeof(double);
+    static std::once_flag once;
+    std::call_once(once, [smem] { cudaFuncSetAttribute(trsm_unit_lower_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); });
+    trsm_unit_lower_small_kernel<<<(unsigned)ceil_div(nrhs, (size_t)kTrsmCols), 256, smem, st>>>(l, (long long)ldl, (int)n1, b, (long long)ldb, (int)nrhs);
     NAB_LAUNCH_CHECK();
     return NA_OK;
 }
@@ -570,4 +580,10 @@ extern "C" __attribute__((visibility("default"))) int na_debug_getf2_prof(long l
     cudaMemcpyFromSymbol(out, nab::g_getf2_prof, sizeof(long long) * 16);
     if (reset) { long long z[16] = {0}; cudaMemcpyToSymbol(nab::g_getf2_prof, z, sizeof(z)); }
     return 0;
+}
+
+// test hook for tools/trsm_small_check.py (not part of include/nalgebra_b200.h)
+extern "C" __attribute__((visibility("default"))) int na_debug_trsm_unit_lower_small(size_t n1, const double* l, size_t ldl, double* b,
+                                                                                   size_t ldb, size_t nrhs, void* stream) {
+    return nab::trsm_unit_lower_small(static_cast<cudaStream_t>(stream), n1, l, ldl, b, ldb, nrhs);
 }

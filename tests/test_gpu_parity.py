@@ -178,6 +178,32 @@ def test_gemm_full_size_linearity_on_device(L):
         del C3
 
 
+def test_lu_panel_trsm_kernel(L):
+    """The direct unit-lower TRSM of the LU panel recursion (trsm_unit_lower_small_kernel) against numpy, through its
+    test hook: block sizes around 64/128, ragged right-hand-side counts, garbage on and above L's diagonal, padding rows
+    untouched.  (Round 1: a __restrict__ shared-memory pointer let nvcc keep a stale value across __syncthreads.)"""
+    import ctypes as C
+    import torch
+    from nalgebra_b200 import _capi
+    f = L.na_debug_trsm_unit_lower_small
+    f.restype = C.c_int
+    f.argtypes = [C.c_size_t, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_size_t, C.c_void_p]
+    s = torch.cuda.current_stream().cuda_stream
+    rng = np.random.default_rng(1)
+    for n1 in (1, 37, 64, 65, 100, 127, 128):
+        for nrhs in (1, 3, 64, 65, 200):
+            ldl, ldb = n1 + 6, n1 + 10
+            lm = np.asfortranarray(np.tril(rng.random((ldl, n1)) - 0.5, -1))
+            lfull = lm.copy(); lfull[:n1][np.triu_indices(n1)] = 7.7
+            b = np.asfortranarray(rng.random((ldb, nrhs)))
+            ref = np.linalg.solve(np.tril(lm[:n1], -1) + np.eye(n1), b[:n1])
+            dl = torch.from_numpy(lfull.T.copy()).cuda(); db = torch.from_numpy(b.T.copy()).cuda()
+            _capi.check(f(n1, dl.data_ptr(), ldl, db.data_ptr(), ldb, nrhs, s)); torch.cuda.synchronize()
+            got = db.cpu().numpy().T
+            assert np.abs(got[:n1] - ref).max() <= 1e-11 * max(1.0, np.abs(ref).max()), (n1, nrhs)
+            assert np.array_equal(got[n1:], b[n1:]), (n1, nrhs)
+
+
 # ---- Cholesky --------------------------------------------------------------------------------------
 def test_cholesky_kats(nab):
     k = K["cholesky_with_substitute"]
