@@ -133,12 +133,30 @@ __global__ void __launch_bounds__(256, 1) geqr2_coop_kernel(const Geqr2Params p)
         const double seq = (double)(p.seq0 + c + 1);
         const int par = c & 1;
         const int np = w - c;                                   // slots c .. w-1
-        for (int idx = tid; idx < G * np; idx += nt) {
-            const int g = idx / np, j = c + (idx - g * np);
-            const double2* src = p.xch + ((size_t)par * G + g) * 32 + j;
-            double x, y;
-            do { ld_pair_raw(src, x, y); } while (y != seq);
-            stage[g * 32 + j] = x;
+        // A thread owns up to G*np/256 slots (12 at G = 98, np = 32).  Their loads are issued in batches of 8 before
+        // any sequence number is checked: polled one after the other, every slot cost a full L2 round trip.
+        const int total = G * np;
+        for (int base = 0; base < total; base += 8 * nt) {
+            double xv[8], yv[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const int idx = base + u * nt + tid;
+                xv[u] = 0.0; yv[u] = seq;
+                if (idx < total) {
+                    const int g = idx / np, j = c + (idx - g * np);
+                    ld_pair_raw(p.xch + ((size_t)par * G + g) * 32 + j, xv[u], yv[u]);
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const int idx = base + u * nt + tid;
+                if (idx < total) {
+                    const int g = idx / np, j = c + (idx - g * np);
+                    const double2* src = p.xch + ((size_t)par * G + g) * 32 + j;
+                    while (yv[u] != seq) ld_pair_raw(src, xv[u], yv[u]);
+                    stage[g * 32 + j] = xv[u];
+                }
+            }
         }
         if (tid < np) {
             double x, y;
