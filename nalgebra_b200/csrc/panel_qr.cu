@@ -64,6 +64,13 @@ __device__ __forceinline__ double warp_reduce_scatter32(double (&vals)[32], int 
     return vals[0];
 }
 
+__device__ long long g_geqr2_prof[16];
+#ifdef NAB_GEQR2_PROF   // per-phase cycle counters of CTA 0 / thread 0 (tools/qr_timing.py), off in the product build
+#define QPROF(i) do { if (threadIdx.x == 0 && blockIdx.x == 0) { const long long t_ = clock64(); g_geqr2_prof[i] += t_ - qt_prev; qt_prev = t_; } } while (0)
+#else
+#define QPROF(i) do { (void)qt_prev; } while (0)
+#endif
+
 __global__ void __launch_bounds__(256, 1) geqr2_coop_kernel(const Geqr2Params p) {
     extern __shared__ double sm[];
     const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, warp = tid >> 5;
@@ -82,6 +89,7 @@ __global__ void __launch_bounds__(256, 1) geqr2_coop_kernel(const Geqr2Params p)
         for (int r = tid; r < nrows; r += nt) s[r + c * rp] = p.a[(long long)(r_begin + r) + (long long)c * p.lda];
     __syncthreads();
     const int ncol = min(w, p.m);
+    long long qt_prev = clock64();
 
     // One pass over the local rows: applies reflector `c` (c < 0: nothing to apply) and accumulates, for
     // the next column cn = c + 1, vals[j] = sum_{r > cn} x[r] * a[r, j] (j >= cn) with x = updated column cn.
@@ -91,6 +99,12 @@ __global__ void __launch_bounds__(256, 1) geqr2_coop_kernel(const Geqr2Params p)
         double vals[32];
 #pragma unroll
         for (int j = 0; j < 32; ++j) vals[j] = 0.0;
+        // (measured: this loop was 8500 of 16500 cycles per column at m = 65536 whatever the width -- every thread
+        // issued all 32 predicated column bodies and re-read dots[j] per row; now tau*v^T a_j sits in registers and
+        // finished 8-column groups are skipped by a uniform branch)
+        double dj[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) dj[j] = (c >= 0 && j >= cn && j < w) ? dots[j] : 0.0;
         for (int r = tid; r < nrows; r += nt) {
             const int gr = r_begin + r;
             if (gr < cn && !(gr == c)) continue;            // finished rows (R part) above the pivot row
@@ -101,17 +115,39 @@ __global__ void __launch_bounds__(256, 1) geqr2_coop_kernel(const Geqr2Params p)
             }
             double x = 0.0;
 #pragma unroll
-            for (int j = 0; j < 32; ++j) {
-                if (j < cn || j >= w) continue;              // columns right of c only
-                double aj = s[r + j * rp];
-                if (c >= 0) { aj -= dots[j] * v; s[r + j * rp] = aj; }
-                if (j == cn) x = (gr > cn) ? aj : 0.0;       // rows below the next pivot row feed the sums
-                vals[j] += x * aj;
+            for (int b = 0; b < 4; ++b) {
+                if (8 * b + 7 < cn || 8 * b >= w) continue;  // whole group finished / beyond the panel (uniform)
+                // the 8 loads of a group are issued before any store of the group: interleaved, every load waited
+                // for the previous store (possible aliasing) and the loop ran at shared-memory latency
+                double aj[8];
+#pragma unroll
+                for (int jj = 0; jj < 8; ++jj) {
+                    const int j = 8 * b + jj;
+                    aj[jj] = (j >= cn && j < w) ? s[r + j * rp] : 0.0;
+                }
+#pragma unroll
+                for (int jj = 0; jj < 8; ++jj) {
+                    const int j = 8 * b + jj;
+                    if (j < cn || j >= w) continue;          // columns right of c only
+                    if (c >= 0) aj[jj] -= dj[j] * v;
+                    if (j == cn) x = (gr > cn) ? aj[jj] : 0.0;   // rows below the next pivot row feed the sums
+                    vals[j] += x * aj[jj];
+                }
+                if (c >= 0) {
+#pragma unroll
+                    for (int jj = 0; jj < 8; ++jj) {
+                        const int j = 8 * b + jj;
+                        if (j >= cn && j < w) s[r + j * rp] = aj[jj];
+                    }
+                }
             }
         }
+        QPROF(4);
         const double mine = warp_reduce_scatter32(vals, lane);
         wred[warp * 32 + lane] = mine;
+        QPROF(5);
         __syncthreads();
+        QPROF(6);
         // cross-warp sum and publish: slot j = column j (slot cn = sigma), plus row cn from its owner
         if (cn < ncol) {
             const double seq = (double)(p.seq0 + cn + 1);
@@ -175,7 +211,9 @@ __global__ void __launch_bounds__(256, 1) geqr2_coop_kernel(const Geqr2Params p)
 
     pass(-1, 0.0, 0.0);                                          // partial sums of column 0
     for (int c = 0; c < ncol; ++c) {
+        QPROF(0);
         receive(c);
+        QPROF(1);
         const double alpha = rowv[c], sigma = tot[c];
         const double nrm = sqrt(alpha * alpha + sigma);
         double beta = 0.0, tau = 0.0, scale = 0.0;
@@ -189,8 +227,11 @@ __global__ void __launch_bounds__(256, 1) geqr2_coop_kernel(const Geqr2Params p)
         if (tid < w && tid > c) dots[tid] = tau * (rowv[tid] + scale * tot[tid]);   // tau * v^T a_j
         if (tid == 0 && c >= r_begin && c < r_begin + nrows) s[(c - r_begin) + c * rp] = beta;
         __syncthreads();
+        QPROF(2);
         if (c + 1 < w || true) pass(c, scale, tau);
+        QPROF(7);
         __syncthreads();
+        QPROF(3);
     }
     for (int c = 0; c < w; ++c)
         for (int r = tid; r < nrows; r += nt) p.a[(long long)(r_begin + r) + (long long)c * p.lda] = s[r + c * rp];
@@ -454,3 +495,9 @@ int scale_signs(cudaStream_t st, double* b, size_t ldb, size_t rows, size_t cols
 }
 
 }  // namespace nab
+
+extern "C" __attribute__((visibility("default"))) int na_debug_geqr2_prof(long long* out, int reset) {
+    cudaMemcpyFromSymbol(out, nab::g_geqr2_prof, sizeof(long long) * 16);
+    if (reset) { long long z[16] = {0}; cudaMemcpyToSymbol(nab::g_geqr2_prof, z, sizeof(z)); }
+    return 0;
+}
