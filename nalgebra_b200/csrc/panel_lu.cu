@@ -66,6 +66,23 @@ __device__ __forceinline__ double pivot_key(double x, bool first) {
     return (v != v) ? (first ? __longlong_as_double(0x7ff0000000000000LL) : -1.0) : v;
 }
 
+// Warp-wide winner of (v, r) under cand_better -- larger key, lowest row on ties -- with redux.sync on the
+// key's bit pattern instead of five rounds of three shuffles (keys are |x| >= 0, +inf, or the markers -1 / -2,
+// so `bits + 2` / 1 / 0 is monotone).  Every lane returns the winner; `tag` follows it (e.g. the CTA index).
+__device__ __forceinline__ void warp_best(double& v, int& r, int& tag) {
+    const unsigned FULL = 0xffffffffu;
+    const unsigned long long kb = v >= 0.0 ? (unsigned long long)__double_as_longlong(v) + 2ull : (v == -1.0 ? 1ull : 0ull);
+    const unsigned hi = (unsigned)(kb >> 32), lo = (unsigned)kb;
+    const unsigned mhi = __reduce_max_sync(FULL, hi);
+    const unsigned mlo = __reduce_max_sync(FULL, hi == mhi ? lo : 0u);
+    const bool is_max = hi == mhi && lo == mlo;
+    const int mr = __reduce_min_sync(FULL, is_max ? r : 0x7fffffff);
+    tag = __reduce_min_sync(FULL, (is_max && r == mr) ? tag : 0x7fffffff);
+    const unsigned long long mk = ((unsigned long long)mhi << 32) | mlo;
+    v = mk >= 2ull ? __longlong_as_double((long long)(mk - 2ull)) : (mk == 1ull ? -1.0 : -2.0);
+    r = mr;
+}
+
 __device__ long long g_getf2_prof[16];
 #ifdef NAB_GETF2_PROF   // per-phase cycle counters of CTA 0 / thread 0 (tools/lu_timing.py), off in the product build
 #define PROF(i) do { if (tid == 0 && cta == 0) { const long long t_ = clock64(); g_getf2_prof[i] += t_ - t_prev; t_prev = t_; } } while (0)
@@ -104,22 +121,13 @@ __global__ void __launch_bounds__(256, 1) getf2_coop_kernel(const Getf2Params p)
 
     // Local winner of (bv, br) over the CTA -> s_lrow; publishes the header of column `col`.
     auto reduce_and_publish_header = [&](double bv, int br, int col) {
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-            const double ov = __shfl_xor_sync(0xffffffffu, bv, o);
-            const int orow = __shfl_xor_sync(0xffffffffu, br, o);
-            if (cand_better(ov, orow, bv, br)) { bv = ov; br = orow; }
-        }
+        int tag0 = 0;
+        warp_best(bv, br, tag0);
         if (lane == 0) { red_v[warp] = bv; red_r[warp] = br; }
         __syncthreads();
         if (warp == 0) {
             double v = lane < 8 ? red_v[lane] : -2.0; int r = lane < 8 ? red_r[lane] : 0x7fffffff;
-#pragma unroll
-            for (int o = 4; o > 0; o >>= 1) {
-                const double ov = __shfl_xor_sync(0xffffffffu, v, o);
-                const int orow = __shfl_xor_sync(0xffffffffu, r, o);
-                if (cand_better(ov, orow, v, r)) { v = ov; r = orow; }
-            }
+            warp_best(v, r, tag0);
             if (lane == 0) {
                 if (G > 1) lu_st_pair(p.xch + ((size_t)(col & 1) * G + cta) * SL, v, pack_seq_row(p.seq0 + col + 1, r));
                 s_lrow = r;
@@ -172,13 +180,7 @@ __global__ void __launch_bounds__(256, 1) getf2_coop_kernel(const Getf2Params p)
             PROF(1);
             const int nw_used = min(8, (G + 31) / 32);
             if (warp < nw_used) {
-#pragma unroll
-                for (int o = 16; o > 0; o >>= 1) {
-                    const double ov = __shfl_xor_sync(0xffffffffu, gv, o);
-                    const int orow = __shfl_xor_sync(0xffffffffu, grow, o);
-                    const int ow = __shfl_xor_sync(0xffffffffu, gcta, o);
-                    if (cand_better(ov, orow, gv, grow)) { gv = ov; grow = orow; gcta = ow; }
-                }
+                warp_best(gv, grow, gcta);
                 if (lane == 0) { red_v[warp] = gv; red_r[warp] = grow; red_w[warp] = gcta; }
             }
             __syncthreads();
