@@ -38,6 +38,7 @@ struct Geqr2Params {
     double* tau;               // [w] out
     double2* xch;              // [2][G][32]  (partial sum, seq) pairs, slot j = column j (slot c = sigma)
     double2* rowc;             // [2][32]     (a[c, j], seq) pairs published by the owner of row c
+    double2* totx;             // [2][32]     (T_j, seq) totals published by the reducer CTA of slot j (two-stage exchange)
     int seq0;                  // sequence numbers already consumed in this workspace
 };
 
@@ -169,6 +170,45 @@ __global__ void __launch_bounds__(256, 1) geqr2_coop_kernel(const Geqr2Params p)
         const double seq = (double)(p.seq0 + c + 1);
         const int par = c & 1;
         const int np = w - c;                                   // slots c .. w-1
+        if (G >= 56) {    // below that the one-stage all-to-all is faster (measured: G = 25: 2600 vs 4500 cycles; G = 98: 5900 vs 3600)
+            // Two-stage exchange (reduce-scatter + all-gather through L2): slot j = c + q is summed by ONE reducer CTA
+            // (the q-th from the end, away from CTA 0 which owns the pivot rows) in a fixed order and published as a
+            // total; every CTA then reads np totals instead of G * np partials (98 x 32 pairs = 50 KB per CTA and
+            // column at m = 65536: measured 5900 of 16500 cycles per column).
+            for (int q = G - 1 - cta; q < np; q += G) {
+                const int j = c + q;
+                double v = 0.0;
+                if (tid < G) {
+                    const double2* src = p.xch + ((size_t)par * G + tid) * 32 + j;
+                    double y;
+                    do { ld_pair_raw(src, v, y); } while (y != seq);
+                }
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+                if (lane == 0) wred[warp] = v;
+                __syncthreads();
+                if (tid == 0) {
+                    double t = 0.0;
+                    const int nwu = (G + 31) / 32;
+                    for (int i = 0; i < nwu; ++i) t += wred[i];
+                    st_pair(p.totx + par * 32 + j, t, seq);
+                }
+                __syncthreads();
+            }
+            if (tid < np) {
+                double x, y;
+                const double2* src = p.totx + par * 32 + c + tid;
+                do { ld_pair_raw(src, x, y); } while (y != seq);
+                tot[c + tid] = x;
+            } else if (tid >= 32 && tid < 32 + np) {
+                double x, y;
+                const double2* src = p.rowc + par * 32 + c + (tid - 32);
+                do { ld_pair_raw(src, x, y); } while (y != seq);
+                rowv[c + (tid - 32)] = x;
+            }
+            __syncthreads();
+            return;
+        }
         // A thread owns up to G*np/256 slots (12 at G = 98, np = 32).  Their loads are issued in batches of 8 before
         // any sequence number is checked: polled one after the other, every slot cost a full L2 round trip.
         const int total = G * np;
@@ -210,6 +250,7 @@ __global__ void __launch_bounds__(256, 1) geqr2_coop_kernel(const Geqr2Params p)
     };
 
     pass(-1, 0.0, 0.0);                                          // partial sums of column 0
+    __syncthreads();                                             // wred is reused by the reducers in receive()
     for (int c = 0; c < ncol; ++c) {
         QPROF(0);
         receive(c);
@@ -238,7 +279,7 @@ __global__ void __launch_bounds__(256, 1) geqr2_coop_kernel(const Geqr2Params p)
 }
 
 constexpr size_t kGeqr2MaxCtas = 160;
-size_t geqr2_workspace_bytes() { return (2 * kGeqr2MaxCtas * 32 + 2 * 32) * sizeof(double2); }
+size_t geqr2_workspace_bytes() { return (2 * kGeqr2MaxCtas * 32 + 2 * 32 + 2 * 32) * sizeof(double2); }
 
 // *seq_state (host) carries the sequence numbers consumed so far in this (zero-initialised) workspace.
 int geqr2_panel(cudaStream_t st, double* a_panel, size_t lda, size_t m, size_t w, double* tau, void* ws, int* seq_state) {
@@ -261,6 +302,7 @@ int geqr2_panel(cudaStream_t st, double* a_panel, size_t lda, size_t m, size_t w
     p.a = a_panel; p.lda = (long long)lda; p.m = (int)m; p.w = (int)w; p.rp = (int)rp; p.tau = tau;
     p.xch = static_cast<double2*>(ws);
     p.rowc = p.xch + 2 * kGeqr2MaxCtas * 32;
+    p.totx = p.rowc + 2 * 32;
     p.seq0 = *seq_state;
     *seq_state += (int)w + 2 + ((w & 1) ? 1 : 0);
     void* args[] = {(void*)&p};
