@@ -7,6 +7,8 @@
 // reflectors I - V T V^T with three GEMMs; applying T (or T^T) is a triangular solve with
 // S = T^-1 = triu(V^T V, 1) + diag(1/tau), so no LARFT recurrence is needed.
 #include <algorithm>
+#include <cstdio>
+#include <cstdlib>
 
 #include "common.cuh"
 #include "kernels.cuh"
@@ -54,6 +56,128 @@ struct QrWork {
     }
 };
 
+// One outer panel: leaves of kQrLeaf columns (cooperative GEQR2), each applied to the rest of the panel as a
+// 32-wide block reflector.  vleaf / sleaf / wkleaf: leaf-level workspaces.
+static int qr_panel(cudaStream_t s, QrWork& w, size_t m, double* a, size_t lda, double* tau, size_t j, size_t jb,
+                    double* vleaf, double* sleaf, double* wkleaf) {
+    const size_t W = kQrLeaf;
+    for (size_t l = 0; l < jb; l += W) {
+        const size_t lw = std::min(W, jb - l), jl = j + l, ml = m - jl;
+        double* apanel = a + jl + jl * lda;
+        NAB_TRY(geqr2_panel(s, apanel, lda, ml, lw, tau + jl, w.ws_geqr2.p, &w.seq_state));
+        const size_t nc = (j + jb) - (jl + lw);          // rest of the outer panel
+        if (nc > 0) {
+            NAB_TRY(extract_v_gram(s, vleaf, w.ldv, apanel, lda, ml, lw, tau + jl, sleaf, w.lds, w.ws_gram.p));
+            NAB_TRY(apply_block_reflector(s, ml, lw, vleaf, w.ldv, sleaf, w.lds, true, apanel + lw * lda, lda, nc, wkleaf, w.ldw));
+        }
+    }
+    return NA_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Tall matrices with many panels: right-looking outer blocks with one-step look-ahead on two streams, like
+// the LU driver.  la(j) applies block reflector j to the next panel's columns (whole GPU, critical chain);
+// bulk(j) applies it to the columns right of that: part A beside panel(j + nb) on the SMs the cooperative
+// GEQR2 grid leaves free, part B on the whole GPU once the panel is done.  The outer V / S are double-buffered
+// (bulk B(j) may still read them while panel(j + nb) builds its own leaves' V / S in separate buffers).
+// ------------------------------------------------------------------------------------------------
+static bool qr_lookahead_enabled() {
+    static bool v = [] { const char* e = getenv("NAB_QR_LOOKAHEAD"); return e ? atoi(e) != 0 : true; }();
+    return v;
+}
+
+static int qr_lookahead(cudaStream_t sp, QrWork& w, size_t m, size_t n, double* a, size_t lda, double* tau, size_t k) {
+    cudaStream_t su = nullptr;
+    cudaEvent_t ev_p = nullptr, ev_u = nullptr, ev_d = nullptr;
+    NAB_CUDA(cudaStreamCreateWithFlags(&su, cudaStreamNonBlocking));
+    NAB_CUDA(cudaEventCreateWithFlags(&ev_p, cudaEventDisableTiming));
+    NAB_CUDA(cudaEventCreateWithFlags(&ev_u, cudaEventDisableTiming));
+    NAB_CUDA(cudaEventCreateWithFlags(&ev_d, cudaEventDisableTiming));
+    Scratch vwo[2], smo[2], wkla, wkbulk;
+    int st = NA_OK;
+    for (int i = 0; i < 2 && st == NA_OK; ++i) {
+        st = vwo[i].alloc(w.ldv * QR_NB * sizeof(double), sp);
+        if (st == NA_OK) st = smo[i].alloc(w.lds * QR_NB * sizeof(double), sp);
+    }
+    if (st == NA_OK) st = wkla.alloc(w.ldw * QR_NB * sizeof(double), sp);
+    if (st == NA_OK) st = wkbulk.alloc(w.ldw * std::max<size_t>(n, 1) * sizeof(double), sp);
+    const int sms = ctx().sm_count;
+    Timeline tr("NAB_QR_TRACE", "qr_trace");
+    tr.start(sp);
+    auto outer = [&](cudaStream_t s, size_t j, size_t jb, int par, size_t c0, size_t nc, double* wk) {
+        // columns [c0, c0 + nc) <- (I - V T^T V^T) columns, V = outer panel j (rows j..)
+        return apply_block_reflector(s, m - j, jb, vwo[par].as<double>(), w.ldv, smo[par].as<double>(), w.lds, true,
+                                     a + j + c0 * lda, lda, nc, wk, w.ldw);
+    };
+    auto prep = [&](size_t j, size_t jb, int par) {
+        NAB_TRY(extract_v(sp, vwo[par].as<double>(), w.ldv, a + j + j * lda, lda, m - j, jb, tau + j, 0));
+        return build_s_from_v(sp, m - j, jb, vwo[par].as<double>(), w.ldv, tau + j, smo[par].as<double>(), w.lds);
+    };
+    bool bulk_pending = false;
+    int par = 0;
+    cudaEvent_t t0 = tr.mark(sp);
+    if (st == NA_OK) st = qr_panel(sp, w, m, a, lda, tau, 0, std::min(QR_NB, k), w.vw.as<double>(), w.smat.as<double>(), w.wk.as<double>());
+    tr.add("panel", 0, t0, tr.mark(sp));
+    for (size_t j = 0; st == NA_OK; j += QR_NB) {
+        const size_t jb = std::min(QR_NB, k - j), jn = j + jb;
+        const size_t jbn = jn < k ? std::min(QR_NB, k - jn) : 0;
+        if (jn >= n) break;                                   // nothing right of this panel
+        st = prep(j, jb, par);
+        if (st != NA_OK) break;
+        if (bulk_pending) cudaStreamWaitEvent(sp, ev_u, 0);
+        // la(j): the next panel's columns (or, after the last panel, nothing)
+        cudaEvent_t t_la = tr.mark(sp);
+        if (jbn) st = outer(sp, j, jb, par, jn, jbn, wkla.as<double>());
+        if (st != NA_OK) break;
+        tr.add("la", j, t_la, tr.mark(sp));
+        cudaEventRecord(ev_p, sp);
+        const size_t x0 = jn + jbn, nx = n - x0, mj = m - j;
+        // SMs of the panel chain = the cooperative GEQR2 grid of the next panel's first (tallest) leaf
+        const int rp = jbn ? std::min(sms - 16, geqr2_grid(m - jn, std::min<size_t>(kQrLeaf, jbn)) + 2) : 0;
+        size_t wa = nx;
+        if (jbn && nx) {
+            const double t_panel = (double)jbn / 32.0 * 0.44e-3;              // measured: ~3.5 ms per 256 columns
+            const double target = t_panel * (sms - rp) * 0.18e12;
+            wa = round_up((size_t)(target / (4.0 * (double)mj * (double)jb)) + 1, 128);
+            if (wa + 256 >= nx) wa = nx;
+        }
+        if (nx) {
+            cudaStreamWaitEvent(su, ev_p, 0);
+            cudaEvent_t t_a = tr.mark(su);
+            set_gemm_sm_limit(jbn ? sms - rp : 0);
+            st = outer(su, j, jb, par, x0, wa, wkbulk.as<double>());
+            set_gemm_sm_limit(0);
+            if (st != NA_OK) break;
+            tr.add("bulkA", j, t_a, tr.mark(su));
+        }
+        if (jbn == 0) { if (nx) { cudaEventRecord(ev_u, su); bulk_pending = true; } break; }
+        cudaEvent_t t_p = tr.mark(sp);
+        set_gemm_sm_limit(rp);
+        st = qr_panel(sp, w, m, a, lda, tau, jn, jbn, w.vw.as<double>(), w.smat.as<double>(), w.wk.as<double>());
+        set_gemm_sm_limit(0);
+        if (st != NA_OK) break;
+        tr.add("panel", jn, t_p, tr.mark(sp));
+        if (nx) {
+            if (wa < nx) {
+                cudaEventRecord(ev_d, sp);
+                cudaStreamWaitEvent(su, ev_d, 0);
+                cudaEvent_t t_b = tr.mark(su);
+                st = outer(su, j, jb, par, x0 + wa, nx - wa, wkbulk.as<double>() + wa * w.ldw);
+                if (st != NA_OK) break;
+                tr.add("bulkB", j, t_b, tr.mark(su));
+            }
+            cudaEventRecord(ev_u, su);
+            bulk_pending = true;
+        }
+        par ^= 1;
+    }
+    if (bulk_pending) cudaStreamWaitEvent(sp, ev_u, 0);
+    cudaStreamSynchronize(su);
+    tr.dump();
+    cudaEventDestroy(ev_p); cudaEventDestroy(ev_u); cudaEventDestroy(ev_d); cudaStreamDestroy(su);
+    return st;
+}
+
 // diag: DEVICE pointer, min(m,n) entries.
 int qr_device(cudaStream_t s, size_t m, size_t n, double* a, size_t lda, double* diag) {
     const size_t k = std::min(m, n);
@@ -64,20 +188,13 @@ int qr_device(cudaStream_t s, size_t m, size_t n, double* a, size_t lda, double*
     NAB_TRY(w.init(s, m, n, k));
     double* tau = w.tau.as<double>();
     double* vw = w.vw.as<double>();
-    const size_t W = kQrLeaf;
+    if (qr_lookahead_enabled() && k >= 4 * QR_NB && m >= 8192 && n <= m) {
+        NAB_TRY(qr_lookahead(s, w, m, n, a, lda, tau, k));
+        return qr_convert_to_nalgebra(s, a, lda, m, n, tau, w.csign.as<double>(), diag);
+    }
     for (size_t j = 0; j < k; j += QR_NB) {
         const size_t jb = std::min(QR_NB, k - j), mj = m - j;
-        for (size_t l = 0; l < jb; l += W) {
-            const size_t lw = std::min(W, jb - l), jl = j + l, ml = m - jl;
-            double* apanel = a + jl + jl * lda;
-            NAB_TRY(geqr2_panel(s, apanel, lda, ml, lw, tau + jl, w.ws_geqr2.p, &w.seq_state));
-            const size_t nc = (j + jb) - (jl + lw);          // rest of the outer panel
-            if (nc > 0) {
-                NAB_TRY(extract_v_gram(s, vw, w.ldv, apanel, lda, ml, lw, tau + jl, w.smat.as<double>(), w.lds, w.ws_gram.p));
-                NAB_TRY(apply_block_reflector(s, ml, lw, vw, w.ldv, w.smat.as<double>(), w.lds, true,
-                                              apanel + lw * lda, lda, nc, w.wk.as<double>(), w.ldw));
-            }
-        }
+        NAB_TRY(qr_panel(s, w, m, a, lda, tau, j, jb, vw, w.smat.as<double>(), w.wk.as<double>()));
         const size_t nt = n - (j + jb);                       // trailing columns
         if (nt > 0) {
             double* apanel = a + j + j * lda;

@@ -49,6 +49,7 @@ int trsm_unit_lower_small(cudaStream_t st, size_t n1, const double* l, size_t ld
 // ---- panel_qr.cu ---------------------------------------------------------------------------------
 constexpr int kQrLeaf = 32;        // GEQR2 leaf panel width
 size_t geqr2_workspace_bytes();
+int geqr2_grid(size_t m, size_t w);       // CTAs (= SMs) the cooperative GEQR2 launch of an m x w panel occupies
 int geqr2_panel(cudaStream_t st, double* a_panel, size_t lda, size_t m, size_t w, double* tau, void* ws, int* seq_state);
 int extract_v(cudaStream_t st, double* vw, size_t ldv, const double* a, size_t lda, size_t m, size_t w, const double* tau, int mode);
 int build_s(cudaStream_t st, double* g, size_t ldg, size_t w, const double* tau);

@@ -281,20 +281,29 @@ __global__ void __launch_bounds__(256, 1) geqr2_coop_kernel(const Geqr2Params p)
 constexpr size_t kGeqr2MaxCtas = 160;
 size_t geqr2_workspace_bytes() { return (2 * kGeqr2MaxCtas * 32 + 2 * 32 + 2 * 32) * sizeof(double2); }
 
-// *seq_state (host) carries the sequence numbers consumed so far in this (zero-initialised) workspace.
-int geqr2_panel(cudaStream_t st, double* a_panel, size_t lda, size_t m, size_t w, double* tau, void* ws, int* seq_state) {
-    if (m == 0 || w == 0) return NA_OK;
-    if (w > (size_t)kQrLeaf) { set_error("geqr2: panel too wide"); return NA_EINVAL; }
+// CTAs (and rows per CTA) the cooperative GEQR2 launch uses for an m x w panel; 0 if it does not fit.
+static size_t geqr2_grid_rows(size_t m, size_t w, size_t& rp_out) {
     const int sms = ctx().sm_count;
-    // smem: w*rp + 8*32 + 3*32 + G*32 doubles
     size_t G = 1, rp = 0;
     for (;; ++G) {
-        if (G > (size_t)std::min<int>(sms, (int)kGeqr2MaxCtas)) { set_error("geqr2: %zu x %zu panel does not fit in shared memory", m, w); return NA_EINVAL; }
+        if (G > (size_t)std::min<int>(sms, (int)kGeqr2MaxCtas)) return 0;
         rp = round_up(ceil_div(m, G), 32);
         const size_t bytes = (w * rp + 352 + G * 32) * sizeof(double);
         if (bytes <= 200 * 1024 && (rp <= 768 || G * 2 > (size_t)sms)) break;   // prefer <= 768 rows per CTA when SMs allow
     }
-    G = ceil_div(m, rp);
+    rp_out = rp;
+    return ceil_div(m, rp);
+}
+int geqr2_grid(size_t m, size_t w) { size_t rp; return (int)geqr2_grid_rows(m, w, rp); }
+
+// *seq_state (host) carries the sequence numbers consumed so far in this (zero-initialised) workspace.
+int geqr2_panel(cudaStream_t st, double* a_panel, size_t lda, size_t m, size_t w, double* tau, void* ws, int* seq_state) {
+    if (m == 0 || w == 0) return NA_OK;
+    if (w > (size_t)kQrLeaf) { set_error("geqr2: panel too wide"); return NA_EINVAL; }
+    // smem: w*rp + 8*32 + 3*32 + G*32 doubles
+    size_t rp = 0;
+    const size_t G = geqr2_grid_rows(m, w, rp);
+    if (G == 0) { set_error("geqr2: %zu x %zu panel does not fit in shared memory", m, w); return NA_EINVAL; }
     const size_t smem = (w * rp + 352 + G * 32) * sizeof(double);
     static std::once_flag once;
     std::call_once(once, [] { cudaFuncSetAttribute(geqr2_coop_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024); });
