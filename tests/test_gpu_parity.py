@@ -424,3 +424,59 @@ def test_qr_65536x4096_residual_and_orthogonality(L):
     assert torch.linalg.norm(Qm.t() @ Qm - torch.eye(n, device=dev, dtype=torch.float64)).item() <= 10 * m * EPS
     axes = torch.tril(A.view(n, m).t())
     assert (torch.linalg.norm(axes, dim=0) - 1.0).abs().max().item() <= 1e-12   # unit Householder axes
+
+
+def test_qr_lookahead_path_vs_oracle(nab, oracle):
+    """The two-stream look-ahead QR driver (m >= 8192, >= 4 outer panels) against the oracle's nalgebra restatement."""
+    m, n = 8200, 1030
+    a = oracle.uniform(m, n, 8) - 0.4
+    qr = nab.QR.new(a)
+    qr_ref, diag_ref = oracle.qr(a)
+    assert np.abs(qr.qr_internal() - qr_ref).max() < 1e-10
+    assert np.abs(qr.diag_internal() - diag_ref).max() < 1e-10
+    q, r = qr.q(), qr.r()
+    assert np.linalg.norm(q @ r - a) / np.linalg.norm(a) <= 10 * m * EPS
+    assert np.abs(q.T @ q - np.eye(n)).max() <= 10 * m * EPS
+
+
+def test_concurrent_calls_from_two_host_threads(L):
+    """The C ABI is called concurrently from two host threads on their own streams (nalgebra's types are Send + Sync,
+    SURVEY 8b 'Threading'): per-call workspaces, thread-local SM limits.  Results must equal the serial ones bit for bit."""
+    import ctypes as C
+    import threading
+    import torch
+    from nalgebra_b200 import _capi
+    n = 2560
+    dev = torch.device("cuda:0")
+    s0 = torch.cuda.current_stream().cuda_stream
+    base_lu = torch.empty(n * n, dtype=torch.float64, device=dev); base_ch = torch.empty_like(base_lu)
+    _capi.check(L.na_fill_uniform_dev(base_lu.data_ptr(), n, n, n, 6, s0))
+    _capi.check(L.na_fill_spd_block_dev(base_ch.data_ptr(), n, n, n, 5, 0, 0, n, s0))
+    torch.cuda.synchronize()
+
+    def run_lu(stream, out):
+        a = base_lu.clone(); torch.cuda.synchronize()
+        swaps = (C.c_size_t * (2 * n))(); ns = C.c_size_t(0)
+        _capi.check(L.na_lu_f64_dev(n, n, a.data_ptr(), n, swaps, C.addressof(ns), stream))
+        torch.cuda.synchronize()
+        out["lu"] = (a.cpu(), list(swaps[: 2 * ns.value]))
+
+    def run_chol(stream, out):
+        a = base_ch.clone(); torch.cuda.synchronize()
+        fail = C.c_size_t(0)
+        _capi.check(L.na_cholesky_f64_dev(n, a.data_ptr(), n, 0, 0.0, C.addressof(fail), stream))
+        torch.cuda.synchronize()
+        out["chol"] = a.cpu()
+
+    serial = {}
+    run_lu(s0, serial); run_chol(s0, serial)
+    for _ in range(3):
+        st1, st2 = torch.cuda.Stream(), torch.cuda.Stream()
+        conc = {}
+        t1 = threading.Thread(target=run_lu, args=(st1.cuda_stream, conc))
+        t2 = threading.Thread(target=run_chol, args=(st2.cuda_stream, conc))
+        t1.start(); t2.start(); t1.join(); t2.join()
+        assert conc["lu"][1] == serial["lu"][1]
+        assert torch.equal(conc["lu"][0], serial["lu"][0])
+        assert torch.equal(conc["chol"], serial["chol"])
+
