@@ -128,6 +128,10 @@ static bool chol_split() {
     static bool v = [] { const char* e = getenv("NAB_CHOL_SPLIT"); return e ? atoi(e) != 0 : false; }();
     return v;
 }
+static int chol_rp_min() {
+    static int v = [] { const char* e = getenv("NAB_CHOL_RP_MIN"); return e ? std::max(4, atoi(e)) : 12; }();     // measured at 16384: 16 -> 54.7 ms, 12 -> 54.05, 8 -> 54.2
+    return v;
+}
 #define CHOL_NB (chol_nb())
 
 static int chol_panel(const CholCtx& c, cudaStream_t sp, size_t n, size_t j, size_t jb, int sm_limit, double* tmp, size_t ldt) {
@@ -140,9 +144,11 @@ static int chol_panel(const CholCtx& c, cudaStream_t sp, size_t n, size_t j, siz
         if (r == 0) continue;
         double* a21 = acc + w;
         set_gemm_sm_limit(sm_limit);
-        // A21 <- A21 * inv(L)^T  (out of place, then copied back)
-        int st = dgemm_device(sp, false, r, w, w, 1.0, a21, 1, (ptrdiff_t)c.lda, inv, (ptrdiff_t)IBs, 1, 0.0, tmp, 1, (ptrdiff_t)ldt);
-        if (st == NA_OK) st = copy_strided(sp, a21, 1, (ptrdiff_t)c.lda, tmp, 1, (ptrdiff_t)ldt, r, w);
+        // A21 <- A21 * inv(L)^T, in place: the result is one tile column wide (w <= 128 = BN), so the output tile of a
+        // CTA is exactly the A operand rows it has finished reading (all its k-blocks have landed in shared memory
+        // before the epilogue stores), and no other CTA touches those rows.
+        (void)tmp; (void)ldt;
+        int st = dgemm_device(sp, false, r, w, w, 1.0, a21, 1, (ptrdiff_t)c.lda, inv, (ptrdiff_t)IBs, 1, 0.0, a21, 1, (ptrdiff_t)c.lda);
         const size_t pw = j + jb - cc - w;               // remaining columns of this panel
         if (st == NA_OK && pw > 0)
             st = dgemm_device(sp, true, r, w, pw, -1.0, a21, 1, (ptrdiff_t)c.lda, a21, (ptrdiff_t)c.lda, 1, 1.0,
@@ -197,7 +203,7 @@ static int chol_lookahead(const CholCtx& c, size_t n) {
                 const double bulk_flops = (double)jb * (double)rr * (double)rr;          // 2 * K * rr^2 / 2
                 double best = 1e30;
                 rp = 16;
-                for (int r = split ? 8 : 16; r <= sms - 28; r += 4) {
+                for (int r = chol_rp_min(); r <= sms - 28; r += 4) {
                     const double tp = (w_p / 128.0) * 100e-6 + m_p * w_p * w_p / (r * 0.15e12);
                     const double tb = bulk_flops / ((sms - r) * kSmFlops);
                     const double rest = std::max(0.0, bulk_flops - tp * (sms - r) * kSmFlops);
