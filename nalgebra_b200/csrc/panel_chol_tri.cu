@@ -52,15 +52,17 @@ __device__ __forceinline__ void tile_trtri_lower(const double* __restrict__ sL, 
                 }
             }
             __syncthreads();
+            // only the 16-blocks that can change: rows i > j live in a >= blk, columns k <= j in b <= blk
+            // ((8 - blk)(blk + 1) block products instead of 64: 15 on average)
             double lcol[8], xrow[8];
 #pragma unroll
-            for (int a = 0; a < 8; ++a) { const int i = tx + 16 * a; lcol[a] = (i > j && i < n) ? sL[i + j * 128] : 0.0; }
+            for (int a = blk; a < 8; ++a) { const int i = tx + 16 * a; lcol[a] = (i > j && i < n) ? sL[i + j * 128] : 0.0; }
 #pragma unroll
-            for (int b = 0; b < 8; ++b) { const int k = ty + 16 * b; xrow[b] = (k <= j) ? rb[k] : 0.0; }
+            for (int b = 0; b <= blk; ++b) { const int k = ty + 16 * b; xrow[b] = (k <= j) ? rb[k] : 0.0; }
 #pragma unroll
-            for (int a = 0; a < 8; ++a)
+            for (int a = blk; a < 8; ++a)
 #pragma unroll
-                for (int b = 0; b < 8; ++b) x.r[a][b] -= lcol[a] * xrow[b];
+                for (int b = 0; b <= blk; ++b) x.r[a][b] -= lcol[a] * xrow[b];
         }
     }
 }
@@ -112,15 +114,17 @@ potf2_trtri_kernel(double* __restrict__ a, long long lda, int n, int use_sub, do
                 }
             }
             __syncthreads();
+            // only the 16-blocks that can change and are stored: rows and columns > j live in blocks >= blk, the lower
+            // triangle in aa >= b ((8 - blk)(9 - blk)/2 block products instead of 64: 15 on average)
             double ci[8], ck[8];
 #pragma unroll
-            for (int aa = 0; aa < 8; ++aa) { const int i = tx + 16 * aa; ci[aa] = (i > j) ? sL[i + j * 128] : 0.0; }
+            for (int aa = blk; aa < 8; ++aa) { const int i = tx + 16 * aa; ci[aa] = (i > j) ? sL[i + j * 128] : 0.0; }
 #pragma unroll
-            for (int b = 0; b < 8; ++b) { const int k = ty + 16 * b; ck[b] = (k > j) ? sL[k + j * 128] : 0.0; }
+            for (int b = blk; b < 8; ++b) { const int k = ty + 16 * b; ck[b] = (k > j) ? sL[k + j * 128] : 0.0; }
 #pragma unroll
-            for (int aa = 0; aa < 8; ++aa)
+            for (int aa = blk; aa < 8; ++aa)
 #pragma unroll
-                for (int b = 0; b < 8; ++b) t.r[aa][b] -= ci[aa] * ck[b];   // entries with i < k are never stored
+                for (int b = blk; b <= aa; ++b) t.r[aa][b] -= ci[aa] * ck[b];   // entries with i < k are never stored
         }
     }
     // store L (lower triangle only)
