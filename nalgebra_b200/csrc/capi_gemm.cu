@@ -2,6 +2,7 @@
 #include "common.cuh"
 #include "kernels.cuh"
 
+#include <utility>
 #include <vector>
 
 using namespace nab;
@@ -79,8 +80,8 @@ static int check_view(const char* name, const void* p, ptrdiff_t rs, ptrdiff_t c
 
 // ------------------------------------------------------------------------------------------------
 // Pipelined host-pointer GEMM for large column-major operands: C is cut into a gr x gc grid of
-// chunks visited in snake order, so that each chunk needs at most one new row block of A or column
-// block of B.  H2D copies (stream h2d), chunk GEMMs (stream cmp) and D2H copies of finished chunks
+// chunks visited shell by shell, so that each chunk needs at most one new row block of A or column
+// block of B and the demand for new panels is spread over the whole run.  H2D copies (stream h2d), chunk GEMMs (stream cmp) and D2H copies of finished chunks
 // (stream d2h) overlap; only the first A/B pieces and the last C chunk are exposed.
 // ------------------------------------------------------------------------------------------------
 static int dgemm_host_pipelined(size_t m, size_t k, size_t n, double alpha, const double* a, size_t lda,
@@ -104,8 +105,50 @@ static int dgemm_host_pipelined(size_t m, size_t k, size_t n, double alpha, cons
         cudaStreamWaitEvent(h2d, ev_alloc, 0); cudaStreamWaitEvent(d2h, ev_alloc, 0);
     }
     std::vector<bool> a_up(nbr, false), b_up(nbc, false);
-    for (size_t step = 0; st == NA_OK && step < nbr * nbc; ++step) {
-        const size_t bi = step / nbc, jj = step % nbc, bj = (bi % 2 == 0) ? jj : nbc - 1 - jj;   // snake order
+    // The first chunk is additionally cut along K: its A row block and B column block arrive as `ks` K-slabs, and the
+    // chunk is computed as ks accumulating GEMMs, so the compute stream starts after 1/ks of the first 2 panels
+    // (19.5 ms of exposed PCIe time at 16384^3 with one slab, ~5 ms with four).
+    const size_t ks = k >= 8192 ? 4 : (k >= 2048 ? 2 : 1);
+    if (st == NA_OK && ks > 1) {
+        const size_t rows = std::min(mc, m), cols = std::min(nc, n);
+        const size_t kw = round_up(ceil_div(k, ks), 16);
+        double* dcc = dc.as<double>();
+        cudaEvent_t ev_c0 = nullptr;
+        if (beta != 0.0) {
+            if (cudaMemcpy2DAsync(dcc, lddc * 8, c, ldc * 8, rows * 8, cols, cudaMemcpyHostToDevice, h2d) != cudaSuccess) st = NA_ECUDA;
+            mk(ev_c0); cudaEventRecord(ev_c0, h2d); cudaStreamWaitEvent(cmp, ev_c0, 0);
+        }
+        std::vector<cudaEvent_t> ev_s;
+        for (size_t k0 = 0; st == NA_OK && k0 < k; k0 += kw) {
+            const size_t kk = std::min(kw, k - k0);
+            if (cudaMemcpy2DAsync(da.as<double>() + k0 * ldda, ldda * 8, a + k0 * lda, lda * 8, rows * 8, kk, cudaMemcpyHostToDevice, h2d) != cudaSuccess ||
+                cudaMemcpy2DAsync(db.as<double>() + k0, lddb * 8, b + k0, ldb * 8, kk * 8, cols, cudaMemcpyHostToDevice, h2d) != cudaSuccess) { st = NA_ECUDA; break; }
+            cudaEvent_t e = nullptr; mk(e); cudaEventRecord(e, h2d); ev_s.push_back(e);
+            cudaStreamWaitEvent(cmp, e, 0);
+            st = dgemm_device(cmp, false, rows, kk, cols, alpha, da.as<double>() + k0 * ldda, 1, (ptrdiff_t)ldda,
+                              db.as<double>() + k0, 1, (ptrdiff_t)lddb, k0 == 0 ? beta : 1.0, dcc, 1, (ptrdiff_t)lddc);
+        }
+        if (st == NA_OK) {
+            a_up[0] = true; b_up[0] = true;
+            mk(ev_a[0]); cudaEventRecord(ev_a[0], h2d); mk(ev_b[0]); cudaEventRecord(ev_b[0], h2d);
+            mk(ev_c[0]); cudaEventRecord(ev_c[0], cmp);
+            cudaStreamWaitEvent(d2h, ev_c[0], 0);
+            if (cudaMemcpy2DAsync(c, ldc * 8, dcc, lddc * 8, rows * 8, cols, cudaMemcpyDeviceToHost, d2h) != cudaSuccess) st = NA_ECUDA;
+        }
+        for (cudaEvent_t e : ev_s) ev_cin.push_back(e);      // destroyed with the others once the streams are idle
+        if (ev_c0) ev_cin.push_back(ev_c0);
+    }
+    // Chunk order: shells.  Shell L adds column block L (chunks (0..L-1, L): only B_L is new), then the corner (L, L)
+    // (A_L is new), then row block L (chunks (L, L-1..0): nothing new).  New panels are needed at steps 0, 1, 2, 4, 6,
+    // 9, 12 of 16 instead of at every step of the first row, so the H2D stream stays ahead of the compute stream.
+    std::vector<std::pair<size_t, size_t>> order;
+    for (size_t L = 0; L < std::max(nbr, nbc); ++L) {
+        if (L < nbc) for (size_t i = 0; i < std::min(L, nbr); ++i) order.push_back({i, L});
+        if (L < nbr && L < nbc) order.push_back({L, L});
+        if (L < nbr) for (size_t j = std::min(L, nbc); j-- > 0;) order.push_back({L, j});
+    }
+    for (size_t step = (ks > 1 ? 1 : 0); st == NA_OK && step < order.size(); ++step) {
+        const size_t bi = order[step].first, bj = order[step].second;
         const size_t r0 = bi * mc, rows = std::min(mc, m - r0), c0 = bj * nc, cols = std::min(nc, n - c0);
         if (!a_up[bi]) {
             if (cudaMemcpy2DAsync(da.as<double>() + r0, ldda * 8, a + r0, lda * 8, rows * 8, k, cudaMemcpyHostToDevice, h2d) != cudaSuccess) { st = NA_ECUDA; break; }
