@@ -89,9 +89,19 @@ static int dgemm_host_pipelined(size_t m, size_t k, size_t n, double alpha, cons
     Context& cx = ctx();
     cudaStream_t cmp = cx.stream, h2d = cx.stream2, d2h = nullptr;
     NAB_CUDA(cudaStreamCreateWithFlags(&d2h, cudaStreamNonBlocking));
-    const size_t gr = m >= 8192 ? 4 : 2, gc = n >= 8192 ? 4 : 2;
-    const size_t mc = round_up(ceil_div(m, gr), 128), nc = round_up(ceil_div(n, gc), 128);
-    const size_t nbr = ceil_div(m, mc), nbc = ceil_div(n, nc);
+    // Non-uniform chunk grid: a large first block (half of the rows / columns), then quarters.  The first chunk is
+    // the one that has to hide the upload of two panels behind its own compute -- (r + c) K bytes against 2 r c K
+    // flops, so it must be big (measured with a uniform 4 x 4 grid: the first two chunks waited 14 ms for PCIe) --
+    // and the last chunk, whose D2H copy is exposed, must be small.
+    auto cuts = [](size_t len) {
+        std::vector<size_t> v{0};
+        if (len >= 8192) { v.push_back(round_up(len / 2, 128)); v.push_back(round_up(3 * len / 4, 128)); }
+        else v.push_back(round_up(len / 2, 128));
+        v.push_back(len);
+        return v;
+    };
+    const std::vector<size_t> rb = cuts(m), cb = cuts(n);
+    const size_t nbr = rb.size() - 1, nbc = cb.size() - 1;
     Scratch da, db, dc;
     const size_t ldda = round_up(m, 2), lddb = round_up(k, 2), lddc = round_up(m, 2);
     int st = da.alloc(ldda * k * 8, cmp);
@@ -104,13 +114,15 @@ static int dgemm_host_pipelined(size_t m, size_t k, size_t n, double alpha, cons
         mk(ev_alloc); cudaEventRecord(ev_alloc, cmp);
         cudaStreamWaitEvent(h2d, ev_alloc, 0); cudaStreamWaitEvent(d2h, ev_alloc, 0);
     }
+    Timeline tr("NAB_GEMM_TRACE", "gemm_trace");
+    tr.start(cmp);
     std::vector<bool> a_up(nbr, false), b_up(nbc, false);
-    // The first chunk is additionally cut along K: its A row block and B column block arrive as `ks` K-slabs, and the
-    // chunk is computed as ks accumulating GEMMs, so the compute stream starts after 1/ks of the first 2 panels
-    // (19.5 ms of exposed PCIe time at 16384^3 with one slab, ~5 ms with four).
-    const size_t ks = k >= 8192 ? 4 : (k >= 2048 ? 2 : 1);
+    // The first chunk is additionally cut along K: its A row block and B column block arrive as `ks` K-slabs (>= 1024
+    // deep), and the chunk is computed as ks accumulating GEMMs, so the compute stream starts after 1/ks of the first
+    // two panels.
+    const size_t ks = k >= 2048 ? std::min<size_t>(16, k / 1024) : 1;
     if (st == NA_OK && ks > 1) {
-        const size_t rows = std::min(mc, m), cols = std::min(nc, n);
+        const size_t rows = rb[1], cols = cb[1];
         const size_t kw = round_up(ceil_div(k, ks), 16);
         double* dcc = dc.as<double>();
         cudaEvent_t ev_c0 = nullptr;
@@ -125,8 +137,10 @@ static int dgemm_host_pipelined(size_t m, size_t k, size_t n, double alpha, cons
                 cudaMemcpy2DAsync(db.as<double>() + k0, lddb * 8, b + k0, ldb * 8, kk * 8, cols, cudaMemcpyHostToDevice, h2d) != cudaSuccess) { st = NA_ECUDA; break; }
             cudaEvent_t e = nullptr; mk(e); cudaEventRecord(e, h2d); ev_s.push_back(e);
             cudaStreamWaitEvent(cmp, e, 0);
+            cudaEvent_t tg = tr.mark(cmp);
             st = dgemm_device(cmp, false, rows, kk, cols, alpha, da.as<double>() + k0 * ldda, 1, (ptrdiff_t)ldda,
                               db.as<double>() + k0, 1, (ptrdiff_t)lddb, k0 == 0 ? beta : 1.0, dcc, 1, (ptrdiff_t)lddc);
+            tr.add("slab", k0, tg, tr.mark(cmp));
         }
         if (st == NA_OK) {
             a_up[0] = true; b_up[0] = true;
@@ -143,13 +157,15 @@ static int dgemm_host_pipelined(size_t m, size_t k, size_t n, double alpha, cons
     // 9, 12 of 16 instead of at every step of the first row, so the H2D stream stays ahead of the compute stream.
     std::vector<std::pair<size_t, size_t>> order;
     for (size_t L = 0; L < std::max(nbr, nbc); ++L) {
+        const bool last_shell = L + 1 == std::max(nbr, nbc);      // its corner (the smallest chunk) goes last: its D2H is exposed
         if (L < nbc) for (size_t i = 0; i < std::min(L, nbr); ++i) order.push_back({i, L});
-        if (L < nbr && L < nbc) order.push_back({L, L});
+        if (L < nbr && L < nbc && !last_shell) order.push_back({L, L});
         if (L < nbr) for (size_t j = std::min(L, nbc); j-- > 0;) order.push_back({L, j});
+        if (L < nbr && L < nbc && last_shell) order.push_back({L, L});
     }
     for (size_t step = (ks > 1 ? 1 : 0); st == NA_OK && step < order.size(); ++step) {
         const size_t bi = order[step].first, bj = order[step].second;
-        const size_t r0 = bi * mc, rows = std::min(mc, m - r0), c0 = bj * nc, cols = std::min(nc, n - c0);
+        const size_t r0 = rb[bi], rows = rb[bi + 1] - r0, c0 = cb[bj], cols = cb[bj + 1] - c0;
         if (!a_up[bi]) {
             if (cudaMemcpy2DAsync(da.as<double>() + r0, ldda * 8, a + r0, lda * 8, rows * 8, k, cudaMemcpyHostToDevice, h2d) != cudaSuccess) { st = NA_ECUDA; break; }
             mk(ev_a[bi]); cudaEventRecord(ev_a[bi], h2d); a_up[bi] = true;
@@ -166,14 +182,19 @@ static int dgemm_host_pipelined(size_t m, size_t k, size_t n, double alpha, cons
         }
         cudaStreamWaitEvent(cmp, ev_a[bi], 0);
         cudaStreamWaitEvent(cmp, ev_b[bj], 0);
+        cudaEvent_t tg = tr.mark(cmp);
         st = dgemm_device(cmp, false, rows, k, cols, alpha, da.as<double>() + r0, 1, (ptrdiff_t)ldda,
                           db.as<double>() + c0 * lddb, 1, (ptrdiff_t)lddb, beta, dcc, 1, (ptrdiff_t)lddc);
         if (st != NA_OK) break;
+        tr.add("chunk", step, tg, tr.mark(cmp));
         mk(ev_c[step]); cudaEventRecord(ev_c[step], cmp);
         cudaStreamWaitEvent(d2h, ev_c[step], 0);
+        cudaEvent_t td = tr.mark(d2h);
         if (cudaMemcpy2DAsync(c + r0 + c0 * ldc, ldc * 8, dcc, lddc * 8, rows * 8, cols, cudaMemcpyDeviceToHost, d2h) != cudaSuccess) { st = NA_ECUDA; break; }
+        tr.add("d2h", step, td, tr.mark(d2h));
     }
     cudaError_t e1 = cudaStreamSynchronize(d2h), e2 = cudaStreamSynchronize(h2d), e3 = cudaStreamSynchronize(cmp);
+    tr.dump();
     for (auto* v : {&ev_a, &ev_b, &ev_c, &ev_cin}) for (cudaEvent_t e : *v) if (e) cudaEventDestroy(e);
     if (ev_alloc) cudaEventDestroy(ev_alloc);
     cudaStreamDestroy(d2h);

@@ -128,6 +128,22 @@ def test_gemm_strided_views_and_odd_offsets(nab, oracle):
     assert np.abs(out - a @ big[:40, :30]).max() <= gemm_tol(a, big[:40, :30], 40)
 
 
+def test_gemm_host_pipelined_path(nab):
+    """Host-pointer na_dgemm above the pipelining threshold (m, n >= 2048, k >= 512): non-uniform chunk grid, shell order,
+    K-slabs of the first chunk (k >= 2048), C uploaded only when beta != 0 (NaN-filled otherwise)."""
+    rng = np.random.default_rng(7)
+    for (m, k, n) in [(2200, 2050, 2100), (2048, 600, 2304), (8320, 1100, 2176)]:
+        a = np.asfortranarray(rng.random((m, k)) - 0.5); b = np.asfortranarray(rng.random((k, n)) - 0.5)
+        c0 = np.asfortranarray(rng.random((m, n)))
+        for (alpha, beta) in [(1.0, 0.0), (1.5, 0.5)]:
+            c = c0.copy(order="F")
+            if beta == 0.0:
+                c[...] = np.nan
+            nab.gemm(alpha, a, b, beta, c)
+            ref = alpha * (a @ b) + (beta * c0 if beta != 0.0 else 0.0)
+            assert np.abs(c - ref).max() <= gemm_tol(a, b, k), (m, k, n, alpha, beta)
+
+
 def test_sgemm_vs_oracle(nab, oracle):
     a = (oracle.uniform(130, 70, 1) - 0.5).astype(np.float32)
     b = (oracle.uniform(70, 90, 2) - 0.5).astype(np.float32)
