@@ -172,12 +172,16 @@ def run_gpu(args):
     # Inputs resident in HBM, block-distributed WITHOUT replication:
     #   rank (r, c) owns the K-chunk c of the row panel A[r-rows, :]   (m_loc x N/pc, contiguous)
     #   and the K-chunk r of the column panel B[:, c-cols]             (N/pr x n_loc, contiguous).
-    # A step assembles the panels over NVLink (one NCCL broadcast per foreign chunk, in the row /
-    # column sub-communicators, all issued up front) and accumulates C over K-pieces as they arrive,
-    # starting with the locally owned ones: the exchange overlaps the DMMA work.  (N = 1: no exchange.)
+    # A step assembles the panels over NVLink -- ONE in-place all-gather per panel, in the row / column
+    # sub-communicator, both issued up front -- and accumulates C over K-pieces as they become available:
+    # fully local pieces first, then those that only need the (smaller, earlier) B gather, then the rest.
+    # The exchange overlaps the DMMA work; while a gather is outstanding the persistent GEMM leaves 20 SMs
+    # to NCCL's kernels.  (N = 1: no exchange.)  Per-chunk broadcasts (4 + 2 collectives, the later ones
+    # queued behind full-grid GEMM pieces) cost 7.4 ms per step at 8 GPUs.
     kca, kcb = N // pc, N // pr
     A = torch.empty(m_loc * N, dtype=torch.float64, device=dev)                       # full row panel, ld = m_loc
-    Bc = [torch.empty(kcb * n_loc, dtype=torch.float64, device=dev) for _ in range(pr)]   # K-chunks of the column panel
+    Bfull = torch.empty(pr * kcb * n_loc, dtype=torch.float64, device=dev)
+    Bc = [Bfull[q * kcb * n_loc:(q + 1) * kcb * n_loc] for q in range(pr)]              # K-chunks of the column panel
     Cd = torch.empty(m_loc * n_loc, dtype=torch.float64, device=dev)
     a_chunks = [A[q * kca * m_loc:(q + 1) * kca * m_loc] for q in range(pc)]
     _capi.check(L.na_fill_uniform_block_dev(a_chunks[my_c].data_ptr(), m_loc, kca, m_loc, 1, row0, my_c * kca, N, stream))
@@ -193,8 +197,12 @@ def run_gpu(args):
             if c == my_c:
                 col_group = g
     kp = min(kca, kcb, 2048 if world > 1 else N)   # K-piece of one GEMM call (small pieces: only the first runs on a reduced grid)
-    pieces = sorted(range(N // kp), key=lambda t: (not ((t * kp) // kca == my_c and (t * kp) // kcb == my_r),
-                                                   not ((t * kp) // kca == my_c or (t * kp) // kcb == my_r), t))
+    piece_ms = 2.0 * m_loc * n_loc * kp / 36e12 * 1e3
+    n_limited = max(1, int(-(-5.0 // piece_ms)))          # pieces that start within ~5 ms of the step
+    def piece_class(t):      # 0: both operands local, 1: only B foreign, 2: only A foreign, 3: both foreign
+        a_loc, b_loc = (t * kp) // kca == my_c, (t * kp) // kcb == my_r
+        return 0 if (a_loc and b_loc) else (1 if a_loc else (2 if b_loc else 3))
+    pieces = sorted(range(N // kp), key=lambda t: (piece_class(t), t))
 
     def gemm_piece(t, first):
         k0 = t * kp
@@ -205,28 +213,26 @@ def run_gpu(args):
                                    Cd.data_ptr(), 1, m_loc, stream))
 
     def step():
-        wa, wb = {}, {}
+        ha = hb = None
         if world > 1:
-            # every member of a sub-communicator takes part in every broadcast (the owner as the source)
-            if pc > 1:
-                for q in range(pc):
-                    h = dist.broadcast(a_chunks[q], src=my_r * pc + q, group=row_group, async_op=True)
-                    if q != my_c:
-                        wa[q] = h
             if pr > 1:
-                for q in range(pr):
-                    h = dist.broadcast(Bc[q], src=q * pc + my_c, group=col_group, async_op=True)
-                    if q != my_r:
-                        wb[q] = h
+                hb = dist.all_gather_into_tensor(Bfull, Bc[my_r], group=col_group, async_op=True)
+            if pc > 1:
+                ha = dist.all_gather_into_tensor(A, a_chunks[my_c], group=row_group, async_op=True)
         for i, t in enumerate(pieces):
-            qa, qb = (t * kp) // kca, (t * kp) // kcb
-            if qa in wa:
-                wa.pop(qa).wait()
-            if qb in wb:
-                wb.pop(qb).wait()
-            # while chunks are still in flight, leave SMs to NCCL's copy kernels (the GEMM is persistent)
-            L.na_set_gemm_sm_limit(sm_count - 20 if (i == 0 and (wa or wb)) else 0)
+            cls = piece_class(t)
+            if hb is not None and cls in (1, 3):
+                hb.wait(); hb = None
+            if ha is not None and cls in (2, 3):
+                ha.wait(); ha = None
+            # while a gather can still be in flight (the first ~5 ms of the step: 0.27 - 1.07 GB over NVLink), leave SMs
+            # to NCCL's kernels: the GEMM is persistent, a full grid would make the CTAs that find no SM start late
+            L.na_set_gemm_sm_limit(sm_count - 20 if (i < n_limited and (ha is not None or hb is not None)) else 0)
             gemm_piece(t, i == 0)
+        if ha is not None:
+            ha.wait()
+        if hb is not None:
+            hb.wait()
         L.na_set_gemm_sm_limit(0)
 
     def step_replicated():
@@ -281,6 +287,13 @@ def run_gpu(args):
         nk = pr
     else:
         kernel_ms = ms_total / args.steps
+    exchange_check = None
+    if ngpus > 1:      # the exchanged + K-pieced product against the product of the assembled panels (same kernel, other K order)
+        step(); torch.cuda.synchronize()
+        c_step = Cd.clone()
+        step_replicated(); torch.cuda.synchronize()
+        exchange_check = float((c_step - Cd).abs().max().item() / max(Cd.abs().max().item(), 1e-300))
+        del c_step
     achieved = (flops / ngpus) / (kernel_ms * 1e-3) / 1e12
     traffic = None
     try:   # DRAM bytes of one launch from the committed `ncu --set full` capture (same workload only)
@@ -391,7 +404,7 @@ def run_gpu(args):
                        "distribution": ("single GPU" if ngpus == 1 else
                                         f"A and B block-distributed without replication; per step each rank receives {pc - 1} A K-chunks "
                                         f"({(pc - 1) * kca * m_loc * 8 / 1e9:.2f} GB) and {pr - 1} B K-chunks ({(pr - 1) * kcb * n_loc * 8 / 1e9:.2f} GB) "
-                                        "over NVLink (NCCL broadcasts in row/column sub-communicators) overlapped with the K-chunked GEMM"),
+                                        "over NVLink (one in-place NCCL all-gather per panel in the row / column sub-communicator) overlapped with the K-chunked GEMM"),
                        "l2": "inputs (>=1.6 GB per GPU) exceed the 126 MB L2; no explicit flush",
                        "pct_of_fp64_peak": 100.0 * value / 1e3 / (FP64_PEAK_TFLOPS * ngpus)},
             "roofline": {"bound": "tensor", "achieved": achieved, "peak": FP64_PEAK_TFLOPS, "unit": "TFLOP/s",
@@ -401,6 +414,8 @@ def run_gpu(args):
                          "compute_only_ms_per_step": kernel_ms},
             "clocks": clocks, "gpu_launches": int(launches),
         }
+        if exchange_check is not None:
+            line["config"]["exchange_check_max_rel_diff"] = exchange_check     # exchanged K-pieced product vs assembled panels
         if e2e:
             line["e2e"] = e2e
         if cpu:
