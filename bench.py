@@ -145,7 +145,7 @@ def run_gpu(args):
     import torch
     import torch.distributed as dist
     from nalgebra_b200 import _capi
-    from nalgebra_b200.sharding import process_grid
+    from nalgebra_b200.sharding import gemm_piece_class, gemm_piece_order, process_grid
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -200,9 +200,8 @@ def run_gpu(args):
     piece_ms = 2.0 * m_loc * n_loc * kp / 36e12 * 1e3
     n_limited = max(1, int(-(-5.0 // piece_ms)))          # pieces that start within ~5 ms of the step
     def piece_class(t):      # 0: both operands local, 1: only B foreign, 2: only A foreign, 3: both foreign
-        a_loc, b_loc = (t * kp) // kca == my_c, (t * kp) // kcb == my_r
-        return 0 if (a_loc and b_loc) else (1 if a_loc else (2 if b_loc else 3))
-    pieces = sorted(range(N // kp), key=lambda t: (piece_class(t), t))
+        return gemm_piece_class(t, kp, kca, kcb, my_r, my_c)
+    pieces = gemm_piece_order(N, kp, kca, kcb, my_r, my_c)
 
     def gemm_piece(t, first):
         k0 = t * kp

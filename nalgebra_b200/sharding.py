@@ -41,3 +41,21 @@ def block_cyclic_owner(block: int, world: int) -> int:
 
 def block_cyclic_local_blocks(rank: int, world: int, nblocks: int) -> list[int]:
     return list(range(rank, nblocks, world))
+
+
+def gemm_piece_class(t: int, kp: int, kca: int, kcb: int, my_r: int, my_c: int) -> int:
+    """Which operands of K-piece t (k in [t*kp, (t+1)*kp)) rank (my_r, my_c) already owns in the non-replicated
+    layout (A row panel cut into K-chunks of kca columns, chunk c owned by grid column c; B column panel cut into
+    K-chunks of kcb rows, chunk r owned by grid row r): 0 both, 1 only A (B arrives with the column gather),
+    2 only B (A arrives with the row gather), 3 neither."""
+    a_loc, b_loc = (t * kp) // kca == my_c, (t * kp) // kcb == my_r
+    return 0 if (a_loc and b_loc) else (1 if a_loc else (2 if b_loc else 3))
+
+
+def gemm_piece_order(n_k: int, kp: int, kca: int, kcb: int, my_r: int, my_c: int) -> list[int]:
+    """Order in which a rank accumulates the K-pieces of its C tile: local pieces first, then those that wait only
+    for the (smaller, earlier) B gather, then those that wait for the A gather, then both -- so the DMMA work
+    overlaps the exchange."""
+    assert kca % kp == 0 and kcb % kp == 0 and n_k % kp == 0
+    return sorted(range(n_k // kp), key=lambda t: (gemm_piece_class(t, kp, kca, kcb, my_r, my_c), t))
+

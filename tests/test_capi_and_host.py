@@ -103,3 +103,32 @@ def test_sharding_grid_arithmetic():
             cover[r0:r1, c0:c1] += 1
         assert (cover == 1).all()
     assert S.block_cyclic_local_blocks(1, 4, 10) == [1, 5, 9] and S.block_cyclic_owner(7, 4) == 3
+
+
+def test_gemm_exchange_piece_order():
+    """K-piece schedule of the multi-GPU GEMM step (bench.py): every piece exactly once, local pieces before the ones
+    that wait for a gather, and the classes agree with the ownership rule of the non-replicated layout."""
+    from nalgebra_b200 import sharding as S
+    n = 16384
+    for world in (2, 4, 8):
+        pr, pc = S.process_grid(world)
+        kca, kcb = n // pc, n // pr
+        kp = min(kca, kcb, 2048)
+        n_local_local = 0
+        for rank in range(world):
+            r, c = divmod(rank, pc)
+            order = S.gemm_piece_order(n, kp, kca, kcb, r, c)
+            assert sorted(order) == list(range(n // kp))
+            classes = [S.gemm_piece_class(t, kp, kca, kcb, r, c) for t in order]
+            assert classes == sorted(classes)
+            for t in order:
+                k0 = t * kp
+                a_local = c * kca <= k0 < (c + 1) * kca
+                b_local = r * kcb <= k0 < (r + 1) * kcb
+                assert S.gemm_piece_class(t, kp, kca, kcb, r, c) == (0 if a_local and b_local else 1 if a_local else 2 if b_local else 3)
+            # every rank owns one A chunk and one B chunk: kca / kp pieces with A local, kcb / kp with B local
+            assert sum(1 for x in classes if x in (0, 1)) == kca // kp
+            assert sum(1 for x in classes if x in (0, 2)) == kcb // kp
+            n_local_local += classes.count(0)
+        assert n_local_local > 0
+
