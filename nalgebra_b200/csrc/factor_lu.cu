@@ -89,7 +89,11 @@ static int lu_rec(const LuCtx& c, size_t j0, size_t nc) {
 //   bulk(j)   : the same on all remaining columns (and the row swaps on the columns left of the
 //               panel), on a second stream with the remaining SMs, concurrent with panel(j + nb).
 // ------------------------------------------------------------------------------------------------
-constexpr size_t LU_NB = 512;
+static size_t lu_nb() {
+    static size_t v = [] { const char* e = getenv("NAB_LU_NB"); size_t x = e ? (size_t)atoi(e) : 512; return x >= 128 ? x / 64 * 64 : 512; }();
+    return v;
+}
+#define LU_NB (lu_nb())
 
 static int lu_right_update(const LuCtx& c, cudaStream_t st, size_t j, size_t jb, size_t x0, size_t nx, const void* ws_outer,
                            const double* inv_l11) {
