@@ -166,7 +166,10 @@ NAB_API int na_tri_solve_f64_dev(int lower, int trans, int unit_diag, size_t n, 
 
 /* Upper bound on the CTAs (= SMs: the GEMM kernels are persistent, one CTA per SM) that GEMM launches
  * issued by the CALLING THREAD may use; 0 restores "all SMs".  Lets a caller keep SMs free for work on
- * other streams (NCCL copy kernels while panels are staged over NVLink, a concurrent panel kernel). */
+ * other streams (NCCL copy kernels while panels are staged over NVLink, a concurrent panel kernel).
+ * The setting is thread-local (it has no effect on launches made from other host threads) and stays in
+ * force across factorization calls: the blocked drivers combine it with their own panel/bulk split
+ * (the smaller limit applies) and never clear it. */
 NAB_API int na_set_gemm_sm_limit(int max_ctas);
 
 /* ---- building blocks of the multi-GPU (1D block-cyclic) factorizations, device pointers ------ */

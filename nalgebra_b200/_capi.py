@@ -10,7 +10,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libnalgebra_b200.so")
+LIB_PATH = os.environ.get("NAB_LIB") or os.path.join(_HERE, "libnalgebra_b200.so")
 
 NA_OK, NA_NOT_PD, NA_SINGULAR = 0, 1, 2
 NA_EINVAL, NA_ECUDA, NA_ENOMEM, NA_ENCCL = -1, -2, -3, -4

@@ -14,8 +14,12 @@ from concurrent.futures import ThreadPoolExecutor
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
-OBJ_DIR = os.path.join(HERE, "build")
-LIB_PATH = os.path.join(HERE, "libnalgebra_b200.so")
+# A build with extra flags (NAB_EXTRA_NVCC_FLAGS="-DNAB_GETF2_PROF -DNAB_DEBUG_HOOKS": per-phase cycle counters and the
+# debug exports the tools/ scripts use) goes to its own object directory and library; select it with
+# NAB_LIB=nalgebra_b200/libnalgebra_b200_dbg.so.  The product library never carries those symbols.
+_DBG = bool(os.environ.get("NAB_EXTRA_NVCC_FLAGS", "").strip())
+OBJ_DIR = os.path.join(HERE, "build_dbg" if _DBG else "build")
+LIB_PATH = os.path.join(HERE, "libnalgebra_b200_dbg.so" if _DBG else "libnalgebra_b200.so")
 
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 NVCC_FLAGS = [

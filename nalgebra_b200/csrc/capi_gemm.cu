@@ -259,7 +259,7 @@ int na_fill_uniform_block_dev(double* a, size_t nrows, size_t ncols, size_t lda,
 
 int na_set_gemm_sm_limit(int max_ctas) {
     if (max_ctas < 0) { set_error("na_set_gemm_sm_limit: negative limit"); return NA_EINVAL; }
-    set_gemm_sm_limit(max_ctas);
+    set_user_gemm_sm_limit(max_ctas);
     return NA_OK;
 }
 

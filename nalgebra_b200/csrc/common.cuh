@@ -70,6 +70,29 @@ struct Scratch {
     template <typename T> T* as() const { return static_cast<T*>(p); }
 };
 
+// RAII over the side streams / events of the blocked drivers: an early return (NAB_TRY / NAB_CUDA) between creation
+// and the end of a driver neither leaks them nor leaves work pending on them.  Declare guards BEFORE any Scratch
+// that allocates on their stream (destruction runs in reverse order).
+struct StreamGuard {
+    cudaStream_t s = nullptr;
+    // high_priority: the greatest priority the device offers (the latency-bound panel chain goes first when CTAs
+    // of several streams are pending)
+    int create(bool high_priority = false) {
+        int lo = 0, hi = 0;
+        if (high_priority) NAB_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+        NAB_CUDA(cudaStreamCreateWithPriority(&s, cudaStreamNonBlocking, high_priority ? hi : 0));
+        return NA_OK;
+    }
+    ~StreamGuard() { if (s) { cudaStreamSynchronize(s); cudaStreamDestroy(s); } }
+    operator cudaStream_t() const { return s; }
+};
+struct EventGuard {
+    cudaEvent_t e = nullptr;
+    int create() { NAB_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming)); return NA_OK; }
+    ~EventGuard() { if (e) cudaEventDestroy(e); }
+    operator cudaEvent_t() const { return e; }
+};
+
 // ---- optional timelines ----------------------------------------------------------------------------
 // NAB_LU_TRACE=1 / NAB_CHOL_TRACE=1: start and duration of the phases of a blocked driver, taken with CUDA
 // events on the streams the work runs on, printed to stderr when the factorization is done.
@@ -79,10 +102,11 @@ struct Timeline {
     cudaEvent_t t0 = nullptr;
     struct Rec { const char* what; size_t j; cudaEvent_t a, b; };
     std::vector<Rec> recs;
+    std::vector<cudaEvent_t> events;
     Timeline(const char* env, const char* tag_) : tag(tag_) { const char* e = getenv(env); on = e && atoi(e) != 0; }
     cudaEvent_t mark(cudaStream_t s) {
         cudaEvent_t e = nullptr;
-        if (on) { cudaEventCreate(&e); cudaEventRecord(e, s); }
+        if (on) { cudaEventCreate(&e); cudaEventRecord(e, s); events.push_back(e); }
         return e;
     }
     void start(cudaStream_t s) { t0 = mark(s); }
@@ -95,7 +119,9 @@ struct Timeline {
             cudaEventElapsedTime(&s0, t0, r.a); cudaEventElapsedTime(&d, r.a, r.b);
             fprintf(stderr, "%s j=%6zu %-7s start %9.3f ms  dur %8.3f ms\n", tag, r.j, r.what, s0, d);
         }
-        recs.clear();      // diagnostic mode only: the events (shared between records) are left to the context
+        recs.clear();
+        for (cudaEvent_t e : events) cudaEventDestroy(e);
+        events.clear();
     }
 };
 

@@ -503,8 +503,15 @@ static int prepare_operand(cudaStream_t s, const Operand& op, Scratch& scratch, 
 
 // Upper bound on the CTAs a GEMM launch may use (look-ahead: panel work and the bulk trailing update
 // run concurrently on disjoint sets of SMs).  0 = all SMs.  Thread local: set by the blocked drivers.
-static thread_local int g_sm_limit = 0;
+// Two levels: the caller's own reservation (na_set_gemm_sm_limit) and the limit a blocked driver sets around its panel /
+// bulk launches; the smaller non-zero one applies, and a driver clearing ITS limit leaves the caller's in place.
+static thread_local int g_sm_limit = 0, g_user_sm_limit = 0;
 void set_gemm_sm_limit(int limit) { g_sm_limit = limit; }
+void set_user_gemm_sm_limit(int limit) { g_user_sm_limit = limit; }
+static int effective_sm_limit() {
+    if (g_sm_limit > 0 && g_user_sm_limit > 0) return std::min(g_sm_limit, g_user_sm_limit);
+    return g_sm_limit > 0 ? g_sm_limit : g_user_sm_limit;
+}
 
 static int launch_gemm(cudaStream_t s, bool a_kmajor, bool b_kmajor, const CUtensorMap& ma, const CUtensorMap& mb, const GemmParams& p) {
     using namespace cfg;
@@ -519,7 +526,7 @@ static int launch_gemm(cudaStream_t s, bool a_kmajor, bool b_kmajor, const CUten
     });
     if (attr_err != cudaSuccess) return cuda_fail(attr_err, "cudaFuncSetAttribute(dgemm)", __FILE__, __LINE__);
     int grid = std::min(p.num_tiles, ctx().sm_count);
-    if (g_sm_limit > 0) grid = std::min(grid, g_sm_limit);
+    if (effective_sm_limit() > 0) grid = std::min(grid, effective_sm_limit());
     if (a_kmajor) {
         if (b_kmajor) dgemm_tma_dmma_kernel<true, true><<<grid, THREADS, SMEM_BYTES, s>>>(ma, mb, p);
         else dgemm_tma_dmma_kernel<true, false><<<grid, THREADS, SMEM_BYTES, s>>>(ma, mb, p);

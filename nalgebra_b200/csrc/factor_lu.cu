@@ -10,6 +10,7 @@
 #include <algorithm>
 #include <cstdio>
 #include <cstdlib>
+#include <cstring>
 #include <vector>
 
 #include "common.cuh"
@@ -27,7 +28,30 @@ struct LuCtx {
     int* seq_state;           // host counter of exchange sequence numbers used in ws_getf2
     int getf2_limit = 0;      // max CTAs of a GETF2 leaf (look-ahead: the SMs kept free of the bulk GEMM); 0 = no limit
     Timeline* tl = nullptr;   // optional per-node timeline of the panel recursion
+    int* lists = nullptr;     // device: one moved-row list (kRegListInts ints, count zeroed) per leaf of this factorization
+    int* leaf_seq = nullptr;  // host counter: lists handed out so far
+    size_t max_leaves = 0;
 };
+
+// NAB_GETF2=smem selects the shared-memory leaf of panel_lu.cu everywhere (A/B timing); default: the
+// register-resident leaf wherever the panel fits it.
+static bool lu_use_reg() {
+    static bool v = [] { const char* e = getenv("NAB_GETF2"); return !(e && strcmp(e, "smem") == 0); }();
+    return v;
+}
+
+// One GETF2 leaf.  *list (when the register-resident leaf ran and a list slot was left) receives the leaf's
+// moved-row list for rowperm_apply_lists; nullptr means "build the permutation from ipiv".
+static int lu_leaf(const LuCtx& c, double* ajj, size_t m, size_t w, size_t j0, int** list = nullptr) {
+    if (list) *list = nullptr;
+    const int greg = lu_use_reg() ? getf2_reg_grid(m, w) : 0;
+    if (greg > 0 && (c.getf2_limit == 0 || greg <= c.getf2_limit)) {
+        int* l = nullptr;
+        if (list && c.lists && (size_t)*c.leaf_seq < c.max_leaves) { l = c.lists + (size_t)(*c.leaf_seq)++ * kRegListInts; *list = l; }
+        return getf2_panel_reg(c.s, ajj, c.lda, m, w, j0, c.ipiv, c.ws_getf2, c.seq_state, c.getf2_limit, l);
+    }
+    return getf2_panel(c.s, ajj, c.lda, m, w, j0, c.ipiv, c.ws_getf2, c.seq_state, c.getf2_limit);
+}
 
 static int lu_apply_swaps(const LuCtx& c, size_t k0, size_t K, double* cols, size_t ncols) {
     if (K == 0 || ncols == 0) return NA_OK;
@@ -35,12 +59,66 @@ static int lu_apply_swaps(const LuCtx& c, size_t k0, size_t K, double* cols, siz
     return rowperm_apply(c.s, cols, c.lda, ncols, std::min(2 * K, c.M), c.ws_perm, c.M);
 }
 
+// Panels of up to lu_flat() columns: flat right-looking loop over W-column leaves --
+//   GETF2 leaf -> its row moves on the columns right of it (inside the panel) -> U12 = L11^-1 A12 (direct small TRSM)
+//   -> A22 -= A21 U12 (one rank-W GEMM) -> next leaf; the leaves' row moves on the columns LEFT of them come last.
+// 4 launches per leaf instead of the ~7 of the recursive split (no perm build: the register-resident leaf emits its
+// moved-row list; one small TRSM per leaf instead of TRSM + GEMM + TRSM chains at the upper nodes).
+static size_t lu_flat() {
+    static size_t v = [] { const char* e = getenv("NAB_LU_FLAT"); return e ? (size_t)atoi(e) : (size_t)512; }();
+    return v;
+}
+
+static int lu_swaps_from_leaf(const LuCtx& c, const int* list, size_t k0, size_t K, double* cols, size_t ncols) {
+    if (ncols == 0 || K == 0) return NA_OK;
+    if (list) return rowperm_apply_lists(c.s, cols, c.lda, ncols, std::min<size_t>(2 * K, kRegListMax), list, list + 1, list + 1 + kRegListMax);
+    return lu_apply_swaps(c, k0, K, cols, ncols);
+}
+
+static int lu_panel_flat(const LuCtx& c, size_t j0, size_t nc) {
+    std::vector<int*> lists;
+    std::vector<size_t> starts;
+    for (size_t k0 = 0; k0 < nc; k0 += c.W) {
+        const size_t wk = std::min(c.W, nc - k0), jk = j0 + k0, mk = c.M - jk;
+        double* akk = c.a + jk + jk * c.lda;
+        int* list = nullptr;
+        cudaEvent_t t0 = c.tl ? c.tl->mark(c.s) : nullptr;
+        NAB_TRY(lu_leaf(c, akk, mk, wk, jk, &list));
+        cudaEvent_t t1 = c.tl ? c.tl->mark(c.s) : nullptr;
+        lists.push_back(list); starts.push_back(k0);
+        const size_t n2 = nc - k0 - wk, kk = std::min(wk, mk);
+        if (n2 > 0) {
+            double* a12 = akk + wk * c.lda;
+            NAB_TRY(lu_swaps_from_leaf(c, list, jk, kk, a12 - jk, n2));                  // whole rows: columns start at row 0
+            cudaEvent_t t2 = c.tl ? c.tl->mark(c.s) : nullptr;
+            NAB_TRY(trsm_unit_lower_small(c.s, kk, akk, c.lda, a12, c.lda, n2));
+            cudaEvent_t t3 = c.tl ? c.tl->mark(c.s) : nullptr;
+            if (mk > wk)
+                NAB_TRY(dgemm_device(c.s, false, mk - wk, wk, n2, -1.0, akk + wk, 1, (ptrdiff_t)c.lda, a12, 1, (ptrdiff_t)c.lda, 1.0,
+                                     a12 + wk, 1, (ptrdiff_t)c.lda));
+            if (c.tl) {
+                cudaEvent_t t4 = c.tl->mark(c.s);
+                c.tl->add("f.swap", jk, t1, t2); c.tl->add("f.trsm", jk, t2, t3); c.tl->add("f.gemm", jk, t3, t4);
+            }
+        }
+        if (c.tl) c.tl->add("getf2", jk, t0, t1);
+    }
+    cudaEvent_t t5 = c.tl ? c.tl->mark(c.s) : nullptr;
+    for (size_t i = 1; i < lists.size(); ++i) {
+        const size_t k0 = starts[i], jk = j0 + k0;
+        NAB_TRY(lu_swaps_from_leaf(c, lists[i], jk, std::min(std::min(c.W, nc - k0), c.M - jk), c.a + j0 * c.lda, k0));
+    }
+    if (c.tl) c.tl->add("f.swapL", j0, t5, c.tl->mark(c.s));
+    return NA_OK;
+}
+
 static int lu_rec(const LuCtx& c, size_t j0, size_t nc) {
     if (nc == 0) return NA_OK;
     double* ajj = c.a + j0 + j0 * c.lda;
+    if (nc > c.W && nc <= lu_flat() && c.W <= 64) return lu_panel_flat(c, j0, nc);
     if (nc <= c.W) {
         cudaEvent_t t = c.tl ? c.tl->mark(c.s) : nullptr;
-        NAB_TRY(getf2_panel(c.s, ajj, c.lda, c.M - j0, nc, j0, c.ipiv, c.ws_getf2, c.seq_state, c.getf2_limit));
+        NAB_TRY(lu_leaf(c, ajj, c.M - j0, nc, j0));
         if (c.tl) c.tl->add("getf2", j0, t, c.tl->mark(c.s));
         return NA_OK;
     }
@@ -114,12 +192,17 @@ static bool lu_split() {
 }
 
 static int lu_lookahead(LuCtx c, size_t N, size_t mn) {
-    cudaStream_t sp = c.s, su = nullptr;
-    cudaEvent_t ev_p = nullptr, ev_u = nullptr, ev_d = nullptr;
-    NAB_CUDA(cudaStreamCreateWithFlags(&su, cudaStreamNonBlocking));
-    NAB_CUDA(cudaEventCreateWithFlags(&ev_p, cudaEventDisableTiming));
-    NAB_CUDA(cudaEventCreateWithFlags(&ev_u, cudaEventDisableTiming));
-    NAB_CUDA(cudaEventCreateWithFlags(&ev_d, cudaEventDisableTiming));
+    // The panel chain (la + panel) runs on an internal HIGH-priority stream and the bulk update on a normal one:
+    // when both have CTAs pending (right after la, when bulk(j)'s row swaps / TRSM flood the SMs) the cooperative
+    // GETF2 launch of the next panel's first leaf is placed first instead of waiting ~100 us behind them.
+    StreamGuard sp_g, su_g;
+    EventGuard ev_p, ev_u, ev_d, ev_in;
+    NAB_TRY(sp_g.create(true)); NAB_TRY(su_g.create(false));
+    NAB_TRY(ev_p.create()); NAB_TRY(ev_u.create()); NAB_TRY(ev_d.create()); NAB_TRY(ev_in.create());
+    const cudaStream_t caller = c.s, sp = sp_g.s, su = su_g.s;
+    NAB_CUDA(cudaEventRecord(ev_in, caller));
+    NAB_CUDA(cudaStreamWaitEvent(sp, ev_in, 0));
+    c.s = sp;
     Scratch wso[2], invb[2];      // per-step permutation lists and inverses of L11's diagonal blocks, double-buffered
     int st = wso[0].alloc(rowperm_workspace_bytes(c.M), sp);
     if (st == NA_OK) st = wso[1].alloc(rowperm_workspace_bytes(c.M), sp);
@@ -127,7 +210,12 @@ static int lu_lookahead(LuCtx c, size_t N, size_t mn) {
     if (st == NA_OK) st = invb[0].alloc(inv_bytes, sp);
     if (st == NA_OK) st = invb[1].alloc(inv_bytes, sp);
     const int sms = ctx().sm_count;
-    const int g_getf2 = (int)ceil_div(c.M, (size_t)384) + 2;          // CTAs the 64-wide GETF2 leaf needs at full height
+    // CTAs (= SMs kept free of the bulk GEMM) the GETF2 leaf needs for a panel of m rows: the register-resident leaf
+    // holds 256 rows of 64 columns per CTA, the shared-memory leaf 384
+    const bool reg_leaf = lu_use_reg() && getf2_reg_grid(c.M, c.W) > 0;
+    auto leaf_ctas = [&](size_t m) { return reg_leaf ? getf2_reg_grid(m, c.W) : (int)ceil_div(m, (size_t)384) + 2; };
+    static const double tp0 = [] { const char* e = getenv("NAB_LU_TP0"); return e ? atof(e) : 0.0; }();
+    static const double tp1 = [] { const char* e = getenv("NAB_LU_TP1"); return e ? atof(e) : 0.0; }();
     bool bulk_pending = false;
     int par = 0;
     Timeline tr("NAB_LU_TRACE", "lu_trace");
@@ -155,10 +243,13 @@ static int lu_lookahead(LuCtx c, size_t N, size_t mn) {
         // starts when that panel is done and takes the whole GPU: the rp SMs reserved for the latency-bound
         // panel chain (~5.3 us per column whatever its height) idle only while the panel actually runs.
         const size_t x0 = jn + jbn, nx = N - x0, m2 = c.M - jn;
-        const double t_panel = (double)jbn * (4.5e-6 + 2.5e-6 * (double)m2 / 16384.0);   // measured 2.3 .. 4.0 ms per 512
-        // SMs for the panel chain: what the 64-wide GETF2 leaf needs at this height (384 rows per CTA); more (the
-        // leaf then spreads its rows over more CTAs) once the whole bulk update fits beside the panel anyway.
-        int rp = std::min(g_getf2, (int)ceil_div(m2, (size_t)384) + 2);
+        // panel duration model (per column: leaf + recursion nodes), measured per 512 columns: shared-memory leaf
+        // 2.3 .. 4.0 ms, register-resident leaf 1.4 .. 2.2 ms
+        const double t_panel = (double)jbn * (reg_leaf ? (tp0 > 0 ? tp0 : 2.7e-6) + (tp1 > 0 ? tp1 : 1.6e-6) * (double)m2 / 16384.0
+                                                       : 4.5e-6 + 2.5e-6 * (double)m2 / 16384.0);
+        // SMs for the panel chain: what the GETF2 leaf needs at this height; more once the whole bulk update fits
+        // beside the panel anyway.
+        int rp = leaf_ctas(m2);
         {
             const double bulk_flops = 2.0 * (double)m2 * (double)jb * (double)nx;
             for (int r = rp; r <= std::min(72, sms / 2); r += 4)
@@ -201,13 +292,18 @@ static int lu_lookahead(LuCtx c, size_t N, size_t mn) {
         par ^= 1;
     }
     if (bulk_pending) cudaStreamWaitEvent(sp, ev_u, 0);
+    cudaEventRecord(ev_in, sp);
+    cudaStreamWaitEvent(caller, ev_in, 0);             // the caller's stream continues after the whole factorization
     cudaStreamSynchronize(su);
     tr.dump();
-    cudaEventDestroy(ev_p); cudaEventDestroy(ev_u); cudaEventDestroy(ev_d); cudaStreamDestroy(su);
     return st;
 }
 
 static size_t lu_leaf_width(size_t M) {
+    if (lu_use_reg()) {                          // widest register-resident leaf whose rows fit the SMs
+        for (size_t w : {64, 32, 16})
+            if (getf2_reg_grid(M, w) > 0) return w;
+    }
     if (M <= 28000) return 128;
     if (M <= 56000) return 64;
     if (M <= 113000) return 32;
@@ -231,9 +327,16 @@ int lu_device(cudaStream_t s, size_t M, size_t N, double* a, size_t lda, size_t*
     NAB_TRY(iota_int(s, iota.as<int>(), mn, 0));
     NAB_TRY(iota_int(s, ipiv.as<int>(), mn, 0));
     LuCtx c{s, a, lda, M, lu_leaf_width(M), ipiv.as<int>(), iota.as<int>(), wsg.p, wsp.p, &seq_state};
+    Scratch lists;
+    int leaf_seq = 0;
+    c.max_leaves = ceil_div(mn, (size_t)16) + 8;
+    NAB_TRY(lists.alloc(c.max_leaves * kRegListInts * sizeof(int), s));
+    NAB_CUDA(cudaMemsetAsync(lists.p, 0, c.max_leaves * kRegListInts * sizeof(int), s));
+    c.lists = lists.as<int>(); c.leaf_seq = &leaf_seq;
     const bool lookahead = mn >= 4 * LU_NB && M <= 20000;
     if (lookahead) {
-        c.W = 64;
+        static const size_t la_leaf = [] { const char* e = getenv("NAB_LU_LEAF"); const int v = e ? atoi(e) : 64; return (size_t)((v == 16 || v == 32) ? v : 64); }();
+        c.W = la_leaf;
         NAB_TRY(lu_lookahead(c, N, mn));
     } else {
         NAB_TRY(lu_rec(c, 0, mn));

@@ -12,7 +12,8 @@ int dgemm_device(cudaStream_t s, bool lower_only, size_t m, size_t k, size_t n, 
                  const double* a, ptrdiff_t rsa, ptrdiff_t csa, const double* b, ptrdiff_t rsb, ptrdiff_t csb,
                  double beta, double* c, ptrdiff_t rsc, ptrdiff_t csc);
 int fill_spd(cudaStream_t s, double* a, size_t nrows, size_t ncols, size_t lda, uint64_t seed, size_t row0, size_t col0, size_t n);
-void set_gemm_sm_limit(int limit);   // 0 = all SMs; thread local
+void set_gemm_sm_limit(int limit);        // the blocked drivers' limit; 0 = none; thread local
+void set_user_gemm_sm_limit(int limit);   // the caller's reservation (na_set_gemm_sm_limit); thread local
 // Per-SM throughput the look-ahead schedule models assume for K = nb update GEMMs (36.3 TFLOP/s / 148 SMs at ~90 %).
 constexpr double kSmFlops = 0.22e12;
 int pack_strided(cudaStream_t s, double* dst, size_t ldd, const double* src, ptrdiff_t rs, ptrdiff_t cs, size_t rows, size_t cols);
@@ -39,6 +40,16 @@ constexpr int kLuPanel = 128;      // widest GETF2 leaf panel
 size_t getf2_workspace_bytes();
 int getf2_panel(cudaStream_t st, double* a_panel, size_t lda, size_t m, size_t w, size_t j0, int* ipiv, void* ws, int* seq_state,
                 int cta_limit = 0);
+// register-resident leaf (panel_lu_reg.cu): w <= 64, rows in registers, implicit pivoting
+int getf2_reg_grid(size_t m, size_t w);     // CTAs it needs for an m x w panel; 0 = does not fit
+// list (optional, device, zeroed count): the rows the leaf moved, ready for rowperm_apply_lists -- [0] = count,
+// [1 ..] dest[kRegListMax], then src[kRegListMax] (global row indices j0 + ...)
+constexpr int kRegListMax = 128;
+constexpr int kRegListInts = 1 + 2 * kRegListMax + 3;     // one leaf's list, padded to a multiple of 4 ints
+int getf2_panel_reg(cudaStream_t st, double* a_panel, size_t lda, size_t m, size_t w, size_t j0, int* ipiv, void* ws, int* seq_state,
+                    int cta_limit = 0, int* list = nullptr);
+int rowperm_apply_lists(cudaStream_t st, double* a, size_t lda, size_t ncols, size_t max_touched, const int* count, const int* dest,
+                        const int* src);
 size_t rowperm_workspace_bytes(size_t n);
 int rowperm_build(cudaStream_t st, const int* sa, const int* sb, size_t K, size_t stride, size_t n, void* ws);
 int rowperm_apply(cudaStream_t st, double* a, size_t lda, size_t ncols, size_t max_touched, const void* ws, size_t n);

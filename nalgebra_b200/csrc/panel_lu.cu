@@ -11,6 +11,7 @@
 
 #include "common.cuh"
 #include "kernels.cuh"
+#include "panel_lu.cuh"
 
 namespace nab {
 
@@ -35,53 +36,6 @@ struct Getf2Params {
     double2* rowc;                 // [2][w]        (value, seq) pairs: current row c, published by its owner
     int seq0;                      // sequence numbers already consumed in this workspace
 };
-
-// (value, seq) travel in one 16-byte word: a reader that sees the expected seq has the value.
-__device__ __forceinline__ void lu_st_pair(double2* p, double v, double seq) {
-    asm volatile("st.global.v2.f64 [%0], {%1, %2};" ::"l"(p), "d"(v), "d"(seq) : "memory");
-}
-__device__ __forceinline__ double lu_ld_pair(const double2* p, double seq) {
-    double x, y;
-    do {
-        asm volatile("ld.volatile.global.v2.f64 {%0, %1}, [%2];" : "=d"(x), "=d"(y) : "l"(p) : "memory");
-    } while (y != seq);
-    return x;
-}
-
-__device__ __forceinline__ void lu_ld_pair_raw(const double2* p, double& x, double& y) {
-    asm volatile("ld.volatile.global.v2.f64 {%0, %1}, [%2];" : "=d"(x), "=d"(y) : "l"(p) : "memory");
-}
-// candidate header: (|value|, seq << 32 | row) in one 16-byte word
-__device__ __forceinline__ double pack_seq_row(int seq, int row) {
-    return __longlong_as_double(((long long)seq << 32) | (unsigned int)row);
-}
-
-// candidate ordering of icamax: larger value wins; on equal values the lower row wins.
-__device__ __forceinline__ bool cand_better(double v1, int r1, double v2, int r2) {
-    return (v1 > v2) || (v1 == v2 && r1 < r2);
-}
-// |x| as a pivot key: a NaN wins only at index 0 of the searched range (min_max.rs:221-240)
-__device__ __forceinline__ double pivot_key(double x, bool first) {
-    const double v = fabs(x);
-    return (v != v) ? (first ? __longlong_as_double(0x7ff0000000000000LL) : -1.0) : v;
-}
-
-// Warp-wide winner of (v, r) under cand_better -- larger key, lowest row on ties -- with redux.sync on the
-// key's bit pattern instead of five rounds of three shuffles (keys are |x| >= 0, +inf, or the markers -1 / -2,
-// so `bits + 2` / 1 / 0 is monotone).  Every lane returns the winner; `tag` follows it (e.g. the CTA index).
-__device__ __forceinline__ void warp_best(double& v, int& r, int& tag) {
-    const unsigned FULL = 0xffffffffu;
-    const unsigned long long kb = v >= 0.0 ? (unsigned long long)__double_as_longlong(v) + 2ull : (v == -1.0 ? 1ull : 0ull);
-    const unsigned hi = (unsigned)(kb >> 32), lo = (unsigned)kb;
-    const unsigned mhi = __reduce_max_sync(FULL, hi);
-    const unsigned mlo = __reduce_max_sync(FULL, hi == mhi ? lo : 0u);
-    const bool is_max = hi == mhi && lo == mlo;
-    const int mr = __reduce_min_sync(FULL, is_max ? r : 0x7fffffff);
-    tag = __reduce_min_sync(FULL, (is_max && r == mr) ? tag : 0x7fffffff);
-    const unsigned long long mk = ((unsigned long long)mhi << 32) | mlo;
-    v = mk >= 2ull ? __longlong_as_double((long long)(mk - 2ull)) : (mk == 1ull ? -1.0 : -2.0);
-    r = mr;
-}
 
 __device__ long long g_getf2_prof[16];
 #ifdef NAB_GETF2_PROF   // per-phase cycle counters of CTA 0 / thread 0 (tools/lu_timing.py), off in the product build
@@ -441,9 +395,14 @@ int rowperm_build(cudaStream_t st, const int* sa, const int* sb, size_t K, size_
 
 // Applies a built permutation to columns [0, ncols) of `a` (n rows).  max_touched bounds *count.
 int rowperm_apply(cudaStream_t st, double* a, size_t lda, size_t ncols, size_t max_touched, const void* ws, size_t n) {
-    if (ncols == 0 || max_touched == 0) return NA_OK;
     const int* w = static_cast<const int*>(ws);
-    const int* count = w; const int* dest = w + 64; const int* src = dest + n;
+    return rowperm_apply_lists(st, a, lda, ncols, max_touched, w, w + 64, w + 64 + n);
+}
+
+// The same with explicit lists: row dest[i] of the result is row src[i] of the input, i < *count <= max_touched.
+int rowperm_apply_lists(cudaStream_t st, double* a, size_t lda, size_t ncols, size_t max_touched, const int* count, const int* dest,
+                        const int* src) {
+    if (ncols == 0 || max_touched == 0) return NA_OK;
     const size_t stage_bytes = max_touched * sizeof(double);
     if (stage_bytes <= 200 * 1024) {
         static std::once_flag once;
@@ -578,6 +537,7 @@ int iota_int(cudaStream_t st, int* p, size_t n, int offset) {
 
 }  // namespace nab
 
+#ifdef NAB_DEBUG_HOOKS   // debug build only (see nalgebra_b200/build.py): never part of the product library
 extern "C" __attribute__((visibility("default"))) int na_debug_getf2_prof(long long* out, int reset) {
     cudaMemcpyFromSymbol(out, nab::g_getf2_prof, sizeof(long long) * 16);
     if (reset) { long long z[16] = {0}; cudaMemcpyToSymbol(nab::g_getf2_prof, z, sizeof(z)); }
@@ -589,3 +549,4 @@ extern "C" __attribute__((visibility("default"))) int na_debug_trsm_unit_lower_s
                                                                                    size_t ldb, size_t nrhs, void* stream) {
     return nab::trsm_unit_lower_small(static_cast<cudaStream_t>(stream), n1, l, ldl, b, ldb, nrhs);
 }
+#endif  // NAB_DEBUG_HOOKS

@@ -1,8 +1,8 @@
 """Host-side mirror of nalgebra's interface for the hot path, over the C ABI.
 
 The reference is Rust and this image has no Rust toolchain, so the host side above the C ABI is
-mirrored here (and in ``nalgebra_b200/host/nalgebra_b200.hpp`` for C++ callers; the Rust crate a
-maintainer would add is shown in INTEGRATION.md).  Names, argument meaning and error behaviour
+mirrored here (the Rust crate a maintainer would add is written out under ``rust/`` and explained in
+INTEGRATION.md; it cannot be compiled in this image).  Names, argument meaning and error behaviour
 follow the reference:
 
 * ``gemm(alpha, a, b, beta, c)``      -- ``Matrix::gemm``      src/base/blas.rs:729-746
@@ -45,7 +45,14 @@ def _as_matrix(a, dtype=np.float64) -> np.ndarray:
 
 def _owned(a) -> np.ndarray:
     """``clone_owned``: a column-major copy (VecStorage layout)."""
-    return np.array(a, dtype=np.float64, order="F", copy=True, ndmin=2)
+    a = np.asarray(a, dtype=np.float64)
+    if a.ndim == 0:
+        a = a.reshape(1, 1)
+    elif a.ndim == 1:
+        a = a.reshape(-1, 1)          # a DVector is an n x 1 matrix (NOT 1 x n, which ndmin=2 would give)
+    elif a.ndim != 2:
+        raise ValueError("expected a matrix or a vector")
+    return np.array(a, order="F", copy=True)
 
 
 def kernel_launches() -> int:
@@ -101,6 +108,41 @@ def tr_mul(a, b) -> np.ndarray:
         raise ValueError("Matrix multiplication dimensions mismatch")
     out = np.empty((a.shape[1], b.shape[1]), dtype=np.float64, order="F")
     return gemm(1.0, a.T, b, 0.0, out)
+
+
+def tr_mul_to(a, b, out: np.ndarray) -> np.ndarray:
+    """``a.tr_mul_to(&b, &mut out)`` (ops.rs:757-766): out <- a^T * b."""
+    a = _as_matrix(a); b = _as_matrix(b)
+    if a.shape[0] != b.shape[0]:
+        raise ValueError("Matrix multiplication dimensions mismatch")            # ops.rs:724-729
+    if out.shape != (a.shape[1], b.shape[1]):
+        raise ValueError("Matrix multiplication output dimensions mismatch")      # ops.rs:730-735
+    return gemm(1.0, a.T, b, 0.0, out)
+
+
+# f64 is its own conjugate: the adjoint variants are the transposed ones (ops.rs:687-697, 770-779;
+# blas.rs:827-860).
+ad_mul = tr_mul
+ad_mul_to = tr_mul_to
+gemm_ad = gemm_tr
+
+
+def syrk_lower(alpha: float, a, beta: float, c: np.ndarray) -> np.ndarray:
+    """c <- alpha * a * a^T + beta * c on the LOWER triangle (incl. diagonal) of the square c only; the
+    strict upper triangle is neither read nor written.  The bench SPD recipe of the reference is
+    ``M * M^T`` (benches/linalg/cholesky.rs:3-11); Cholesky::new reads only that triangle."""
+    a = _as_matrix(a)
+    if not isinstance(c, np.ndarray) or c.dtype != np.float64 or c.ndim != 2 or not c.flags.writeable:
+        raise ValueError("c must be a writable float64 matrix")
+    n, k = a.shape
+    if c.shape != (n, n):
+        raise ValueError("syrk: dimensions mismatch for addition.")
+    if c.strides[0] != c.itemsize or (n > 1 and c.strides[1] < n * c.itemsize):
+        raise ValueError("syrk: c must be column-major")
+    rsa, csa = _strides(a)
+    check(_capi.lib().na_dsyrk_lower(n, k, float(alpha), a.ctypes.data, rsa, csa, float(beta), c.ctypes.data,
+                                     max(c.strides[1] // c.itemsize, 1) if n > 1 else max(n, 1)))
+    return c
 
 
 def gemm_f32(alpha: float, a, b, beta: float, c: np.ndarray) -> np.ndarray:
@@ -213,6 +255,7 @@ class Cholesky:
         if b.shape[0] != n:
             raise ValueError("Cholesky solve matrix dimension mismatch.")
         x = _owned(b)
+        assert x.shape[0] == n
         check(_capi.lib().na_cholesky_solve_f64(n, self.chol.ctypes.data, max(n, 1), x.ctypes.data, max(n, 1), x.shape[1]))
         b[...] = x.reshape(b.shape, order="F")
 
@@ -281,6 +324,7 @@ class LU:
         if self.lu.shape[0] != self.lu.shape[1]:
             raise ValueError("LU solve: unable to solve a non-square system.")
         x = _owned(b)
+        assert x.shape[0] == n
         sw = np.ascontiguousarray(self._p.ipiv.reshape(-1))
         st = check(_capi.lib().na_lu_solve_f64(n, self.lu.ctypes.data, max(n, 1), sw.ctypes.data, len(self._p),
                                                x.ctypes.data, max(n, 1), x.shape[1]))
@@ -297,6 +341,23 @@ class LU:
         res = np.asfortranarray(np.eye(self.lu.shape[0]))
         return res if self.solve_mut(res) else None
 
+    def try_inverse_to(self, out: np.ndarray) -> bool:               # :283-297
+        """Writes the inverse into `out` (clobbered, like the reference, when it returns False)."""
+        if self.lu.shape[0] != self.lu.shape[1]:
+            raise ValueError("LU inverse: unable to compute the inverse of a non-square matrix.")
+        if out.shape != self.lu.shape:
+            raise ValueError("LU inverse: mismatched output shape.")
+        out[...] = np.eye(self.lu.shape[0])                           # out.fill_with_identity()
+        return self.solve_mut(out)
+
+    def l_unpack(self) -> np.ndarray:                                 # :156-171
+        """Consumes the decomposition and returns L in its storage (the packed matrix is reused)."""
+        m, n = self.lu.shape
+        mn = min(m, n)
+        res = np.asfortranarray(np.tril(self.lu[:, :mn], -1) + np.eye(m, mn))
+        self.lu = None
+        return res
+
     def determinant(self) -> float:                                   # :301-314
         if self.lu.shape[0] != self.lu.shape[1]:
             raise ValueError("LU determinant: unable to compute the determinant of a non-square matrix.")
@@ -309,6 +370,15 @@ class LU:
         if self.lu.shape[0] != self.lu.shape[1]:
             raise ValueError("LU: unable to test the invertibility of a non-square matrix.")
         return bool(np.all(np.diag(self.lu) != 0.0))
+
+
+def try_invert_to(matrix, out: np.ndarray) -> bool:
+    """``lu::try_invert_to(matrix, out)`` (src/linalg/lu.rs:51-86): LU-factors `matrix` and writes its
+    inverse into `out`; False when a diagonal entry of U is exactly zero."""
+    m = _as_matrix(matrix)
+    if m.shape[0] != m.shape[1]:
+        raise ValueError("LU inversion: unable to invert a rectangular matrix.")   # lu.rs:61-64
+    return LU.new(m).try_inverse_to(out)
 
 
 # ---------------------------------------------------------------------------------------------
@@ -361,6 +431,7 @@ class QR:
         if rhs.shape[0] != m:
             raise ValueError("q_tr_mul: dimension mismatch")
         x = _owned(rhs)
+        assert x.shape[0] == m
         check(_capi.lib().na_qr_q_tr_mul_f64(m, n, self.qr.ctypes.data, max(m, 1), np.ascontiguousarray(self.diag).ctypes.data,
                                              x.ctypes.data, max(m, 1), x.shape[1]))
         rhs[...] = x.reshape(rhs.shape, order="F")
@@ -372,6 +443,7 @@ class QR:
         if self.qr.shape[0] != self.qr.shape[1]:
             raise ValueError("QR solve: unable to solve a non-square system.")
         x = _owned(b)
+        assert x.shape[0] == n
         st = check(_capi.lib().na_qr_solve_f64(n, self.qr.ctypes.data, max(n, 1), np.ascontiguousarray(self.diag).ctypes.data,
                                                x.ctypes.data, max(n, 1), x.shape[1]))
         b[...] = x.reshape(b.shape, order="F")
@@ -426,9 +498,15 @@ def tr_solve_upper_triangular(t, b):
 
 
 def solve_lower_triangular_with_diag(t, b, diag: float):
-    """solve.rs:106-133 with the implicit diagonal `diag` (the reference's LU uses diag = 1)."""
+    """solve.rs:106-133: the diagonal of `t` is never read and taken to be `diag`; ``None`` when
+    diag == 0.  The reference's loop is ``coeff = b[i] / diag; b[i+1..] -= coeff * t[i+1.., i]`` and it
+    never stores ``coeff`` back into ``b[i]``, so what it returns is x' with
+    (I + strict_lower(t) / diag) x' = b  (= diag * the solution of (strict_lower(t) + diag I) y = b).
+    That is a unit-lower solve with the strict lower triangle scaled by 1/diag; the scaling is an
+    O(n^2) host pass, the substitution runs on the GPU (LU's use, diag = 1, needs no scaling)."""
     if diag == 0.0:
         return None
-    if diag != 1.0:
-        raise NotImplementedError("only the unit diagonal the reference's LU uses is accelerated")
-    return _tri_solve(t, b, True, False, True)
+    if diag == 1.0:
+        return _tri_solve(t, b, True, False, True)
+    tm = _as_matrix(t)
+    return _tri_solve(np.tril(tm, -1) / float(diag), b, True, False, True)
