@@ -130,12 +130,67 @@ def run_reference(args):
         "impl": "reference", "metric": "f64_gemm_gflops_n16384", "value": value, "unit": "GFLOP/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": f"DMatrix<f64> GEMM {N_FULL}x{N_FULL}x{N_FULL} (C = A*B), uniform [0,1) inputs",
+        "config": {"workload": f"DMatrix<f64> GEMM {N_FULL}x{N_FULL}x{N_FULL} (C = A*B), uniform [0,1) inputs -- CPU arm timed on a "
+                               f"{n}x{n}x{n} sample of it (rate comparison, not the same problem size)",
                    "sample": sample},
         "cpu_baseline": {"value": value, "unit": "GFLOP/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": "GFLOP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line), flush=True)
+
+
+def kernel_source_hash():
+    """sha256 of the dominant kernel's source file: stamps ncu-derived numbers so that they are dropped when it changes."""
+    import hashlib
+    with open(os.path.join(ROOT, "nalgebra_b200", "csrc", "dgemm.cu"), "rb") as f:
+        return hashlib.sha256(f.read()).hexdigest()
+
+
+def gemm_oracle_spot_check(torch, g2d, N, step, nrows=6, ncols=6):
+    """Rows/columns of this rank's C tile against the oracle (na_oracle_dgemm_mm) on generator-defined inputs.
+    Returns the largest |C_gpu - C_oracle| divided by the north-star bound 4*k*eps*max|A|*max|B|-style row/column
+    norms (||a_i|| * ||b_j||); <= 1 passes."""
+    import numpy as np
+    import oracle as O
+    step(); torch.cuda.synchronize()
+    m_loc, n_loc = g2d.m_loc, g2d.n_loc
+    C = g2d.C.view(n_loc, m_loc)                                # [j, i] = C(row0 + i, col0 + j)
+    ri = np.unique(np.linspace(0, m_loc - 1, nrows).astype(np.int64)); cj = np.unique(np.linspace(0, n_loc - 1, ncols).astype(np.int64))
+    k = np.arange(N, dtype=np.uint64)
+    a_rows = np.stack([O.rand01(1, np.uint64(g2d.row0 + i) + k * np.uint64(N)) for i in ri])          # A(i, k) = rand01(1, i + k*N)
+    b_cols = np.stack([O.rand01(2, k + np.uint64(g2d.col0 + j) * np.uint64(N)) for j in cj], axis=1)  # B(k, j) = rand01(2, k + j*N)
+    ref = np.zeros((len(ri), len(cj)), order="F")
+    O.gemm(1.0, np.asfortranarray(a_rows), np.asfortranarray(b_cols), 0.0, ref, path="mm")
+    got = C[torch.as_tensor(cj)][:, torch.as_tensor(ri)].cpu().numpy().T
+    bound = 4 * N * np.finfo(np.float64).eps * np.linalg.norm(a_rows, axis=1)[:, None] * np.linalg.norm(b_cols, axis=0)[None, :]
+    return {"entries": int(ref.size), "max_abs_err": float(np.abs(got - ref).max()), "max_err_over_bound": float((np.abs(got - ref) / bound).max()),
+            "bound": "4*k*eps*||a_i||*||b_j|| per entry (north_star GEMM gate), oracle = matrixmultiply restatement"}
+
+
+def oracle_factor_baselines(which):
+    """the oracle's (1-thread, unblocked, reference operation order) Cholesky / LU / QR timed at small n
+    and extrapolated with the n^3 law to the benchmark sizes.  `which`: {"cholesky": [n...], "lu": [...], "qr": [...]}."""
+    import numpy as np
+    import oracle as O
+    out = {}
+    for name, sizes in which.items():
+        pts = []
+        for n in sizes:
+            if name == "cholesky":
+                a = O.spd_wellcond(n, 5); fl = n ** 3 / 3.0
+                t0 = time.perf_counter(); O.cholesky(a); dt = time.perf_counter() - t0
+            elif name == "lu":
+                a = O.uniform(n, n, 6); fl = 2.0 * n ** 3 / 3.0
+                t0 = time.perf_counter(); O.lu(a); dt = time.perf_counter() - t0
+            else:
+                a = O.uniform(n, n, 8); fl = 4.0 * n ** 3 / 3.0
+                t0 = time.perf_counter(); O.qr(a); dt = time.perf_counter() - t0
+            pts.append({"n": n, "s": dt, "gflops": fl / dt / 1e9})
+        rate = pts[-1]["gflops"]                            # the largest timed size carries the fit (flops / s is flat in n)
+        out[name] = {"value": rate, "unit": "GFLOP/s", "cores": 1, "kind": "port", "points": pts,
+                     "sample": f"oracle (line-faithful C restatement of nalgebra's unblocked {name}), 1 thread, n = {sizes}; "
+                               f"n^3 law: the full-size run would take flops / {rate:.2f} GFLOP/s"}
+    return out
 
 
 # ------------------------------------------------------------------------------------------------
@@ -145,7 +200,6 @@ def run_gpu(args):
     import torch
     import torch.distributed as dist
     from nalgebra_b200 import _capi
-    from nalgebra_b200.sharding import gemm_piece_class, gemm_piece_order, process_grid
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -164,81 +218,23 @@ def run_gpu(args):
     sm_count = torch.cuda.get_device_properties(dev).multi_processor_count
 
     N = args.n
-    pr, pc = process_grid(ngpus)
-    my_r, my_c = rank // pc, rank % pc
-    m_loc, n_loc = N // pr, N // pc
-    row0, col0 = my_r * m_loc, my_c * n_loc
-
-    # Inputs resident in HBM, block-distributed WITHOUT replication:
-    #   rank (r, c) owns the K-chunk c of the row panel A[r-rows, :]   (m_loc x N/pc, contiguous)
-    #   and the K-chunk r of the column panel B[:, c-cols]             (N/pr x n_loc, contiguous).
-    # A step assembles the panels over NVLink -- ONE in-place all-gather per panel, in the row / column
-    # sub-communicator, both issued up front -- and accumulates C over K-pieces as they become available:
-    # fully local pieces first, then those that only need the (smaller, earlier) B gather, then the rest.
-    # The exchange overlaps the DMMA work; while a gather is outstanding the persistent GEMM leaves 20 SMs
-    # to NCCL's kernels.  (N = 1: no exchange.)  Per-chunk broadcasts (4 + 2 collectives, the later ones
-    # queued behind full-grid GEMM pieces) cost 7.4 ms per step at 8 GPUs.
-    kca, kcb = N // pc, N // pr
-    A = torch.empty(m_loc * N, dtype=torch.float64, device=dev)                       # full row panel, ld = m_loc
-    Bfull = torch.empty(pr * kcb * n_loc, dtype=torch.float64, device=dev)
-    Bc = [Bfull[q * kcb * n_loc:(q + 1) * kcb * n_loc] for q in range(pr)]              # K-chunks of the column panel
-    Cd = torch.empty(m_loc * n_loc, dtype=torch.float64, device=dev)
-    a_chunks = [A[q * kca * m_loc:(q + 1) * kca * m_loc] for q in range(pc)]
-    _capi.check(L.na_fill_uniform_block_dev(a_chunks[my_c].data_ptr(), m_loc, kca, m_loc, 1, row0, my_c * kca, N, stream))
-    _capi.check(L.na_fill_uniform_block_dev(Bc[my_r].data_ptr(), kcb, n_loc, kcb, 2, my_r * kcb, col0, N, stream))
-    row_group = col_group = None
-    if world > 1:
-        for r in range(pr):
-            g = dist.new_group([r * pc + c for c in range(pc)])
-            if r == my_r:
-                row_group = g
-        for c in range(pc):
-            g = dist.new_group([r * pc + c for r in range(pr)])
-            if c == my_c:
-                col_group = g
-    kp = min(kca, kcb, 2048 if world > 1 else N)   # K-piece of one GEMM call (small pieces: only the first runs on a reduced grid)
-    piece_ms = 2.0 * m_loc * n_loc * kp / 36e12 * 1e3
-    n_limited = max(1, int(-(-5.0 // piece_ms)))          # pieces that start within ~5 ms of the step
-    def piece_class(t):      # 0: both operands local, 1: only B foreign, 2: only A foreign, 3: both foreign
-        return gemm_piece_class(t, kp, kca, kcb, my_r, my_c)
-    pieces = gemm_piece_order(N, kp, kca, kcb, my_r, my_c)
-
-    def gemm_piece(t, first):
-        k0 = t * kp
-        qa, qb = k0 // kca, k0 // kcb
-        a_ptr = a_chunks[qa].data_ptr() + 8 * (k0 - qa * kca) * m_loc
-        b_ptr = Bc[qb].data_ptr() + 8 * (k0 - qb * kcb)
-        _capi.check(L.na_dgemm_dev(m_loc, kp, n_loc, 1.0, a_ptr, 1, m_loc, b_ptr, 1, kcb, 0.0 if first else 1.0,
-                                   Cd.data_ptr(), 1, m_loc, stream))
+    # The sharded GEMM is the product's (nalgebra_b200.distributed.Gemm2D): A and B block-distributed WITHOUT replication,
+    # rank (r, c) owns K-chunk c of the row panel A[r-rows, :] and K-chunk r of the column panel B[:, c-cols]; a step stages
+    # the missing K-chunks over NVLink (copy-engine peer copies out of CUDA-IPC mapped buffers, or NCCL all-gathers with
+    # NAB_GEMM_EXCHANGE=collective) while the K-pieces whose operands are local already run.  (N = 1: no exchange.)
+    from nalgebra_b200.distributed import DeviceOps, Gemm2D
+    ops = DeviceOps(dev)
+    g2d = Gemm2D(N, N, N, rank, world, ops, exchange=os.environ.get("NAB_GEMM_EXCHANGE", "auto"))
+    pr, pc, my_r, my_c = g2d.pr, g2d.pc, g2d.my_r, g2d.my_c
+    m_loc, n_loc, row0, col0, kca, kcb = g2d.m_loc, g2d.n_loc, g2d.row0, g2d.col0, g2d.kca, g2d.kcb
+    g2d.fill_uniform(1, 2)
+    A, Bc, Cd, pieces = g2d.A, g2d.b_chunks, g2d.C, g2d.pieces
 
     def step():
-        ha = hb = None
-        if world > 1:
-            if pr > 1:
-                hb = dist.all_gather_into_tensor(Bfull, Bc[my_r], group=col_group, async_op=True)
-            if pc > 1:
-                ha = dist.all_gather_into_tensor(A, a_chunks[my_c], group=row_group, async_op=True)
-        for i, t in enumerate(pieces):
-            cls = piece_class(t)
-            if hb is not None and cls in (1, 3):
-                hb.wait(); hb = None
-            if ha is not None and cls in (2, 3):
-                ha.wait(); ha = None
-            # while a gather can still be in flight (the first ~5 ms of the step: 0.27 - 1.07 GB over NVLink), leave SMs
-            # to NCCL's kernels: the GEMM is persistent, a full grid would make the CTAs that find no SM start late
-            L.na_set_gemm_sm_limit(sm_count - 20 if (i < n_limited and (ha is not None or hb is not None)) else 0)
-            gemm_piece(t, i == 0)
-        if ha is not None:
-            ha.wait()
-        if hb is not None:
-            hb.wait()
-        L.na_set_gemm_sm_limit(0)
+        g2d.multiply()
 
     def step_replicated():
-        """Panels already assembled (what `step` leaves in A / Bc): compute only, one call per B chunk."""
-        for q in range(pr):
-            _capi.check(L.na_dgemm_dev(m_loc, kcb, n_loc, 1.0, A.data_ptr() + 8 * q * kcb * m_loc, 1, m_loc,
-                                       Bc[q].data_ptr(), 1, kcb, 0.0 if q == 0 else 1.0, Cd.data_ptr(), 1, m_loc, stream))
+        g2d.multiply_assembled()
 
     def barrier():
         torch.cuda.synchronize()
@@ -293,13 +289,30 @@ def run_gpu(args):
         step_replicated(); torch.cuda.synchronize()
         exchange_check = float((c_step - Cd).abs().max().item() / max(Cd.abs().max().item(), 1e-300))
         del c_step
+    # Parity of the product against the ORACLE (checker only): a few rows and columns of this rank's C tile are recomputed
+    # on the host with the oracle's matrixmultiply restatement from the generator-defined inputs.
+    oracle_check = None
+    if not args.no_cpu:
+        try:
+            oracle_check = gemm_oracle_spot_check(torch, g2d, N, step)
+            if world > 1:
+                oc = torch.tensor([oracle_check["max_err_over_bound"]], dtype=torch.float64, device=dev)
+                dist.all_reduce(oc, op=dist.ReduceOp.MAX)
+                oracle_check["max_err_over_bound"] = oc.item()
+            oracle_check["ok"] = oracle_check["max_err_over_bound"] <= 1.0
+        except Exception as ex:
+            oracle_check = {"error": repr(ex)}
     achieved = (flops / ngpus) / (kernel_ms * 1e-3) / 1e12
     traffic = None
-    try:   # DRAM bytes of one launch from the committed `ncu --set full` capture (same workload only)
-        with open(os.path.join(ROOT, "profiles", "r01_dgemm_traffic.json")) as f:
+    traffic_note = None
+    try:   # DRAM bytes of one launch from the committed `ncu --set full` capture -- valid only for the kernel source it was taken with
+        with open(os.path.join(ROOT, "profiles", "dgemm_traffic.json")) as f:
             tj = json.load(f)
         if ngpus == 1 and N == N_FULL:
-            traffic = tj["traffic_bytes_per_launch"]
+            if tj.get("kernel_source_sha256") == kernel_source_hash():
+                traffic = tj["traffic_bytes_per_launch"]
+            else:
+                traffic_note = "committed ncu capture is from another version of dgemm.cu: dropped"
     except Exception:
         pass
 
@@ -319,7 +332,7 @@ def run_gpu(args):
             _capi.check(L.na_dgemm(m_loc, N, n_loc, 1.0, hA.data_ptr(), 1, m_loc, hB.data_ptr(), 1, N, 0.0,
                                    hC.data_ptr(), 1, m_loc))
 
-        e2e_steps = max(1, min(args.steps, 3))
+        e2e_steps = max(1, min(args.steps, 10))
         e2e_step()
         barrier()
         t0 = time.perf_counter()
@@ -339,49 +352,76 @@ def run_gpu(args):
     extra = {}
     if ngpus == 1 and not args.no_extra:
         try:
-            extra = factorization_extras(L, _capi, torch, dev, stream, N)
+            extra = factorization_extras(L, _capi, torch, dev, stream, N, cpu=not args.no_cpu, e2e=not args.no_e2e)
         except Exception as ex:  # a missing entry point must not kill the headline line
             extra = {"error": repr(ex)}
 
     if ngpus > 1 and not args.no_extra:
-        # BASELINE configs[2]: Cholesky, 1D block-cyclic over the ranks, panels broadcast with NCCL
+        # BASELINE configs[2] / [3] at scale: 1D block-cyclic Cholesky and LU, panels broadcast with NCCL; every timed
+        # factorization is followed by its residual on the distributed layout (north-star gate 10*n*eps), and the
+        # block-cyclic LU must reproduce the single-GPU pivot sequence at the largest size one GPU holds comfortably.
+        eps = 2.220446049250313e-16
         try:
-            from nalgebra_b200.distributed import ColumnBlockCyclic, DeviceOps, cholesky_block_cyclic
+            from nalgebra_b200.distributed import (ColumnBlockCyclic, cholesky_block_cyclic, cholesky_residual_block_cyclic,
+                                                   lu_block_cyclic, lu_residual_block_cyclic)
             n_bc = {2: 32768, 4: 49152, 8: 65536}.get(ngpus, 16384)
             nb_bc = 1024
-            Abc = ColumnBlockCyclic(n_bc, nb_bc, rank, world, DeviceOps(dev))
+
+            def timed(fn):
+                barrier()
+                t0 = time.perf_counter()
+                r = fn()
+                torch.cuda.synchronize()
+                tt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+                dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+                return r, tt.item()
+
+            Abc = ColumnBlockCyclic(n_bc, nb_bc, rank, world, ops)
             best = None
             for _ in range(2):
                 Abc.fill_spd(5)
-                barrier()
-                t0 = time.perf_counter()
-                st_bc = cholesky_block_cyclic(Abc)
-                torch.cuda.synchronize()
-                tt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
-                dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-                best = tt.item() if best is None else min(best, tt.item())
+                st_bc, dt = timed(lambda: cholesky_block_cyclic(Abc))
+                best = dt if best is None else min(best, dt)
+            res = cholesky_residual_block_cyclic(Abc, 5)
             gf = (n_bc ** 3 / 3.0) / best / 1e9
             extra["cholesky_block_cyclic"] = {"n": n_bc, "nb": nb_bc, "ms": best * 1e3, "gflops": gf, "status": st_bc,
                                               "pct_of_fp64_peak": gf / 1e3 / (FP64_PEAK_TFLOPS * ngpus) * 100,
-                                              "exchange": "NCCL broadcast of each factored panel from its owner"}
-            # BASELINE configs[3] at scale: LU with partial pivoting, same layout, panel + pivot pairs broadcast
-            from nalgebra_b200.distributed import lu_block_cyclic
+                                              "residual": res, "residual_bound": 10 * n_bc * eps, "residual_ok": bool(res <= 10 * n_bc * eps),
+                                              "residual_def": "||A - L L^T||_F / ||A||_F over the lower triangle, evaluated on the distributed layout",
+                                              "exchange": "NCCL broadcast of each factored panel from its owner; status word and pivots stay on the device"}
             best = None
             for _ in range(2):
-                for b in Abc.my_blocks:
-                    _capi.check(L.na_fill_uniform_block_dev(Abc.ptr(0, b), n_bc, Abc.width(b), n_bc, 6, 0, b * nb_bc, n_bc, stream))
-                barrier()
-                t0 = time.perf_counter()
-                pairs = lu_block_cyclic(Abc)
-                torch.cuda.synchronize()
-                tt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
-                dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-                best = tt.item() if best is None else min(best, tt.item())
+                Abc.fill_uniform(6)
+                pairs, dt = timed(lambda: lu_block_cyclic(Abc))
+                best = dt if best is None else min(best, dt)
+            res = lu_residual_block_cyclic(Abc, 6)
             gf = (2.0 * n_bc ** 3 / 3.0) / best / 1e9
             extra["lu_block_cyclic"] = {"n": n_bc, "nb": nb_bc, "ms": best * 1e3, "gflops": gf, "nswaps": len(pairs),
                                         "pct_of_fp64_peak": gf / 1e3 / (FP64_PEAK_TFLOPS * ngpus) * 100,
-                                        "exchange": "NCCL broadcast of each factored panel and its pivot pairs from the owner"}
+                                        "residual": res, "residual_bound": 10 * n_bc * eps, "residual_ok": bool(res <= 10 * n_bc * eps),
+                                        "residual_def": "||P A - L U||_F / ||A||_F evaluated on the distributed layout",
+                                        "exchange": "NCCL broadcast of each factored panel and its pivot vector from the owner"}
             del Abc
+            torch.cuda.empty_cache()
+            # pivots: block-cyclic over all ranks vs one GPU (na_lu_f64_dev) on the same N = 16384 matrix
+            n_p = 16384
+            Ap = ColumnBlockCyclic(n_p, nb_bc, rank, world, ops)
+            Ap.fill_uniform(6)
+            pairs_bc = lu_block_cyclic(Ap)
+            same = None
+            if rank == 0:
+                import ctypes as C
+                A1 = torch.empty(n_p * n_p, dtype=torch.float64, device=dev)
+                _capi.check(L.na_fill_uniform_dev(A1.data_ptr(), n_p, n_p, n_p, 6, stream))
+                sw = (C.c_size_t * (2 * n_p))(); ns = C.c_size_t(0)
+                _capi.check(L.na_lu_f64_dev(n_p, n_p, A1.data_ptr(), n_p, sw, C.addressof(ns), stream))
+                pairs_1 = [(sw[2 * i], sw[2 * i + 1]) for i in range(ns.value)]
+                same = pairs_1 == [tuple(p) for p in pairs_bc]
+                first = next((i for i, (x, y) in enumerate(zip(pairs_1, pairs_bc)) if tuple(x) != tuple(y)), None)
+                extra["lu_block_cyclic"]["pivots_equal_single_gpu"] = {"n": n_p, "equal": bool(same), "npairs": len(pairs_1),
+                                                                       "first_divergence": first}
+                del A1
+            del Ap
         except Exception as ex:
             extra.setdefault("cholesky_block_cyclic", {"error": repr(ex)})
             extra.setdefault("lu_block_cyclic", {"error": repr(ex)})
@@ -403,7 +443,7 @@ def run_gpu(args):
                        "distribution": ("single GPU" if ngpus == 1 else
                                         f"A and B block-distributed without replication; per step each rank receives {pc - 1} A K-chunks "
                                         f"({(pc - 1) * kca * m_loc * 8 / 1e9:.2f} GB) and {pr - 1} B K-chunks ({(pr - 1) * kcb * n_loc * 8 / 1e9:.2f} GB) "
-                                        "over NVLink (one in-place NCCL all-gather per panel in the row / column sub-communicator) overlapped with the K-chunked GEMM"),
+                                        "over NVLink (copy-engine peer copies from CUDA-IPC mapped buffers, or one NCCL all-gather per panel) overlapped with the K-chunked GEMM"),
                        "l2": "inputs (>=1.6 GB per GPU) exceed the 126 MB L2; no explicit flush",
                        "pct_of_fp64_peak": 100.0 * value / 1e3 / (FP64_PEAK_TFLOPS * ngpus)},
             "roofline": {"bound": "tensor", "achieved": achieved, "peak": FP64_PEAK_TFLOPS, "unit": "TFLOP/s",
@@ -415,6 +455,11 @@ def run_gpu(args):
         }
         if exchange_check is not None:
             line["config"]["exchange_check_max_rel_diff"] = exchange_check     # exchanged K-pieced product vs assembled panels
+            line["config"]["exchange"] = g2d.exchange
+        if oracle_check is not None:
+            line["config"]["oracle_spot_check"] = oracle_check
+        if traffic_note:
+            line["roofline"]["traffic_note"] = traffic_note
         if e2e:
             line["e2e"] = e2e
         if cpu:
@@ -422,66 +467,151 @@ def run_gpu(args):
         if extra:
             line["extra"] = extra
         print(json.dumps(line), flush=True)
+    g2d.close()
     if world > 1:
         dist.destroy_process_group()
 
 
-def factorization_extras(L, _capi, torch, dev, stream, N):
-    """Cholesky / LU (/ QR) at the BASELINE sizes on one GPU, device resident, CUDA-event timed."""
+def _roof(flops, ms):
+    tf = flops / (ms * 1e-3) / 1e12
+    return {"bound": "tensor", "achieved": tf, "peak": FP64_PEAK_TFLOPS, "unit": "TFLOP/s", "frac": tf / FP64_PEAK_TFLOPS,
+            "note": "whole factorization against the DMMA roofline its trailing updates run on; panels are latency-bound"}
+
+
+def factorization_extras(L, _capi, torch, dev, stream, N, cpu=True, e2e=True):
+    """BASELINE configs[0], [2], [3], [4] on one GPU: device-resident (CUDA events), end to end through the host-pointer
+    C ABI with pinned buffers, and next to the oracle's CPU time (n^3-extrapolated)."""
     import ctypes as C
     out = {}
+    base = oracle_factor_baselines({"cholesky": [1024, 2048, 4096], "lu": [1024, 2048, 4096], "qr": [1024, 2048]}) if cpu else {}
 
-    if hasattr(L, "na_cholesky_f64_dev"):
-        A = torch.empty(N * N, dtype=torch.float64, device=dev)
-        A0 = torch.empty(N * N, dtype=torch.float64, device=dev)
-        _capi.check(L.na_fill_uniform_dev(A0.data_ptr(), N, N, N, 5, stream))
-        M = A0.view(N, N)
-        M.copy_((M + M.t()) * 0.5); M.diagonal().add_(float(N))       # (B+B^T)/2 + n*I, SURVEY §8(d) Cfg 3 (ii)
-        fail = C.c_size_t(0)
+    def dev_time(fn, reps):
         best = None
-        for _ in range(3):
-            A.copy_(A0); torch.cuda.synchronize()
+        for _ in range(reps):
+            torch.cuda.synchronize()
             e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
-            e0.record()
-            st = _capi.check(L.na_cholesky_f64_dev(N, A.data_ptr(), N, 0, 0.0, C.addressof(fail), stream))
-            e1.record(); torch.cuda.synchronize()
+            e0.record(); r = fn(); e1.record(); torch.cuda.synchronize()
             ms = e0.elapsed_time(e1); best = ms if best is None else min(best, ms)
-        gf = (N ** 3 / 3.0) / (best * 1e-3) / 1e9
-        out["cholesky_n16384"] = {"ms": best, "gflops": gf, "pct_of_fp64_peak": gf / 1e3 / FP64_PEAK_TFLOPS * 100, "status": st}
-        del A, A0
-    if hasattr(L, "na_lu_f64_dev"):
-        A = torch.empty(N * N, dtype=torch.float64, device=dev)
-        A0 = torch.empty(N * N, dtype=torch.float64, device=dev)
-        _capi.check(L.na_fill_uniform_dev(A0.data_ptr(), N, N, N, 6, stream))
-        swaps = (C.c_size_t * (2 * N))(); ns = C.c_size_t(0)
+        return best, r
+
+    def host_time(fn, reps):
         best = None
-        for _ in range(3):
-            A.copy_(A0); torch.cuda.synchronize()
-            e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
-            e0.record()
-            _capi.check(L.na_lu_f64_dev(N, N, A.data_ptr(), N, swaps, C.addressof(ns), stream))
-            e1.record(); torch.cuda.synchronize()
-            ms = e0.elapsed_time(e1); best = ms if best is None else min(best, ms)
-        gf = (2.0 * N ** 3 / 3.0) / (best * 1e-3) / 1e9
-        out["lu_n16384"] = {"ms": best, "gflops": gf, "pct_of_fp64_peak": gf / 1e3 / FP64_PEAK_TFLOPS * 100, "nswaps": ns.value}
-        del A, A0
-    if hasattr(L, "na_qr_f64_dev"):
-        m, n = 65536, 4096
-        A = torch.empty(m * n, dtype=torch.float64, device=dev)
-        A0 = torch.empty(m * n, dtype=torch.float64, device=dev)
-        diag = torch.empty(n, dtype=torch.float64, device=dev)
-        _capi.check(L.na_fill_uniform_dev(A0.data_ptr(), m, n, m, 8, stream))
-        best = None
-        for _ in range(2):
-            A.copy_(A0); torch.cuda.synchronize()
-            e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
-            e0.record()
-            _capi.check(L.na_qr_f64_dev(m, n, A.data_ptr(), m, diag.data_ptr(), stream))
-            e1.record(); torch.cuda.synchronize()
-            ms = e0.elapsed_time(e1); best = ms if best is None else min(best, ms)
-        fl = 2.0 * m * n * n - 2.0 * n ** 3 / 3.0
-        gf = fl / (best * 1e-3) / 1e9
-        out["qr_65536x4096"] = {"ms": best, "gflops": gf, "pct_of_fp64_peak": gf / 1e3 / FP64_PEAK_TFLOPS * 100}
+        for _ in range(reps):
+            torch.cuda.synchronize()
+            t0 = time.perf_counter(); fn(); dt = (time.perf_counter() - t0) * 1e3
+            best = dt if best is None else min(best, dt)
+        return best
+
+    # ---- configs[0]: 1024^3 GEMM, device and host pointers
+    n0 = 1024
+    a = torch.empty(n0 * n0, dtype=torch.float64, device=dev); b = torch.empty_like(a); c = torch.empty_like(a)
+    _capi.check(L.na_fill_uniform_dev(a.data_ptr(), n0, n0, n0, 1, stream)); _capi.check(L.na_fill_uniform_dev(b.data_ptr(), n0, n0, n0, 2, stream))
+    def g0():
+        for _ in range(20):
+            _capi.check(L.na_dgemm_dev(n0, n0, n0, 1.0, a.data_ptr(), 1, n0, b.data_ptr(), 1, n0, 0.0, c.data_ptr(), 1, n0, stream))
+    ms0, _ = dev_time(g0, 3); ms0 /= 20
+    ha = a.cpu().pin_memory(); hb = b.cpu().pin_memory(); hc = torch.empty(n0 * n0, dtype=torch.float64).pin_memory()
+    ms0h = host_time(lambda: _capi.check(L.na_dgemm(n0, n0, n0, 1.0, ha.data_ptr(), 1, n0, hb.data_ptr(), 1, n0, 0.0, hc.data_ptr(), 1, n0)), 5)
+    out["gemm_n1024"] = {"ms": ms0, "gflops": 2.0 * n0 ** 3 / ms0 / 1e6, "pct_of_fp64_peak": 2.0 * n0 ** 3 / ms0 / 1e9 / FP64_PEAK_TFLOPS * 100,
+                         "e2e": {"ms": ms0h, "gflops": 2.0 * n0 ** 3 / ms0h / 1e6, "h2d_bytes": 2 * n0 * n0 * 8, "d2h_bytes": n0 * n0 * 8,
+                                 "api": "na_dgemm (host pointers, pinned)"},
+                         "config": "BASELINE configs[0]: 64 output tiles on 148 SMs, launch-bound"}
+    del a, b, c, ha, hb, hc
+
+    # ---- configs[2]: Cholesky
+    A = torch.empty(N * N, dtype=torch.float64, device=dev)
+    A0 = torch.empty(N * N, dtype=torch.float64, device=dev)
+    _capi.check(L.na_fill_spd_block_dev(A0.data_ptr(), N, N, N, 5, 0, 0, N, stream))       # (B+B^T)/2 + n*I, SURVEY 8(d) Cfg 3 (ii)
+    fail = C.c_size_t(0)
+    def chol():
+        A.copy_(A0)
+        return _capi.check(L.na_cholesky_f64_dev(N, A.data_ptr(), N, 0, 0.0, C.addressof(fail), stream))
+    copy_ms, _ = dev_time(lambda: A.copy_(A0), 3)
+    ms, st = dev_time(chol, 3); ms -= copy_ms
+    fl = N ** 3 / 3.0
+    out["cholesky_n16384"] = {"ms": ms, "gflops": fl / ms / 1e6, "pct_of_fp64_peak": fl / ms / 1e9 / FP64_PEAK_TFLOPS * 100, "status": st,
+                              "roofline": _roof(fl, ms)}
+    if e2e:
+        hA = torch.empty(N * N, dtype=torch.float64).pin_memory(); hA0 = A0.cpu()
+        def chol_h():
+            hA.copy_(hA0)
+            t0 = time.perf_counter()
+            _capi.check(L.na_cholesky_f64(N, hA.data_ptr(), N, 0, 0.0, C.addressof(fail)))
+            return (time.perf_counter() - t0) * 1e3
+        msh = min(chol_h() for _ in range(2))
+        out["cholesky_n16384"]["e2e"] = {"ms": msh, "gflops": fl / msh / 1e6, "h2d_bytes": N * N * 8, "d2h_bytes": N * N * 8,
+                                         "api": "na_cholesky_f64 (host pointer, pinned)"}
+        del hA, hA0
+    if "cholesky" in base:
+        out["cholesky_n16384"]["cpu_baseline"] = base["cholesky"]
+    del A0
+
+    # ---- configs[3]: LU + solve with 64 right-hand sides
+    A0 = torch.empty(N * N, dtype=torch.float64, device=dev)
+    _capi.check(L.na_fill_uniform_dev(A0.data_ptr(), N, N, N, 6, stream))
+    swaps = (C.c_size_t * (2 * N))(); ns = C.c_size_t(0)
+    def lu():
+        A.copy_(A0)
+        _capi.check(L.na_lu_f64_dev(N, N, A.data_ptr(), N, swaps, C.addressof(ns), stream))
+    ms, _ = dev_time(lu, 3); ms -= copy_ms
+    fl = 2.0 * N ** 3 / 3.0
+    out["lu_n16384"] = {"ms": ms, "gflops": fl / ms / 1e6, "pct_of_fp64_peak": fl / ms / 1e9 / FP64_PEAK_TFLOPS * 100, "nswaps": ns.value,
+                        "roofline": _roof(fl, ms)}
+    nrhs = 64
+    B0 = torch.empty(N * nrhs, dtype=torch.float64, device=dev); X = torch.empty_like(B0)
+    _capi.check(L.na_fill_uniform_dev(B0.data_ptr(), N, nrhs, N, 7, stream))
+    def solve():
+        X.copy_(B0)
+        return _capi.check(L.na_lu_solve_f64_dev(N, A.data_ptr(), N, swaps, ns.value, X.data_ptr(), N, nrhs, stream))
+    ms_s, st_s = dev_time(solve, 3)
+    # residual of the solve: ||A x - b||_inf / (||A||_inf ||x||_inf) with our own GEMM
+    R = B0.clone()
+    _capi.check(L.na_dgemm_dev(N, N, nrhs, 1.0, A0.data_ptr(), 1, N, X.data_ptr(), 1, N, -1.0, R.data_ptr(), 1, N, stream))
+    torch.cuda.synchronize()
+    rs = float(R.abs().max() / (A0.view(N, N).abs().sum(dim=0).max() * X.abs().max()))
+    out["lu_n16384"]["solve_64rhs"] = {"ms": ms_s, "gflops": 2.0 * N * N * nrhs / ms_s / 1e6, "status": st_s, "scaled_residual": rs,
+                                       "api": "na_lu_solve_f64_dev (LU::solve_mut, lu.rs:242-260)"}
+    del B0, X, R
+    if e2e:
+        hA = torch.empty(N * N, dtype=torch.float64).pin_memory(); hA0 = A0.cpu()
+        def lu_h():
+            hA.copy_(hA0)
+            t0 = time.perf_counter()
+            _capi.check(L.na_lu_f64(N, N, hA.data_ptr(), N, swaps, C.addressof(ns)))
+            return (time.perf_counter() - t0) * 1e3
+        msh = min(lu_h() for _ in range(2))
+        out["lu_n16384"]["e2e"] = {"ms": msh, "gflops": fl / msh / 1e6, "h2d_bytes": N * N * 8, "d2h_bytes": N * N * 8,
+                                   "api": "na_lu_f64 (host pointer, pinned)"}
+        del hA, hA0
+    if "lu" in base:
+        out["lu_n16384"]["cpu_baseline"] = base["lu"]
+    del A, A0
+
+    # ---- configs[4]: Householder QR, tall-skinny
+    m, n = 65536, 4096
+    A = torch.empty(m * n, dtype=torch.float64, device=dev)
+    A0 = torch.empty(m * n, dtype=torch.float64, device=dev)
+    diag = torch.empty(n, dtype=torch.float64, device=dev)
+    _capi.check(L.na_fill_uniform_dev(A0.data_ptr(), m, n, m, 8, stream))
+    def qr():
+        A.copy_(A0)
+        _capi.check(L.na_qr_f64_dev(m, n, A.data_ptr(), m, diag.data_ptr(), stream))
+    ms, _ = dev_time(qr, 2); ms -= copy_ms
+    fl = 2.0 * m * n * n - 2.0 * n ** 3 / 3.0
+    out["qr_65536x4096"] = {"ms": ms, "gflops": fl / ms / 1e6, "pct_of_fp64_peak": fl / ms / 1e9 / FP64_PEAK_TFLOPS * 100, "roofline": _roof(fl, ms)}
+    if e2e:
+        hA = torch.empty(m * n, dtype=torch.float64).pin_memory(); hA0 = A0.cpu(); hd = torch.empty(n, dtype=torch.float64)
+        def qr_h():
+            hA.copy_(hA0)
+            t0 = time.perf_counter()
+            _capi.check(L.na_qr_f64(m, n, hA.data_ptr(), m, hd.data_ptr()))
+            return (time.perf_counter() - t0) * 1e3
+        msh = min(qr_h() for _ in range(2))
+        out["qr_65536x4096"]["e2e"] = {"ms": msh, "gflops": fl / msh / 1e6, "h2d_bytes": m * n * 8, "d2h_bytes": m * n * 8 + n * 8,
+                                       "api": "na_qr_f64 (host pointer, pinned)"}
+        del hA, hA0
+    if "qr" in base:
+        out["qr_65536x4096"]["cpu_baseline"] = base["qr"]
     return out
 
 

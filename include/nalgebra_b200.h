@@ -73,6 +73,14 @@ NAB_API int na_host_free_pinned(void* ptr);
 NAB_API int na_memcpy_h2d(void* dst, const void* src, size_t bytes);
 NAB_API int na_memcpy_d2h(void* dst, const void* src, size_t bytes);
 NAB_API int na_dev_synchronize(void);
+/* Peer memory for the multi-GPU GEMM (one process per GPU): a buffer from na_dev_malloc is exported with
+ * na_ipc_get_handle (64 opaque bytes, sent to the peer process by any means), mapped by the peer with
+ * na_ipc_open_handle and read with na_memcpy_peer_async -- a copy-engine transfer over NVLink that takes no SM from
+ * the running GEMM.  na_ipc_close_handle unmaps. */
+NAB_API int na_ipc_get_handle(const void* dev_ptr, unsigned char handle[64]);
+NAB_API int na_ipc_open_handle(const unsigned char handle[64], void** dev_ptr);
+NAB_API int na_ipc_close_handle(void* dev_ptr);
+NAB_API int na_memcpy_peer_async(void* dst, const void* src, size_t bytes, void* stream);
 /* Fills a device matrix with the counter-based U[0,1) generator shared with the oracle:
  * a(i,j) = rand01(seed, i + j*nrows)  (the distribution of DMatrix::new_random,
  * src/base/construction.rs:293-299). */
@@ -107,6 +115,24 @@ NAB_API int na_sgemm_dev(size_t m, size_t k, size_t n, float alpha,
                  const float* b, ptrdiff_t rsb, ptrdiff_t csb,
                  float beta, float* c, ptrdiff_t rsc, ptrdiff_t csc, void* stream);
 
+/* C <- alpha * A * A^T + beta * C on the LOWER triangle (incl. diagonal) of the n x n column-major C only (A is
+ * n x k, any strides); the strict upper triangle is neither read nor written.  The product the reference's SPD
+ * recipes form with `&m * m.transpose()` (benches/linalg/cholesky.rs:3-11, src/debug/random_sdp.rs:34-45) and of
+ * which Cholesky::new reads exactly this triangle; SURVEY.md 8(f)1. */
+NAB_API int na_dsyrk_lower(size_t n, size_t k, double alpha, const double* a, ptrdiff_t rsa, ptrdiff_t csa,
+                           double beta, double* c, size_t ldc);
+/* gemv_uninit (src/base/blas_uninit.rs:127-177; Matrix::gemv blas.rs:421-440; gemv_tr = the same call with A's
+ * strides swapped, blas.rs:503-540): y (m entries, stride incy) <- alpha * A (m x n) * x + beta * y.  y is not read
+ * when beta == 0; n == 0 scales or zeroes y (:152-160).  The fallback of gemm_uninit for small / non-Dyn shapes. */
+NAB_API int na_dgemv(size_t m, size_t n, double alpha, const double* a, ptrdiff_t rsa, ptrdiff_t csa,
+                     const double* x, ptrdiff_t incx, double beta, double* y, ptrdiff_t incy);
+NAB_API int na_dgemv_dev(size_t m, size_t n, double alpha, const double* a, ptrdiff_t rsa, ptrdiff_t csa,
+                         const double* x, ptrdiff_t incx, double beta, double* y, ptrdiff_t incy, void* stream);
+/* axcpy (src/base/blas_uninit.rs:86-117): y <- a * x * c + b * y with the reference's rounding order ((a*x)*c, unfused);
+ * y is not read when b == 0.  Device pointers. */
+NAB_API int na_daxcpy_dev(size_t n, double a, const double* x, ptrdiff_t incx, double c, double b, double* y, ptrdiff_t incy,
+                          void* stream);
+
 /* ---- seam 2: Cholesky --------------------------------------------------------------------- */
 /* Cholesky::new / new_with_substitute (src/linalg/cholesky.rs:196-272).  On NA_OK the lower
  * triangle (incl. diagonal) of `a` holds L; the strict upper triangle is never read or written
@@ -115,6 +141,11 @@ NAB_API int na_sgemm_dev(size_t m, size_t k, size_t n, float alpha,
 NAB_API int na_cholesky_f64(size_t n, double* a, size_t lda, int use_sub, double sub, size_t* fail_col);
 /* Synchronises `stream` before returning (the status is a value). */
 NAB_API int na_cholesky_f64_dev(size_t n, double* a, size_t lda, int use_sub, double sub, size_t* fail_col, void* stream);
+/* The same without the status read-back (no host synchronisation for n <= 1024): the first failing column, plus
+ * col_offset, is atomicMin'ed into the DEVICE word *fail_col_dev, which the caller set to UINT64_MAX beforehand
+ * (several panels of a block-cyclic factorization may share one word; it stays UINT64_MAX on success). */
+NAB_API int na_cholesky_f64_dev_async(size_t n, double* a, size_t lda, int use_sub, double sub, uint64_t* fail_col_dev,
+                                      size_t col_offset, void* stream);
 /* Cholesky::solve_mut (cholesky.rs:122-129): b <- (L L^T)^-1 b, b is n x nrhs. */
 NAB_API int na_cholesky_solve_f64(size_t n, const double* l, size_t lda, double* b, size_t ldb, size_t nrhs);
 NAB_API int na_cholesky_solve_f64_dev(size_t n, const double* l, size_t lda, double* b, size_t ldb, size_t nrhs, void* stream);
@@ -130,6 +161,13 @@ NAB_API int na_cholesky_solve_f64_dev(size_t n, const double* l, size_t lda, dou
 NAB_API int na_lu_f64(size_t m, size_t n, double* a, size_t lda, size_t* swaps, size_t* nswaps);
 /* swaps/nswaps are HOST pointers; synchronises `stream` before returning. */
 NAB_API int na_lu_f64_dev(size_t m, size_t n, double* a, size_t lda, size_t* swaps, size_t* nswaps, void* stream);
+/* The same without the pivot read-back: ipiv_dev (DEVICE, min(m, n) int32) receives the 0-based pivot row of every
+ * column (LAPACK's ipiv minus one; ipiv[i] == i where the reference records no swap).  Asynchronous on `stream`. */
+NAB_API int na_lu_f64_dev_async(size_t m, size_t n, double* a, size_t lda, int32_t* ipiv_dev, void* stream);
+/* Applies the row interchanges (row0 + s) <-> (row0 + ipiv_dev[s]), s = 0 .. k-1 in order, to the nrows x ncols
+ * column-major device matrix `a` (PermutationSequence::permute_rows for a pivot vector that never left the device). */
+NAB_API int na_apply_ipiv_f64_dev(size_t nrows, double* a, size_t lda, size_t ncols, const int32_t* ipiv_dev, size_t k,
+                                  size_t row0, void* stream);
 /* LU::solve_mut (lu.rs:242-260): permute rows of b, unit-lower solve, upper solve.
  * NA_SINGULAR == `false` (an exactly-zero U[i,i]); b is then garbage, as in the reference. */
 NAB_API int na_lu_solve_f64(size_t n, const double* lu, size_t lda, const size_t* swaps, size_t nswaps,
@@ -171,6 +209,10 @@ NAB_API int na_tri_solve_f64_dev(int lower, int trans, int unit_diag, size_t n, 
  * force across factorization calls: the blocked drivers combine it with their own panel/bulk split
  * (the smaller limit applies) and never clear it. */
 NAB_API int na_set_gemm_sm_limit(int max_ctas);
+
+/* Tuning / diagnostic switches, never needed for correctness.  Keys: "lu_lookahead" (0: factor with the plain
+ * recursive driver instead of the two-stream look-ahead driver; the tests compare the two paths' pivots). */
+NAB_API int na_set_tuning(const char* key, long value);
 
 /* ---- building blocks of the multi-GPU (1D block-cyclic) factorizations, device pointers ------ */
 /* General triangular solve with many right-hand sides, in place on B (m x n, ldb):

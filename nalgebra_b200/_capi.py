@@ -33,6 +33,10 @@ SIGNATURES = {
     "na_memcpy_h2d": (_int, [_p, _p, _sz]),
     "na_memcpy_d2h": (_int, [_p, _p, _sz]),
     "na_dev_synchronize": (_int, []),
+    "na_ipc_get_handle": (_int, [_p, _p]),
+    "na_ipc_open_handle": (_int, [_p, C.POINTER(_p)]),
+    "na_ipc_close_handle": (_int, [_p]),
+    "na_memcpy_peer_async": (_int, [_p, _p, _sz, _p]),
     "na_fill_uniform_dev": (_int, [_p, _sz, _sz, _sz, _u64, _p]),
     "na_fill_uniform_block_dev": (_int, [_p, _sz, _sz, _sz, _u64, _sz, _sz, _sz, _p]),
     "na_dgemm": (_int, _GEMM64),
@@ -59,6 +63,14 @@ SIGNATURES = {
     "na_permute_rows_f64_dev": (_int, [_sz, _p, _sz, _sz, _p, _sz, _int, _p]),
     "na_dgemm_lower_dev": (_int, _GEMM64[:-2] + [_sz, _p]),
     "na_fill_spd_block_dev": (_int, [_p, _sz, _sz, _sz, _u64, _sz, _sz, _sz, _p]),
+    "na_dsyrk_lower": (_int, [_sz, _sz, _dbl, _p, _pd, _pd, _dbl, _p, _sz]),
+    "na_dgemv": (_int, [_sz, _sz, _dbl, _p, _pd, _pd, _p, _pd, _dbl, _p, _pd]),
+    "na_dgemv_dev": (_int, [_sz, _sz, _dbl, _p, _pd, _pd, _p, _pd, _dbl, _p, _pd, _p]),
+    "na_daxcpy_dev": (_int, [_sz, _dbl, _p, _pd, _dbl, _dbl, _p, _pd, _p]),
+    "na_cholesky_f64_dev_async": (_int, [_sz, _p, _sz, _int, _dbl, _p, _sz, _p]),
+    "na_lu_f64_dev_async": (_int, [_sz, _sz, _p, _sz, _p, _p]),
+    "na_apply_ipiv_f64_dev": (_int, [_sz, _p, _sz, _sz, _p, _sz, _sz, _p]),
+    "na_set_tuning": (_int, [C.c_char_p, C.c_long]),
     "na_tri_solve_f64": (_int, [_int, _int, _int, _sz, _p, _sz, _p, _sz, _sz]),
     "na_tri_solve_f64_dev": (_int, [_int, _int, _int, _sz, _p, _sz, _p, _sz, _sz, _p]),
 }

@@ -263,6 +263,51 @@ int na_set_gemm_sm_limit(int max_ctas) {
     return NA_OK;
 }
 
+// C (n x n, column-major, ldc) <- alpha * A * A^T + beta * C on the LOWER triangle only; the strict upper triangle of
+// the host C is neither read nor written.  Staging: the 128-column block trapezoids [j, n) x [j, j+128) travel each
+// way, so the strict upper part only round-trips inside the 128 x 128 diagonal blocks (uploaded first, so what comes
+// back there is what was sent).
+int na_dsyrk_lower(size_t n, size_t k, double alpha, const double* a, ptrdiff_t rsa, ptrdiff_t csa, double beta, double* c, size_t ldc) {
+    NAB_TRY(ensure_init());
+    if (n == 0) return NA_OK;
+    if (!c || ldc < n || (k && !a)) { set_error("syrk: bad arguments"); return NA_EINVAL; }
+    std::lock_guard<std::mutex> lock(host_api_mutex());
+    cudaStream_t s = ctx().stream;
+    Staged sa;
+    Scratch dc;
+    const size_t ldd = round_up(n, 2), B = 128;
+    NAB_TRY(dc.alloc(ldd * n * sizeof(double), s));
+    for (size_t j = 0; j < n; j += B) {           // diagonal blocks always (their strict upper part must come back unchanged)
+        const size_t w = std::min(B, n - j), rows = beta != 0.0 ? n - j : w;
+        NAB_CUDA(cudaMemcpy2DAsync(dc.as<double>() + j + j * ldd, ldd * 8, c + j + j * ldc, ldc * 8, rows * 8, w, cudaMemcpyHostToDevice, s));
+    }
+    if (k == 0) {
+        for (size_t j = 0; j < n; j += B) {       // C <- beta * C (or zeros) on the lower trapezoids, blas_uninit.rs:258-269
+            const size_t w = std::min(B, n - j);
+            if (n - j > w) NAB_TRY(scale_strided(s, dc.as<double>() + (j + w) + j * ldd, 1, (ptrdiff_t)ldd, n - j - w, w, beta));
+            NAB_TRY(scale_lower_block(s, dc.as<double>() + j + j * ldd, ldd, w, beta));
+        }
+    } else {
+        NAB_TRY(stage_in(s, sa, a, rsa, csa, n, k, true));
+        NAB_TRY(dgemm_device(s, true, n, k, n, alpha, sa.buf.as<double>(), sa.rs, sa.cs, sa.buf.as<double>(), sa.cs, sa.rs, beta,
+                             dc.as<double>(), 1, (ptrdiff_t)ldd));
+    }
+    for (size_t j = 0; j < n; j += B) {
+        const size_t w = std::min(B, n - j);
+        NAB_CUDA(cudaMemcpy2DAsync(c + j + j * ldc, ldc * 8, dc.as<double>() + j + j * ldd, ldd * 8, (n - j) * 8, w, cudaMemcpyDeviceToHost, s));
+    }
+    NAB_CUDA(cudaStreamSynchronize(s));
+    return NA_OK;
+}
+
+// Tuning / diagnostic switches (not needed for correctness).  Keys: "lu_lookahead" (0 = plain recursive path).
+int na_set_tuning(const char* key, long value) {
+    if (!key) { set_error("na_set_tuning: null key"); return NA_EINVAL; }
+    if (strcmp(key, "lu_lookahead") == 0) { lu_set_lookahead(value); return NA_OK; }
+    set_error("na_set_tuning: unknown key '%s'", key);
+    return NA_EINVAL;
+}
+
 int na_fill_spd_block_dev(double* a, size_t nrows, size_t ncols, size_t lda, uint64_t seed,
                           size_t row0, size_t col0, size_t n, void* stream) {
     NAB_TRY(ensure_init());

@@ -158,6 +158,32 @@ int na_memcpy_d2h(void* dst, const void* src, size_t bytes) {
     NAB_CUDA(cudaMemcpy(dst, src, bytes, cudaMemcpyDeviceToHost));
     return NA_OK;
 }
+// ---- peer memory (multi-GPU GEMM: panels staged over NVLink by the copy engines) ------------------------------
+int na_ipc_get_handle(const void* dev_ptr, unsigned char handle[64]) {
+    NAB_TRY(ensure_init());
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t is 64 bytes");
+    cudaIpcMemHandle_t h;
+    NAB_CUDA(cudaIpcGetMemHandle(&h, const_cast<void*>(dev_ptr)));
+    memcpy(handle, &h, 64);
+    return NA_OK;
+}
+int na_ipc_open_handle(const unsigned char handle[64], void** dev_ptr) {
+    NAB_TRY(ensure_init());
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle, 64);
+    NAB_CUDA(cudaIpcOpenMemHandle(dev_ptr, h, cudaIpcMemLazyEnablePeerAccess));
+    return NA_OK;
+}
+int na_ipc_close_handle(void* dev_ptr) {
+    NAB_CUDA(cudaIpcCloseMemHandle(dev_ptr));
+    return NA_OK;
+}
+int na_memcpy_peer_async(void* dst, const void* src, size_t bytes, void* stream) {
+    NAB_TRY(ensure_init());
+    NAB_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDefault, static_cast<cudaStream_t>(stream)));
+    return NA_OK;
+}
+
 int na_dev_synchronize(void) {
     NAB_TRY(ensure_init());
     NAB_CUDA(cudaDeviceSynchronize());

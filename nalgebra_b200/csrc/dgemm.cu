@@ -375,6 +375,20 @@ __global__ void scale_strided_kernel(double* __restrict__ c, long long rs, long 
     }
 }
 
+// lower triangle (incl. diagonal) of a w x w block: C <- beta * C, zeros when beta == 0 (C not read)
+__global__ void scale_lower_block_kernel(double* __restrict__ c, long long ldc, int w, double beta) {
+    for (int idx = threadIdx.x; idx < w * w; idx += blockDim.x) {
+        const int r = idx % w, col = idx / w;
+        if (r >= col) { double* p = c + r + col * ldc; *p = (beta == 0.0) ? 0.0 : (*p * beta); }
+    }
+}
+int scale_lower_block(cudaStream_t s, double* c, size_t ldc, size_t w, double beta) {
+    if (w == 0) return NA_OK;
+    scale_lower_block_kernel<<<1, 256, 0, s>>>(c, (long long)ldc, (int)w, beta);
+    NAB_LAUNCH_CHECK();
+    return NA_OK;
+}
+
 __device__ __forceinline__ uint64_t mix64(uint64_t z) {
     z ^= z >> 30; z *= 0xBF58476D1CE4E5B9ULL;
     z ^= z >> 27; z *= 0x94D049BB133111EBULL;

@@ -82,13 +82,14 @@ struct CholCtx {
     int use_sub; double sub;
     double* inv;                      // [n/128][128*128] inverses of L's diagonal blocks
     unsigned long long* fail;         // device: first failing column (init ~0)
+    size_t col_offset = 0;            // added to the reported failing column (block-cyclic drivers: global column)
 };
 
 static int chol_rec(const CholCtx& c, size_t j0, size_t n) {
     if (n == 0) return NA_OK;
     double* ajj = c.a + j0 + j0 * c.lda;
     if (n <= IBs) {
-        return potf2(c.s, ajj, c.lda, (int)n, c.use_sub, c.sub, j0, c.fail, c.inv + (j0 / IBs) * IBs * IBs);
+        return potf2(c.s, ajj, c.lda, (int)n, c.use_sub, c.sub, j0 + c.col_offset, c.fail, c.inv + (j0 / IBs) * IBs * IBs);
     }
     const size_t n1 = round_up(n / 2, IBs), n2 = n - n1;
     NAB_TRY(chol_rec(c, j0, n1));
@@ -139,7 +140,7 @@ static int chol_panel(const CholCtx& c, cudaStream_t sp, size_t n, size_t j, siz
         const size_t cc = j + i, w = std::min(IBs, jb - i);
         double* acc = c.a + cc + cc * c.lda;
         double* inv = c.inv + (cc / IBs) * IBs * IBs;
-        NAB_TRY(potf2(sp, acc, c.lda, (int)w, c.use_sub, c.sub, cc, c.fail, inv));
+        NAB_TRY(potf2(sp, acc, c.lda, (int)w, c.use_sub, c.sub, cc + c.col_offset, c.fail, inv));
         const size_t r = n - cc - w;
         if (r == 0) continue;
         double* a21 = acc + w;
@@ -160,12 +161,10 @@ static int chol_panel(const CholCtx& c, cudaStream_t sp, size_t n, size_t j, siz
 }
 
 static int chol_lookahead(const CholCtx& c, size_t n) {
-    cudaStream_t sp = c.s, su = nullptr;
-    cudaEvent_t ev_p = nullptr, ev_u = nullptr, ev_d = nullptr;
-    NAB_CUDA(cudaStreamCreateWithFlags(&su, cudaStreamNonBlocking));
-    NAB_CUDA(cudaEventCreateWithFlags(&ev_p, cudaEventDisableTiming));
-    NAB_CUDA(cudaEventCreateWithFlags(&ev_u, cudaEventDisableTiming));
-    NAB_CUDA(cudaEventCreateWithFlags(&ev_d, cudaEventDisableTiming));
+    StreamGuard su_g;
+    EventGuard ev_p, ev_u, ev_d;
+    NAB_TRY(su_g.create()); NAB_TRY(ev_p.create()); NAB_TRY(ev_u.create()); NAB_TRY(ev_d.create());
+    const cudaStream_t sp = c.s, su = su_g.s;
     Scratch tmp;
     const size_t ldt = round_up(n, 2);
     int st = tmp.alloc(ldt * IBs * sizeof(double), sp);
@@ -251,20 +250,30 @@ static int chol_lookahead(const CholCtx& c, size_t n) {
     if (bulk_pending) cudaStreamWaitEvent(sp, ev_u, 0);
     cudaStreamSynchronize(su);
     tr.dump();
-    cudaEventDestroy(ev_p); cudaEventDestroy(ev_u); cudaEventDestroy(ev_d); cudaStreamDestroy(su);
     return st;
+}
+
+// Everything but the status read-back: enqueues the factorization on `s`; the first failing column (offset by
+// col_offset) is atomicMin'ed into the device word *fail_dev, which the caller initialised to ~0.
+int cholesky_device_async(cudaStream_t s, size_t n, double* a, size_t lda, int use_sub, double sub,
+                          unsigned long long* fail_dev, size_t col_offset) {
+    if (n == 0) return NA_OK;
+    if (lda < n) { set_error("cholesky: lda < n"); return NA_EINVAL; }
+    Scratch inv;
+    NAB_TRY(inv.alloc(ceil_div(n, IBs) * IBs * IBs * sizeof(double), s));
+    CholCtx c{s, a, lda, use_sub, sub, inv.as<double>(), fail_dev, col_offset};
+    if (n <= 2 * CHOL_NB) NAB_TRY(chol_rec(c, 0, n));
+    else NAB_TRY(chol_lookahead(c, n));
+    return NA_OK;
 }
 
 int cholesky_device(cudaStream_t s, size_t n, double* a, size_t lda, int use_sub, double sub, size_t* fail_col) {
     if (n == 0) return NA_OK;
     if (lda < n) { set_error("cholesky: lda < n"); return NA_EINVAL; }
-    Scratch inv, flag;
-    NAB_TRY(inv.alloc(ceil_div(n, IBs) * IBs * IBs * sizeof(double), s));
+    Scratch flag;
     NAB_TRY(flag.alloc(sizeof(unsigned long long), s));
     NAB_CUDA(cudaMemsetAsync(flag.p, 0xff, sizeof(unsigned long long), s));
-    CholCtx c{s, a, lda, use_sub, sub, inv.as<double>(), flag.as<unsigned long long>()};
-    if (n <= 2 * CHOL_NB) NAB_TRY(chol_rec(c, 0, n));
-    else NAB_TRY(chol_lookahead(c, n));
+    NAB_TRY(cholesky_device_async(s, n, a, lda, use_sub, sub, flag.as<unsigned long long>(), 0));
     unsigned long long h = 0;
     NAB_CUDA(cudaMemcpyAsync(&h, flag.p, sizeof(h), cudaMemcpyDeviceToHost, s));
     NAB_CUDA(cudaStreamSynchronize(s));
@@ -310,6 +319,14 @@ extern "C" {
 int na_cholesky_f64_dev(size_t n, double* a, size_t lda, int use_sub, double sub, size_t* fail_col, void* stream) {
     NAB_TRY(ensure_init());
     return cholesky_device(static_cast<cudaStream_t>(stream), n, a, lda, use_sub, sub, fail_col);
+}
+
+int na_cholesky_f64_dev_async(size_t n, double* a, size_t lda, int use_sub, double sub, uint64_t* fail_col_dev, size_t col_offset,
+                              void* stream) {
+    NAB_TRY(ensure_init());
+    if (!fail_col_dev) { set_error("cholesky (async): fail_col_dev is null"); return NA_EINVAL; }
+    return cholesky_device_async(static_cast<cudaStream_t>(stream), n, a, lda, use_sub, sub,
+                                 reinterpret_cast<unsigned long long*>(fail_col_dev), col_offset);
 }
 
 int na_cholesky_f64(size_t n, double* a, size_t lda, int use_sub, double sub, size_t* fail_col) {
@@ -377,6 +394,9 @@ int na_trsm_f64_dev(int side_right, int lower, int trans, int unit_diag, size_t 
     const size_t nt = side_right ? n : m;
     if (!t || !b || ldt < nt || ldb < m) { set_error("trsm: bad arguments"); return NA_EINVAL; }
     if (!side_right) {
+        // unit-lower, untransposed, at most 128 rows: the direct substitution kernel of the LU panels (one launch,
+        // no inverse blocks)
+        if (lower && !trans && unit_diag && m <= 128) return trsm_unit_lower_small(s, m, t, ldt, b, ldb, n);
         const bool eff_lower = (lower != 0) != (trans != 0);
         const ptrdiff_t rsm = trans ? (ptrdiff_t)ldt : 1, csm = trans ? 1 : (ptrdiff_t)ldt;
         return trsm_left(s, eff_lower, unit_diag != 0, m, t, rsm, csm, nullptr, nullptr, b, 1, (ptrdiff_t)ldb, n);

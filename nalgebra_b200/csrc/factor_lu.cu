@@ -310,30 +310,32 @@ static size_t lu_leaf_width(size_t M) {
     return 16;
 }
 
-// swaps/nswaps: HOST outputs (PermutationSequence pairs).
-int lu_device(cudaStream_t s, size_t M, size_t N, double* a, size_t lda, size_t* swaps, size_t* nswaps) {
+static long g_lu_lookahead = 1;      // na_set_tuning("lu_lookahead", 0) forces the plain recursive / flat path
+void lu_set_lookahead(long v) { g_lu_lookahead = v; }
+
+// Everything but the pivot read-back: enqueues the factorization on `s`; ipiv_dev (device, min(M, N) ints) receives
+// the 0-based pivot row of every column (LAPACK ipiv minus one; ipiv[i] == i where no swap happened).
+int lu_device_async(cudaStream_t s, size_t M, size_t N, double* a, size_t lda, int* ipiv_dev) {
     const size_t mn = std::min(M, N);
-    if (nswaps) *nswaps = 0;
     if (mn == 0) return NA_OK;
     if (lda < M) { set_error("lu: lda < m"); return NA_EINVAL; }
     if (M > 0x7fffff00ull || N > 0x7fffff00ull) { set_error("lu: dimension exceeds 2^31"); return NA_EINVAL; }
-    Scratch ipiv, iota, wsg, wsp;
-    NAB_TRY(ipiv.alloc(mn * sizeof(int), s));
+    Scratch iota, wsg, wsp;
     NAB_TRY(iota.alloc(mn * sizeof(int), s));
     NAB_TRY(wsg.alloc(getf2_workspace_bytes(), s));
     NAB_CUDA(cudaMemsetAsync(wsg.p, 0, getf2_workspace_bytes(), s));
     int seq_state = 0;
     NAB_TRY(wsp.alloc(rowperm_workspace_bytes(M), s));
     NAB_TRY(iota_int(s, iota.as<int>(), mn, 0));
-    NAB_TRY(iota_int(s, ipiv.as<int>(), mn, 0));
-    LuCtx c{s, a, lda, M, lu_leaf_width(M), ipiv.as<int>(), iota.as<int>(), wsg.p, wsp.p, &seq_state};
+    NAB_TRY(iota_int(s, ipiv_dev, mn, 0));
+    LuCtx c{s, a, lda, M, lu_leaf_width(M), ipiv_dev, iota.as<int>(), wsg.p, wsp.p, &seq_state};
     Scratch lists;
     int leaf_seq = 0;
     c.max_leaves = ceil_div(mn, (size_t)16) + 8;
     NAB_TRY(lists.alloc(c.max_leaves * kRegListInts * sizeof(int), s));
     NAB_CUDA(cudaMemsetAsync(lists.p, 0, c.max_leaves * kRegListInts * sizeof(int), s));
     c.lists = lists.as<int>(); c.leaf_seq = &leaf_seq;
-    const bool lookahead = mn >= 4 * LU_NB && M <= 20000;
+    const bool lookahead = g_lu_lookahead != 0 && mn >= 4 * LU_NB && M <= 20000;
     if (lookahead) {
         static const size_t la_leaf = [] { const char* e = getenv("NAB_LU_LEAF"); const int v = e ? atoi(e) : 64; return (size_t)((v == 16 || v == 32) ? v : 64); }();
         c.W = la_leaf;
@@ -346,6 +348,17 @@ int lu_device(cudaStream_t s, size_t M, size_t N, double* a, size_t lda, size_t*
         NAB_TRY(lu_apply_swaps(c, 0, mn, ar, N - mn));
         NAB_TRY(trsm_left(s, true, true, mn, a, 1, (ptrdiff_t)lda, nullptr, nullptr, ar, 1, (ptrdiff_t)lda, N - mn));
     }
+    return NA_OK;
+}
+
+// swaps/nswaps: HOST outputs (PermutationSequence pairs).
+int lu_device(cudaStream_t s, size_t M, size_t N, double* a, size_t lda, size_t* swaps, size_t* nswaps) {
+    const size_t mn = std::min(M, N);
+    if (nswaps) *nswaps = 0;
+    if (mn == 0) return NA_OK;
+    Scratch ipiv;
+    NAB_TRY(ipiv.alloc(mn * sizeof(int), s));
+    NAB_TRY(lu_device_async(s, M, N, a, lda, ipiv.as<int>()));
     std::vector<int> h(mn);
     NAB_CUDA(cudaMemcpyAsync(h.data(), ipiv.p, mn * sizeof(int), cudaMemcpyDeviceToHost, s));
     NAB_CUDA(cudaStreamSynchronize(s));
@@ -400,6 +413,24 @@ extern "C" {
 int na_lu_f64_dev(size_t m, size_t n, double* a, size_t lda, size_t* swaps, size_t* nswaps, void* stream) {
     NAB_TRY(ensure_init());
     return lu_device(static_cast<cudaStream_t>(stream), m, n, a, lda, swaps, nswaps);
+}
+
+int na_lu_f64_dev_async(size_t m, size_t n, double* a, size_t lda, int32_t* ipiv_dev, void* stream) {
+    NAB_TRY(ensure_init());
+    if (std::min(m, n) && (!a || !ipiv_dev)) { set_error("lu (async): null pointer"); return NA_EINVAL; }
+    return lu_device_async(static_cast<cudaStream_t>(stream), m, n, a, lda, ipiv_dev);
+}
+
+int na_apply_ipiv_f64_dev(size_t nrows, double* a, size_t lda, size_t ncols, const int32_t* ipiv_dev, size_t k, size_t row0,
+                          void* stream) {
+    NAB_TRY(ensure_init());
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    if (nrows == 0 || ncols == 0 || k == 0) return NA_OK;
+    if (!a || !ipiv_dev || lda < nrows || nrows > 0x7fffff00ull || row0 + k > nrows) { set_error("apply_ipiv: bad arguments"); return NA_EINVAL; }
+    Scratch wsp;
+    NAB_TRY(wsp.alloc(rowperm_workspace_bytes(nrows), s));
+    NAB_TRY(rowperm_build_ipiv(s, ipiv_dev, k, (int)row0, nrows, wsp.p));
+    return rowperm_apply(s, a, lda, ncols, std::min(2 * k, nrows), wsp.p, nrows);
 }
 
 int na_lu_f64(size_t m, size_t n, double* a, size_t lda, size_t* swaps, size_t* nswaps) {

@@ -18,6 +18,7 @@ void set_user_gemm_sm_limit(int limit);   // the caller's reservation (na_set_ge
 constexpr double kSmFlops = 0.22e12;
 int pack_strided(cudaStream_t s, double* dst, size_t ldd, const double* src, ptrdiff_t rs, ptrdiff_t cs, size_t rows, size_t cols);
 int scatter_strided(cudaStream_t s, double* dst, ptrdiff_t rs, ptrdiff_t cs, const double* src, size_t lds, size_t rows, size_t cols);
+int scale_lower_block(cudaStream_t s, double* c, size_t ldc, size_t w, double beta);
 int scale_strided(cudaStream_t s, double* c, ptrdiff_t rs, ptrdiff_t cs, size_t rows, size_t cols, double beta);
 int fill_uniform(cudaStream_t s, double* a, size_t nrows, size_t ncols, size_t lda, uint64_t seed,
                  size_t row0, size_t col0, size_t global_rows);
@@ -52,6 +53,7 @@ int rowperm_apply_lists(cudaStream_t st, double* a, size_t lda, size_t ncols, si
                         const int* src);
 size_t rowperm_workspace_bytes(size_t n);
 int rowperm_build(cudaStream_t st, const int* sa, const int* sb, size_t K, size_t stride, size_t n, void* ws);
+int rowperm_build_ipiv(cudaStream_t st, const int* ipiv, size_t K, int row0, size_t n, void* ws);
 int rowperm_apply(cudaStream_t st, double* a, size_t lda, size_t ncols, size_t max_touched, const void* ws, size_t n);
 int iota_int(cudaStream_t st, int* p, size_t n, int offset);
 // B (n1 x nrhs, column-major) <- L^-1 B, L = unit lower triangle of l (n1 <= 128); one launch, no inverse blocks
@@ -79,6 +81,7 @@ int scale_signs(cudaStream_t st, double* b, size_t ldb, size_t rows, size_t cols
 // diagonal blocks (trtri_blocks layout); computed internally when null.
 int trsm_left(cudaStream_t s, bool eff_lower, bool unit, size_t n, const double* m, ptrdiff_t rsm, ptrdiff_t csm,
               const double* diag_abs, const double* inv_blocks, double* b, ptrdiff_t rsb, ptrdiff_t csb, size_t nrhs);
+void lu_set_lookahead(long v);
 int cholesky_device(cudaStream_t s, size_t n, double* a, size_t lda, int use_sub, double sub, size_t* fail_col);
 int upload_matrix(cudaStream_t s, Scratch& buf, size_t& ldd, const double* h, size_t ldh, size_t rows, size_t cols);
 int download_matrix(cudaStream_t s, double* h, size_t ldh, const double* d, size_t ldd, size_t rows, size_t cols);

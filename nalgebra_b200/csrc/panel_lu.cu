@@ -296,8 +296,10 @@ int getf2_panel(cudaStream_t st, double* a_panel, size_t lda, size_t m, size_t w
 // row src[i] of the input".  One CTA; the arrangement lives in shared memory (int32, n <= 51200)
 // or in a global scratch array for taller matrices.
 // ------------------------------------------------------------------------------------------------
+// sa == nullptr: the swap sequence is (row0 + s, row0 + sb[s]) -- a panel-relative LAPACK-style ipiv (0-based) whose
+// panel starts at row `row0`; otherwise the pairs (sa[s * stride], sb[s * stride]) and row0 = 0.
 __global__ void __launch_bounds__(1024, 1)
-perm_from_swaps_kernel(const int* __restrict__ sa, const int* __restrict__ sb, int K, int sa_stride, int n,
+perm_from_swaps_kernel(const int* __restrict__ sa, const int* __restrict__ sb, int K, int sa_stride, int row0, int n,
                        int* __restrict__ gperm, int use_global, int swaps_in_smem,
                        int* __restrict__ dest, int* __restrict__ src, int* __restrict__ count) {
     extern __shared__ int sperm[];
@@ -310,7 +312,7 @@ perm_from_swaps_kernel(const int* __restrict__ sa, const int* __restrict__ sb, i
     __shared__ int s_count;
     if (tid == 0) s_count = 0;
     for (int s = tid; s < K; s += nt) {
-        const int x = sa[(size_t)s * sa_stride], y = sb[(size_t)s * sa_stride];
+        const int x = sa ? sa[(size_t)s * sa_stride] : row0 + s, y = row0 + sb[(size_t)s * sa_stride];
         if (swaps_in_smem) { sx[s] = x; sy[s] = y; }
         perm[x] = x; perm[y] = y;                  // racing writers store the same value
     }
@@ -323,7 +325,7 @@ perm_from_swaps_kernel(const int* __restrict__ sa, const int* __restrict__ sb, i
             }
         } else {
             for (int s = 0; s < K; ++s) {
-                const int x = sa[(size_t)s * sa_stride], y = sb[(size_t)s * sa_stride];
+                const int x = sa ? sa[(size_t)s * sa_stride] : row0 + s, y = row0 + sb[(size_t)s * sa_stride];
                 if (x != y) { const int t = perm[x]; perm[x] = perm[y]; perm[y] = t; }
             }
         }
@@ -333,7 +335,8 @@ perm_from_swaps_kernel(const int* __restrict__ sa, const int* __restrict__ sb, i
     // resets its entry to the identity, so later claimants see an untouched row
     for (int s = tid; s < 2 * K; s += nt) {
         const int h = s >= K ? 1 : 0, si = s - h * K;
-        const int r = swaps_in_smem ? (h ? sy[si] : sx[si]) : (h ? sb[(size_t)si * sa_stride] : sa[(size_t)si * sa_stride]);
+        const int r = swaps_in_smem ? (h ? sy[si] : sx[si])
+                                    : (h ? row0 + sb[(size_t)si * sa_stride] : (sa ? sa[(size_t)si * sa_stride] : row0 + si));
         const int v = atomicExch(&perm[r], r);
         if (v != r) { const int i = atomicAdd(&s_count, 1); dest[i] = r; src[i] = v; }
     }
@@ -377,7 +380,15 @@ __global__ void permute_rows_scatter_kernel(double* __restrict__ a, long long ld
 size_t rowperm_workspace_bytes(size_t n) { return (3 * n + 64) * sizeof(int); }
 
 // Builds the permutation equivalent to the swap sequence (sa[s*stride], sb[s*stride]), s < K, over rows [0, n).
+static int rowperm_build_impl(cudaStream_t st, const int* sa, const int* sb, size_t K, size_t stride, int row0, size_t n, void* ws);
 int rowperm_build(cudaStream_t st, const int* sa, const int* sb, size_t K, size_t stride, size_t n, void* ws) {
+    return rowperm_build_impl(st, sa, sb, K, stride, 0, n, ws);
+}
+// The permutation of the swap sequence (row0 + s, row0 + ipiv[s]), s < K (ipiv: device, 0-based, relative to row0).
+int rowperm_build_ipiv(cudaStream_t st, const int* ipiv, size_t K, int row0, size_t n, void* ws) {
+    return rowperm_build_impl(st, nullptr, ipiv, K, 1, row0, n, ws);
+}
+static int rowperm_build_impl(cudaStream_t st, const int* sa, const int* sb, size_t K, size_t stride, int row0, size_t n, void* ws) {
     int* w = static_cast<int*>(ws);
     int* count = w; int* dest = w + 64; int* src = dest + n; int* gperm = src + n;
     const size_t budget = 200 * 1024;
@@ -387,7 +398,7 @@ int rowperm_build(cudaStream_t st, const int* sa, const int* sb, size_t K, size_
     const size_t smem = perm_bytes + (swaps_in_smem ? 2 * K * sizeof(int) : 0);
     static std::once_flag once;
     std::call_once(once, [] { cudaFuncSetAttribute(perm_from_swaps_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); });
-    perm_from_swaps_kernel<<<1, 1024, smem, st>>>(sa, sb, (int)K, (int)stride, (int)n, gperm, use_global ? 1 : 0, swaps_in_smem ? 1 : 0,
+    perm_from_swaps_kernel<<<1, 1024, smem, st>>>(sa, sb, (int)K, (int)stride, row0, (int)n, gperm, use_global ? 1 : 0, swaps_in_smem ? 1 : 0,
                                                    dest, src, count);
     NAB_LAUNCH_CHECK();
     return NA_OK;

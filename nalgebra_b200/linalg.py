@@ -127,6 +127,30 @@ ad_mul_to = tr_mul_to
 gemm_ad = gemm_tr
 
 
+def gemv(alpha: float, a, x, beta: float, y: np.ndarray) -> np.ndarray:
+    """``y.gemv(alpha, &a, &x, beta)``: y <- alpha*a*x + beta*y in place (blas.rs:421-440 -> gemv_uninit,
+    blas_uninit.rs:127-177); y is not read when beta == 0."""
+    a = _as_matrix(a)
+    x = np.asarray(x, dtype=np.float64)
+    if x.ndim != 1 or y.ndim != 1 or y.dtype != np.float64 or not y.flags.writeable:
+        raise ValueError("gemv: x and y must be float64 vectors (y writable)")
+    m, n = a.shape
+    if x.shape[0] != n or y.shape[0] != m:
+        raise ValueError("Gemv: dimensions mismatch.")                          # blas_uninit.rs:143-150
+    rsa, csa = _strides(a)
+    check(_capi.lib().na_dgemv(m, n, float(alpha), a.ctypes.data, rsa, csa, x.ctypes.data, x.strides[0] // 8 if n else 1,
+                               float(beta), y.ctypes.data, y.strides[0] // 8 if m else 1))
+    return y
+
+
+def gemv_tr(alpha: float, a, x, beta: float, y: np.ndarray) -> np.ndarray:
+    """``y.gemv_tr(alpha, &a, &x, beta)``: y <- alpha*a^T*x + beta*y (blas.rs:503-540): the same call on the transposed view."""
+    return gemv(alpha, _as_matrix(a).T, x, beta, y)
+
+
+gemv_ad = gemv_tr
+
+
 def syrk_lower(alpha: float, a, beta: float, c: np.ndarray) -> np.ndarray:
     """c <- alpha * a * a^T + beta * c on the LOWER triangle (incl. diagonal) of the square c only; the
     strict upper triangle is neither read nor written.  The bench SPD recipe of the reference is

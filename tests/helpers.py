@@ -56,3 +56,39 @@ def relative_eq(a, b, epsilon):
     a = np.asarray(a); b = np.asarray(b)
     d = np.abs(a - b)
     return bool(np.all((d <= epsilon) | (d <= EPS * np.maximum(np.abs(a), np.abs(b)))))
+
+
+def first_pivot_divergence(a, lu_packed, swaps_a, swaps_b):
+    """Tie-aware comparison of two PermutationSequences of the same matrix.  None when they are equal; otherwise the
+    first step at which they differ, the two pivot rows, their candidate values in that column (recomputed from the
+    common prefix of the factorization: s = (P A)[i:, i] - L[i:, :i] U[:i, i]) and the relative gap between them --
+    a gap of a few ulps means a legitimate near-tie resolved differently by a different summation order, anything
+    larger is a bug.  `lu_packed` must belong to `swaps_a`."""
+    sa = [tuple(int(v) for v in p) for p in np.asarray(swaps_a).reshape(-1, 2)]
+    sb = [tuple(int(v) for v in p) for p in np.asarray(swaps_b).reshape(-1, 2)]
+    if sa == sb:
+        return None
+    n = a.shape[0]
+    da, db = dict(sa), dict(sb)                      # step -> pivot row (missing: no swap, pivot = step)
+    step = min(i for i in range(min(a.shape)) if da.get(i, i) != db.get(i, i))
+    perm = np.arange(n)
+    for i, j in sa:
+        if i >= step:
+            break
+        perm[[i, j]] = perm[[j, i]]
+    pa = a[perm]
+    l = np.tril(lu_packed[:, :step], -1)[step:, :]   # rows >= step of L's first `step` columns (A's permutation beyond `step` does not matter
+    # for the candidates' VALUES, only for their positions: use positions of sequence a up to `step`, which both share)
+    u = np.triu(lu_packed[:step, :])[:, step] if step else np.zeros(0)
+    # rows >= step of lu_packed are permuted by a's later swaps; undo them to address rows by their position at `step`
+    later = [(i, j) for i, j in sa if i >= step]
+    rowpos = np.arange(n)
+    for i, j in later:
+        rowpos[[i, j]] = rowpos[[j, i]]
+    lfull = np.empty((n - step, step))
+    lfull[rowpos[step:] - step] = l                  # row r of the final factor sat at position rowpos[r] at `step`
+    s = pa[step:, step] - lfull @ u
+    ra, rb = da.get(step, step), db.get(step, step)
+    va, vb = s[ra - step], s[rb - step]
+    return {"step": step, "rows": (ra, rb), "values": (float(va), float(vb)),
+            "relative_gap": float(abs(abs(va) - abs(vb)) / max(abs(va), abs(vb), 1e-300))}

@@ -195,15 +195,13 @@ def test_gemm_full_size_linearity_on_device(L):
 
 
 def test_lu_panel_trsm_kernel(L):
-    """The direct unit-lower TRSM of the LU panel recursion (trsm_unit_lower_small_kernel) against numpy, through its
-    test hook: block sizes around 64/128, ragged right-hand-side counts, garbage on and above L's diagonal, padding rows
+    """The direct unit-lower TRSM of the LU panels (trsm_unit_lower_small_kernel) against numpy, through na_trsm_f64_dev: block sizes around 64/128, ragged right-hand-side counts, garbage on and above L's diagonal, padding rows
     untouched.  (Round 1: a __restrict__ shared-memory pointer let nvcc keep a stale value across __syncthreads.)"""
     import ctypes as C
     import torch
     from nalgebra_b200 import _capi
-    f = L.na_debug_trsm_unit_lower_small
-    f.restype = C.c_int
-    f.argtypes = [C.c_size_t, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_size_t, C.c_void_p]
+    def f(n1, l_ptr, ldl, b_ptr, ldb, nrhs, stream):      # na_trsm_f64_dev routes unit-lower solves of <= 128 rows to that kernel
+        return L.na_trsm_f64_dev(0, 1, 0, 1, n1, nrhs, l_ptr, ldl, b_ptr, ldb, stream)
     s = torch.cuda.current_stream().cuda_stream
     rng = np.random.default_rng(1)
     for n1 in (1, 37, 64, 65, 100, 127, 128):
@@ -496,3 +494,172 @@ def test_concurrent_calls_from_two_host_threads(L):
         assert torch.equal(conc["lu"][0], serial["lu"][0])
         assert torch.equal(conc["chol"], serial["chol"])
 
+
+
+# ---- round 2: parity holes the round-1 review named ---------------------------------------------------
+def test_vector_right_hand_sides(nab, oracle):
+    """A DVector rhs (1-D array) is an n x 1 matrix: solve / solve_mut / q_tr_mul / triangular solves (round 1 turned it
+    into 1 x n and read n*n doubles from an n-double buffer)."""
+    n = 37
+    spd = oracle.spd_wellcond(n, 5); a = oracle.uniform(n, n, 6) - 0.3
+    b = oracle.uniform(n, 1, 7)[:, 0].copy()
+    ch = nab.Cholesky.new(spd); x = ch.solve(b)
+    assert x.shape == (n,) and np.abs(spd @ x - b).max() <= 1e-10
+    b2 = b.copy(); ch.solve_mut(b2); assert np.array_equal(b2, x)
+    lu = nab.LU.new(a); x = lu.solve(b)
+    assert x.shape == (n,) and np.abs(a @ x - b).max() <= 1e-9
+    qr = nab.QR.new(a); x = qr.solve(b)
+    assert x.shape == (n,) and np.abs(a @ x - b).max() <= 1e-9
+    v = b.copy(); qr.q_tr_mul(v)
+    assert np.abs(v - qr.q().T @ b).max() <= 1e-12
+    t = np.tril(a) + 3 * np.eye(n)
+    x = nab.solve_lower_triangular(t, b)
+    assert x.shape == (n,) and np.abs(t @ x - b).max() <= 1e-10
+    with pytest.raises(ValueError):
+        ch.solve(np.ones(n + 1))
+
+
+def test_solve_lower_triangular_with_diag(nab, oracle):
+    """solve.rs:106-133 including its quirk: the diagonal is `diag`, and b[i] is never divided by it."""
+    C_ = C
+    for n, diag in ((1, 2.5), (7, 1.0), (33, -0.75), (130, 3.0)):
+        t = np.asfortranarray(oracle.uniform(n, n, 3) - 0.5); b = np.asfortranarray(oracle.uniform(n, 3, 4))
+        ref = b.copy(order="F")
+        assert oracle.lib().na_oracle_solve_lower_with_diag_f64(n, t.ctypes.data, n, C_.c_double(diag), ref.ctypes.data, n, 3) == 1
+        got = nab.solve_lower_triangular_with_diag(t, b, diag)
+        assert np.abs(got - ref).max() <= 1e-10 * max(1.0, np.abs(ref).max()), (n, diag)
+    assert nab.solve_lower_triangular_with_diag(np.eye(3), np.ones(3), 0.0) is None
+
+
+def test_api_names_of_the_reference(nab, oracle):
+    """tr_mul_to / ad_mul(_to) / gemm_ad (ops.rs:674-779, blas.rs:827-860), LU::try_inverse_to / l_unpack,
+    lu::try_invert_to (lu.rs:51-86, 156-171, 283-297)."""
+    a = oracle.uniform(40, 23, 1) - 0.5; b = oracle.uniform(40, 17, 2) - 0.5
+    out = np.full((23, 17), np.nan, order="F")
+    nab.tr_mul_to(a, b, out)
+    assert np.abs(out - a.T @ b).max() <= gemm_tol(a, b, 40)
+    assert np.array_equal(nab.ad_mul(a, b), nab.tr_mul(a, b))
+    with pytest.raises(ValueError):
+        nab.tr_mul_to(a, b, np.empty((17, 23), order="F"))
+    m = oracle.uniform(30, 30, 6) - 0.3
+    inv = np.empty((30, 30), order="F")
+    assert nab.try_invert_to(m, inv) and np.abs(inv @ m - np.eye(30)).max() <= 1e-9
+    inv2 = np.empty((30, 30), order="F")
+    lu = nab.LU.new(m)
+    assert lu.try_inverse_to(inv2) and np.array_equal(inv, inv2)
+    l = lu.l(); assert np.array_equal(lu.l_unpack(), l)
+    sing = m.copy(); sing[:, 4] = 0.0
+    assert not nab.try_invert_to(sing, inv)
+
+
+def test_syrk_lower_host_entry(nab, oracle):
+    """na_dsyrk_lower: C <- alpha*A*A^T + beta*C on the lower triangle only; the strict upper triangle of the host matrix
+    (NaN here) is neither read nor written.  The reference's SPD recipes form M*M^T (benches/linalg/cholesky.rs:3-11)."""
+    for (n, k) in ((1, 1), (5, 3), (130, 70), (257, 300), (600, 64)):
+        a = oracle.uniform(n, k, 4) - 0.5
+        for alpha, beta in ((1.0, 0.0), (1.5, 0.5)):
+            c0 = oracle.uniform(n, n, 9)
+            c = np.asfortranarray(np.tril(c0) + np.triu(np.full((n, n), np.nan), 1))
+            nab.syrk_lower(alpha, a, beta, c)
+            ref = alpha * (a @ a.T) + (beta * c0 if beta else 0.0)
+            assert np.all(np.isnan(c[np.triu_indices(n, 1)])), (n, k)
+            assert np.abs(np.tril(c) - np.tril(ref)).max() <= gemm_tol(a, a, k) + 1e-14, (n, k, alpha, beta)
+    # the bench SPD recipe end to end: M*M^T + sqrt(eps)*|M|_F^2*I on the GPU, then Cholesky::new of it
+    n = 300
+    m = oracle.uniform(n, n, 4)
+    c = np.zeros((n, n), order="F")
+    nab.syrk_lower(1.0, m, 0.0, c)
+    c[np.diag_indices(n)] += np.sqrt(EPS) * np.linalg.norm(m) ** 2
+    assert nab.Cholesky.new(c) is not None
+    # k == 0: the beta contract of gemm_uninit (blas_uninit.rs:258-269) on the triangle
+    c = np.asfortranarray(np.tril(np.ones((5, 5))) + np.triu(np.full((5, 5), np.nan), 1))
+    nab.syrk_lower(1.0, np.zeros((5, 0)), 0.5, c)
+    assert np.array_equal(np.tril(c), 0.5 * np.tril(np.ones((5, 5)))) and np.all(np.isnan(c[np.triu_indices(5, 1)]))
+
+
+def test_gemv_and_axcpy(nab, oracle, L):
+    """gemv_uninit / gemv_tr / axcpy (blas_uninit.rs:86-177, blas.rs:503-540): G8, the Level-1/2 fallbacks."""
+    import torch
+    from nalgebra_b200 import _capi
+    for (m, n) in ((1, 1), (5, 3), (3, 5), (130, 70), (1000, 513), (2000, 3000)):
+        a = oracle.uniform(m, n, 1) - 0.5; x = oracle.uniform(n, 1, 2)[:, 0] - 0.5; y0 = oracle.uniform(m, 1, 3)[:, 0]
+        tol = 4 * n * EPS * np.linalg.norm(a) * np.linalg.norm(x) + 1e-300
+        for alpha, beta in ((1.0, 0.0), (1.5, 0.5)):
+            y = np.full(m, np.nan) if beta == 0.0 else y0.copy()
+            nab.gemv(alpha, a, x, beta, y)
+            assert np.abs(y - (alpha * a @ x + (beta * y0 if beta else 0.0))).max() <= tol, (m, n)
+            # row-major A (transposed view) and a strided x / y
+            y = np.zeros(2 * m); y[::2] = y0
+            nab.gemv(alpha, np.ascontiguousarray(a), np.repeat(x, 2)[::2], beta, y[::2])
+            assert np.abs(y[::2] - (alpha * a @ x + (beta * y0 if beta else 0.0))).max() <= tol
+        yt = np.full(n, np.nan)
+        nab.gemv_tr(1.0, a, y0, 0.0, yt)
+        assert np.abs(yt - a.T @ y0).max() <= 4 * m * EPS * np.linalg.norm(a) * np.linalg.norm(y0) + 1e-300
+    y = np.ones(4); nab.gemv(1.0, np.zeros((4, 0)), np.zeros(0), 0.5, y); assert np.array_equal(y, 0.5 * np.ones(4))
+    # axcpy on the device: (a*x)*c + b*y with the reference's unfused rounding == the oracle's axcpy bit for bit
+    n = 1000
+    xs = oracle.uniform(n, 1, 5)[:, 0]; ys = oracle.uniform(n, 1, 6)[:, 0]
+    dx = torch.from_numpy(xs).cuda(); dy = torch.from_numpy(ys.copy()).cuda()
+    _capi.check(L.na_daxcpy_dev(n, 1.7, dx.data_ptr(), 1, 0.3, -2.5, dy.data_ptr(), 1, torch.cuda.current_stream().cuda_stream))
+    assert np.array_equal(dy.cpu().numpy(), (1.7 * xs) * 0.3 + (-2.5) * ys)
+
+
+def test_lu_pivot_divergence_report(nab, oracle):
+    """The tie-aware comparator (SURVEY "hard part 2"): equal sequences -> None; a forced divergence is located and the
+    relative gap of the two candidates is what was planted."""
+    from helpers import first_pivot_divergence
+    n = 200
+    a = oracle.uniform(n, n, 6) - 0.3
+    lu = nab.LU.new(a)
+    lur, swr = oracle.lu(a)
+    assert first_pivot_divergence(a, lu.lu_internal(), lu.p().ipiv, swr) is None
+    # plant a near-tie in column 0: rows r1 < r2 hold the two largest |values|, r2 larger by 1e-13 relative
+    b = a.copy()
+    col = np.abs(b[:, 0]); r1 = int(np.argmax(col)); big = col[r1]
+    r2 = (r1 + 7) % n
+    b[r2, 0] = big * (1 + 4e-13)
+    lub = nab.LU.new(b)
+    fake = lub.p().ipiv.copy()
+    fake[0] = (0, r1) if r1 != 0 else fake[0]
+    rep = first_pivot_divergence(b, lub.lu_internal(), lub.p().ipiv, fake)
+    if r1 != 0 and r2 != 0:
+        assert rep is not None and rep["step"] == 0 and rep["rows"] == (r2, r1) and 1e-13 < rep["relative_gap"] < 1e-12
+
+
+def test_lu_8192_pivots_bit_exact_vs_oracle(nab, oracle, L):
+    """BASELINE configs[3] asks for bit-exact pivots vs the CPU: the look-ahead driver (flat 512-panels, register-resident
+    GETF2 leaves, DMMA trailing updates) against the oracle's unblocked, unfused LU at N = 8192 (~3 min of one CPU core)."""
+    from helpers import first_pivot_divergence
+    n = 8192
+    a = oracle.uniform(n, n, 6)
+    lu = nab.LU.new(a)
+    lur, swr = oracle.lu(a)
+    rep = first_pivot_divergence(a, lu.lu_internal(), lu.p().ipiv, swr)
+    assert rep is None, rep
+    assert np.abs(lu.lu_internal() - lur).max() <= 1e-8
+
+
+def test_lu_16384_lookahead_and_plain_paths_agree(L):
+    """N = 16384: the two-stream look-ahead driver and the plain recursive driver (different blocking of the trailing
+    updates) must produce the same PermutationSequence; the factors agree to rounding."""
+    import torch
+    from nalgebra_b200 import _capi
+    n = 16384
+    dev = torch.device("cuda:0"); s = torch.cuda.current_stream().cuda_stream
+    A0 = torch.empty(n * n, dtype=torch.float64, device=dev)
+    _capi.check(L.na_fill_uniform_dev(A0.data_ptr(), n, n, n, 6, s))
+    res = []
+    try:
+        for la in (1, 0):
+            _capi.check(L.na_set_tuning(b"lu_lookahead", la))
+            A = A0.clone(); swaps = (C.c_size_t * (2 * n))(); ns = C.c_size_t(0)
+            _capi.check(L.na_lu_f64_dev(n, n, A.data_ptr(), n, swaps, C.addressof(ns), s))
+            res.append((A, np.frombuffer(swaps, dtype=np.uint64)[: 2 * ns.value].copy()))
+    finally:
+        _capi.check(L.na_set_tuning(b"lu_lookahead", 1))
+    if not np.array_equal(res[0][1], res[1][1]):
+        from helpers import first_pivot_divergence
+        rep = first_pivot_divergence(A0.view(n, n).t().cpu().numpy(), res[0][0].view(n, n).t().cpu().numpy(),
+                                     res[0][1].reshape(-1, 2), res[1][1].reshape(-1, 2))
+        pytest.fail(f"pivot sequences differ: {rep}")
+    assert (res[0][0] - res[1][0]).abs().max().item() <= 1e-7

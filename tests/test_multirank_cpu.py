@@ -82,27 +82,51 @@ class _OracleOps:
         bji = self.O.rand01(seed, (j + i * np.uint64(n)).ravel()).reshape(nrows, ncols)
         self._mat(ptr, nrows, ncols, ld)[...] = (bij + bji) * 0.5 + n * (i == j)
 
-    def potrf(self, ptr, w, ld):
-        fail = self.C.c_size_t(0)
-        return self.O.lib().na_oracle_cholesky_f64(w, ptr, ld, 0, 0.0, self.C.addressof(fail))
+    def status_word(self):
+        return torch.full((1,), -1, dtype=torch.int64)
+
+    def ipiv(self, n):
+        return torch.zeros(max(n, 1), dtype=torch.int32)
+
+    def fill_uniform(self, ptr, nrows, ncols, ld, seed, row0, col0, global_rows):
+        i = (np.arange(row0, row0 + nrows)[:, None]).astype(np.uint64); j = (np.arange(col0, col0 + ncols)[None, :]).astype(np.uint64)
+        self._mat(ptr, nrows, ncols, ld)[...] = self.O.rand01(seed, (i + j * np.uint64(global_rows)).ravel()).reshape(nrows, ncols)
+
+    def potrf_async(self, ptr, w, ld, fail, col_offset):
+        fc = self.C.c_size_t(0)
+        st = self.O.lib().na_oracle_cholesky_f64(w, ptr, ld, 0, 0.0, self.C.addressof(fc))
+        if st != 0:
+            cur = int(fail[0]) & ((1 << 64) - 1)
+            new = min(cur, fc.value + col_offset)
+            fail[0] = new if new < (1 << 63) else new - (1 << 64)
 
     def trsm_right_lower_trans(self, m, w, t_ptr, ldt, b_ptr, ldb):
         import scipy.linalg as sl
         t = np.tril(self._mat(t_ptr, w, w, ldt)); b = self._mat(b_ptr, m, w, ldb)
         b[...] = sl.solve_triangular(t, b.T, lower=True).T
 
-    def lu_panel(self, ptr, m, w, ld):
+    def lu_panel_async(self, ptr, m, w, ld, ipiv_ptr):
         mn = min(m, w)
         swaps = (self.C.c_size_t * (2 * max(mn, 1)))(); ns = self.C.c_size_t(0)
         self.O.lib().na_oracle_lu_f64(m, w, ptr, ld, swaps, self.C.addressof(ns))
-        return [(swaps[2 * i], swaps[2 * i + 1]) for i in range(ns.value)]
+        piv = np.frombuffer((self.C.c_int32 * mn).from_address(ipiv_ptr), dtype=np.int32)
+        piv[...] = np.arange(mn)
+        for i in range(ns.value):
+            piv[swaps[2 * i]] = swaps[2 * i + 1]
 
-    def permute_rows(self, ptr, nrows, ld, ncols, pairs):
-        if not pairs or ncols == 0:
+    def apply_ipiv(self, ptr, nrows, ld, ncols, ipiv_ptr, k, row0):
+        if ncols == 0 or k == 0:
             return
+        piv = np.frombuffer((self.C.c_int32 * k).from_address(ipiv_ptr), dtype=np.int32)
         a = self._mat(ptr, nrows, ncols, ld)
-        for i, j in pairs:
-            a[[i, j]] = a[[j, i]]
+        for s_ in range(k):
+            i, j = row0 + s_, row0 + int(piv[s_])
+            if i != j:
+                a[[i, j]] = a[[j, i]]
+
+    def gemm(self, m, k, n, alpha, a_ptr, lda, b_ptr, ldb, beta, c_ptr, ldc):
+        a = self._mat(a_ptr, m, k, lda); b = self._mat(b_ptr, k, n, ldb); c = self._mat(c_ptr, m, n, ldc)
+        c[...] = alpha * (a @ b) + (beta * c if beta != 0.0 else 0.0)
 
     def trsm_left_unit_lower(self, m, n, t_ptr, ldt, b_ptr, ldb):
         import scipy.linalg as sl
@@ -129,10 +153,19 @@ def _chol_worker(rank, world, port, n, nb, out_dir, lookahead):
     A = ColumnBlockCyclic(n, nb, rank, world, _OracleOps())
     A.fill_spd(5)
     st = cholesky_block_cyclic(A, lookahead=lookahead)
+    from nalgebra_b200.distributed import cholesky_residual_block_cyclic
+    res = cholesky_residual_block_cyclic(A, 5)
+    # a non-PD matrix: every rank must report the same failing column, with no host round trip per panel
+    B = ColumnBlockCyclic(n, nb, rank, world, _OracleOps())
+    B.fill_spd(5)
+    bad = 37
+    if bad // nb in B.my_blocks:
+        _OracleOps()._mat(B.ptr(0, bad // nb), n, B.width(bad // nb), n)[bad, bad % nb] = -1.0
+    st_bad = cholesky_block_cyclic(B, lookahead=lookahead)
     full = A.gather_to(0)
     if rank == 0:
         np.save(os.path.join(out_dir, f"l_{world}_{int(lookahead)}.npy"), full.numpy())
-        np.save(os.path.join(out_dir, f"st_{world}_{int(lookahead)}.npy"), np.array([st]))
+        np.save(os.path.join(out_dir, f"st_{world}_{int(lookahead)}.npy"), np.array([st, res, st_bad, -1 if B.fail_col is None else B.fail_col]))
     dist.barrier()
     dist.destroy_process_group()
 
@@ -144,7 +177,9 @@ def test_block_cyclic_cholesky_logic(tmp_path, oracle):
     for world, port in ((2, 29621), (3, 29622)):
         mp.spawn(_chol_worker, args=(world, port, n, nb, str(tmp_path), True), nprocs=world, join=True)
         got = np.load(tmp_path / f"l_{world}_1.npy")
-        assert np.load(tmp_path / f"st_{world}_1.npy")[0] == 0
+        st, res, st_bad, fail_col = np.load(tmp_path / f"st_{world}_1.npy")
+        assert st == 0 and res <= 10 * n * np.finfo(np.float64).eps
+        assert st_bad == 1 and fail_col == 37                            # NA_NOT_PD + the failing column, read back once
         assert np.abs(np.tril(got) - lref).max() <= 1e-12 * np.abs(lref).max()
         assert np.array_equal(np.triu(got, 1), np.triu(spd, 1))          # strict upper never touched
 
@@ -164,7 +199,14 @@ def _lu_worker(rank, world, port, n, nb, out_dir):
         ops._mat(A.ptr(0, b), n, w, n)[...] = full0[:, b * nb: b * nb + w]
     pairs = lu_block_cyclic(A)
     full = A.gather_to(0)
+    # the residual replay against the generator-defined matrix (what the 8-GPU bench runs at N = 65536)
+    from nalgebra_b200.distributed import lu_residual_block_cyclic
+    G = ColumnBlockCyclic(n, nb, rank, world, ops)
+    G.fill_uniform(6)
+    lu_block_cyclic(G)
+    res = lu_residual_block_cyclic(G, 6)
     if rank == 0:
+        np.save(os.path.join(out_dir, f"lures_{world}.npy"), np.array([res]))
         np.save(os.path.join(out_dir, f"lu_{world}.npy"), full.numpy())
         np.save(os.path.join(out_dir, f"sw_{world}.npy"), np.array(pairs, dtype=np.int64).reshape(-1, 2))
     dist.barrier()
@@ -180,3 +222,40 @@ def test_block_cyclic_lu_logic(tmp_path, oracle):
         got = np.load(tmp_path / f"lu_{world}.npy"); sw = np.load(tmp_path / f"sw_{world}.npy")
         assert np.array_equal(sw, sw_ref.astype(np.int64))                # PermutationSequence identical
         assert np.abs(got - lu_ref).max() <= 1e-11
+        assert np.load(tmp_path / f"lures_{world}.npy")[0] <= 10 * n * np.finfo(np.float64).eps
+
+
+# ---------------------------------------------------------------------------------------------------
+# Gemm2D (the product's sharded GEMM) on CPU: collective exchange over gloo, oracle arithmetic, 2 and 4 ranks
+# ---------------------------------------------------------------------------------------------------
+def _gemm2d_worker(rank, world, port, n, out_dir):
+    sys.path.insert(0, ROOT)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from nalgebra_b200.distributed import Gemm2D
+    g = Gemm2D(n, n, n, rank, world, _OracleOps(), exchange="collective", kp=16)
+    g.fill_uniform(1, 2)
+    c = g.multiply().clone()
+    c2 = g.multiply_assembled().clone()
+    tiles = [None] * world
+    dist.all_gather_object(tiles, (g.row0, g.col0, g.m_loc, g.n_loc, c.numpy(), float((c - c2).abs().max())))
+    if rank == 0:
+        full = np.zeros((n, n))
+        for (r0, c0, ml, nl, t, d) in tiles:
+            full[r0:r0 + ml, c0:c0 + nl] = t.reshape(nl, ml).T          # column-major tile
+            assert d <= 1e-12
+        np.save(os.path.join(out_dir, f"g2d_{world}.npy"), full)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_gemm2d_product_logic(tmp_path, oracle):
+    n = 64
+    a, b = oracle.uniform(n, n, 1), oracle.uniform(n, n, 2)
+    ref = np.zeros((n, n), order="F")
+    oracle.gemm(1.0, a, b, 0.0, ref)
+    for world, port in ((2, 29631), (4, 29632)):
+        mp.spawn(_gemm2d_worker, args=(world, port, n, str(tmp_path)), nprocs=world, join=True)
+        full = np.load(tmp_path / f"g2d_{world}.npy")
+        assert np.abs(full - ref).max() <= 4 * n * np.finfo(np.float64).eps * np.linalg.norm(a) * np.linalg.norm(b)
