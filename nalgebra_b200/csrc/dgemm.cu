@@ -223,14 +223,20 @@ dgemm_tma_dmma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
 
     int stage = 0;
     uint32_t phase = 0;
-    // Deferred release: the empty-barrier arrive for a stage is issued only after the NEXT stage's
-    // full-barrier wait.  ptxas sinks the last k-step's DMMAs below an arrive placed at the end of the
-    // iteration, which leaves that step's final LDS still in flight when the slot is handed back; under a
-    // backed-up LSU (beta != 0 epilogues of the sibling warps) the refill TMA then won the race about once
-    // per 1e8 stage reads and one A fragment of one warp came from the wrong k-block.  The spin-wait loop
-    // in between is a scheduling barrier: every DMMA of the previous stage (hence every LDS result) has
-    // issued before the arrive below.
+    // Stage hand-back.  The slot may be refilled by TMA as soon as the empty barrier completes, so every fragment
+    // LDS of the stage must have RETURNED its data before this warp arrives.  (Round 1: with a plain arrive at the
+    // end of the iteration ptxas sank the last k-step's DMMAs below it, that step's final LDS was still in flight
+    // when the slot was handed back, and under a backed-up LSU the refill won the race about once per 1e8 stage
+    // reads.)  Two independent guards:
+    //   1. an explicit DATA dependency: `frag_dep` folds the high words of all 12 fragment registers of the stage's
+    //      last k-step into a value that is always 0 but opaque to the compiler (x*x + x is even), and the arrive
+    //      adds it to its count operand -- the arrive cannot issue before those loads have written their registers
+    //      (shared-memory loads of a warp return in order, so the earlier k-steps' loads are covered too);
+    //   2. the arrive is deferred until after the NEXT stage's full-barrier wait, as before.
+    // Gating regression: tools/gemm_stress.py (repeated full-size beta != 0 launches must agree bit for bit) and
+    // test_gemm_full_size_linearity_on_device; validated with nvcc 12.9.86.
     int release_stage = -1;
+    uint32_t release_dep = 0;
     for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
         int tm, tn;
         const int tile = t / p.splits, split = t - tile * p.splits;
@@ -245,7 +251,7 @@ dgemm_tma_dmma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
 
         for (int kb = kb0; kb < kb1; ++kb) {
             ptx::mbar_wait(bar_base + 8 * stage, phase);
-            if (release_stage >= 0 && lane == 0) ptx::mbar_arrive(bar_base + 8 * (STAGES + release_stage));
+            if (release_stage >= 0 && lane == 0) ptx::mbar_arrive_cnt(bar_base + 8 * (STAGES + release_stage), 1u + release_dep);
             const uint8_t* sptr = smem_gen + stage * STAGE_BYTES;
 #pragma unroll
             for (int kk = 0; kk < 4; ++kk) {
@@ -258,6 +264,14 @@ dgemm_tma_dmma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
                 for (int i = 0; i < MT; ++i)
 #pragma unroll
                     for (int j = 0; j < NT; ++j) ptx::dmma884(acc[i][j][0], acc[i][j][1], a[i], b[j]);
+                if (kk == 3) {
+                    uint32_t x = 0;
+#pragma unroll
+                    for (int i = 0; i < MT; ++i) x ^= (uint32_t)__double2hiint(a[i]);
+#pragma unroll
+                    for (int j = 0; j < NT; ++j) x ^= (uint32_t)__double2hiint(b[j]);
+                    release_dep = ptx::opaque_zero(x);
+                }
             }
             release_stage = stage;
             if (++stage == STAGES) { stage = 0; phase ^= 1; }

@@ -25,6 +25,17 @@ __device__ __forceinline__ void fence_proxy_async() {
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
+// arrive with an explicit count (callers pass 1 + a data-dependent zero to order the arrive after their loads)
+__device__ __forceinline__ void mbar_arrive_cnt(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+// Always 0, but derived from x in a way neither nvcc nor ptxas can fold (x*x + x is even for every x): turns "the
+// registers feeding x have been written" into a dependency of whatever consumes the result.
+__device__ __forceinline__ uint32_t opaque_zero(uint32_t x) {
+    uint32_t z;
+    asm volatile("{\n\t.reg .u32 t;\n\tmad.lo.u32 t, %1, %1, %1;\n\tand.b32 %0, t, 1;\n\t}" : "=r"(z) : "r"(x));
+    return z;
+}
 __device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
