@@ -238,6 +238,27 @@ NAB_API int na_dgemm_lower_dev(size_t m, size_t k, size_t n, double alpha,
 NAB_API int na_fill_spd_block_dev(double* a, size_t nrows, size_t ncols, size_t lda, uint64_t seed,
                                   size_t row0, size_t col0, size_t n, void* stream);
 
+/* ---- seam 2': LAPACK symbols (Fortran ABI) for `nalgebra-lapack --features lapack-custom` -------------------------
+ * /root/reference/nalgebra-lapack/src/lib.rs:33-36; call sites cholesky.rs:181-224, lu.rs:351-446, qr.rs:166-237 and
+ * 369-590.  Every argument by pointer, INTEGER = int32, characters as one byte, info through the last argument; HOST
+ * pointers, LAPACK layouts (potrf 'L'/'U' factor in place, getrf L\U + 1-based ipiv, geqrf R + reflector vectors + tau).
+ * Workspace queries (lwork = -1) answer 1.  Without an sm_100 device info = -1000 (no CPU fallback). */
+NAB_API void dpotrf_(const char* uplo, const int* n, double* a, const int* lda, int* info);
+NAB_API void dpotrs_(const char* uplo, const int* n, const int* nrhs, const double* a, const int* lda, double* b, const int* ldb, int* info);
+NAB_API void dpotri_(const char* uplo, const int* n, double* a, const int* lda, int* info);
+NAB_API void dgetrf_(const int* m, const int* n, double* a, const int* lda, int* ipiv, int* info);
+NAB_API void dlaswp_(const int* n, double* a, const int* lda, const int* k1, const int* k2, const int* ipiv, const int* incx);
+NAB_API void dgetrs_(const char* trans, const int* n, const int* nrhs, const double* a, const int* lda, const int* ipiv, double* b,
+                     const int* ldb, int* info);
+NAB_API void dgetri_(const int* n, double* a, const int* lda, const int* ipiv, double* work, const int* lwork, int* info);
+NAB_API void dgeqrf_(const int* m, const int* n, double* a, const int* lda, double* tau, double* work, const int* lwork, int* info);
+NAB_API void dormqr_(const char* side, const char* trans, const int* m, const int* n, const int* k, const double* a, const int* lda,
+                     const double* tau, double* c, const int* ldc, double* work, const int* lwork, int* info);
+NAB_API void dorgqr_(const int* m, const int* n, const int* k, double* a, const int* lda, const double* tau, double* work,
+                     const int* lwork, int* info);
+NAB_API void dtrtrs_(const char* uplo, const char* trans, const char* diag, const int* n, const int* nrhs, const double* a, const int* lda,
+                     double* b, const int* ldb, int* info);
+
 #ifdef __cplusplus
 }
 #endif

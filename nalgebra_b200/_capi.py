@@ -71,6 +71,10 @@ SIGNATURES = {
     "na_lu_f64_dev_async": (_int, [_sz, _sz, _p, _sz, _p, _p]),
     "na_apply_ipiv_f64_dev": (_int, [_sz, _p, _sz, _sz, _p, _sz, _sz, _p]),
     "na_set_tuning": (_int, [C.c_char_p, C.c_long]),
+    # Fortran-ABI LAPACK facade: every argument by pointer
+    "dpotrf_": (None, [_p] * 5), "dpotrs_": (None, [_p] * 8), "dpotri_": (None, [_p] * 5),
+    "dgetrf_": (None, [_p] * 6), "dlaswp_": (None, [_p] * 7), "dgetrs_": (None, [_p] * 9), "dgetri_": (None, [_p] * 7),
+    "dgeqrf_": (None, [_p] * 8), "dormqr_": (None, [_p] * 13), "dorgqr_": (None, [_p] * 9), "dtrtrs_": (None, [_p] * 10),
     "na_tri_solve_f64": (_int, [_int, _int, _int, _sz, _p, _sz, _p, _sz, _sz]),
     "na_tri_solve_f64_dev": (_int, [_int, _int, _int, _sz, _p, _sz, _p, _sz, _sz, _p]),
 }

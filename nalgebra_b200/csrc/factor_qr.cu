@@ -178,8 +178,10 @@ static int qr_lookahead(cudaStream_t sp, QrWork& w, size_t m, size_t n, double* 
     return st;
 }
 
-// diag: DEVICE pointer, min(m,n) entries.
-int qr_device(cudaStream_t s, size_t m, size_t n, double* a, size_t lda, double* diag) {
+// diag: DEVICE pointer, min(m,n) entries (nalgebra storage).  tau_out != nullptr instead: stop before the storage
+// conversion -- `a` then holds the classical / LAPACK geqrf form (R on and above the diagonal, the reflector vectors v
+// with implicit unit head below it) and tau_out (DEVICE, min(m,n)) the scalar factors.
+int qr_device(cudaStream_t s, size_t m, size_t n, double* a, size_t lda, double* diag, double* tau_out) {
     const size_t k = std::min(m, n);
     if (k == 0) return NA_OK;
     if (lda < m) { set_error("qr: lda < m"); return NA_EINVAL; }
@@ -188,9 +190,13 @@ int qr_device(cudaStream_t s, size_t m, size_t n, double* a, size_t lda, double*
     NAB_TRY(w.init(s, m, n, k));
     double* tau = w.tau.as<double>();
     double* vw = w.vw.as<double>();
+    auto finish = [&]() -> int {
+        if (tau_out) { NAB_CUDA(cudaMemcpyAsync(tau_out, tau, k * sizeof(double), cudaMemcpyDeviceToDevice, s)); return NA_OK; }
+        return qr_convert_to_nalgebra(s, a, lda, m, n, tau, w.csign.as<double>(), diag);
+    };
     if (qr_lookahead_enabled() && k >= 4 * QR_NB && m >= 8192 && n <= m) {
         NAB_TRY(qr_lookahead(s, w, m, n, a, lda, tau, k));
-        return qr_convert_to_nalgebra(s, a, lda, m, n, tau, w.csign.as<double>(), diag);
+        return finish();
     }
     for (size_t j = 0; j < k; j += QR_NB) {
         const size_t jb = std::min(QR_NB, k - j), mj = m - j;
@@ -204,25 +210,27 @@ int qr_device(cudaStream_t s, size_t m, size_t n, double* a, size_t lda, double*
                                           apanel + jb * lda, lda, nt, w.wk.as<double>(), w.ldw));
         }
     }
-    return qr_convert_to_nalgebra(s, a, lda, m, n, tau, w.csign.as<double>(), diag);
+    return finish();
 }
 
 // B (m x nb, ldb) <- Q_L^T B (forward = true) or Q_L B restricted to the trailing block structure
 // (forward = false), where Q_L = H_0 H_1 ... H_{k-1}, H_i = I - 2 u_i u_i^T from nalgebra's storage.
 // For forward == false only columns [col_lo(j), nb) of B are touched at block j when `triangular_q`
 // (forming Q from [I; 0]: columns left of the block are still unit vectors untouched by it).
-static int apply_q_blocks(cudaStream_t s, size_t m, size_t k, const double* qr, size_t lda, const double* diag,
-                          double* b, size_t ldb, size_t nb, bool forward, bool triangular_q) {
+// lapack_tau != nullptr: `qr` is in LAPACK geqrf storage with these scalar factors (DEVICE) instead of nalgebra's.
+int apply_q_blocks(cudaStream_t s, size_t m, size_t k, const double* qr, size_t lda, const double* diag,
+                   double* b, size_t ldb, size_t nb, bool forward, bool triangular_q, const double* lapack_tau) {
     if (k == 0 || nb == 0) return NA_OK;
     QrWork w;
     NAB_TRY(w.init(s, m, nb, k));
     double* tau = w.tau.as<double>();
-    NAB_TRY(tau_from_diag(s, tau, diag, k));
+    if (lapack_tau) NAB_CUDA(cudaMemcpyAsync(tau, lapack_tau, k * sizeof(double), cudaMemcpyDeviceToDevice, s));
+    else NAB_TRY(tau_from_diag(s, tau, diag, k));
     const size_t nblk = ceil_div(k, QR_NB);
     for (size_t bi = 0; bi < nblk; ++bi) {
         const size_t blk = forward ? bi : nblk - 1 - bi;
         const size_t j = blk * QR_NB, jb = std::min(QR_NB, k - j), mj = m - j;
-        NAB_TRY(extract_v(s, w.vw.as<double>(), w.ldv, qr + j + j * lda, lda, mj, jb, tau + j, 1));
+        NAB_TRY(extract_v(s, w.vw.as<double>(), w.ldv, qr + j + j * lda, lda, mj, jb, tau + j, lapack_tau ? 0 : 1));
         NAB_TRY(build_s_from_v(s, mj, jb, w.vw.as<double>(), w.ldv, tau + j, w.smat.as<double>(), w.lds));
         const size_t c0 = triangular_q ? j : 0;
         NAB_TRY(apply_block_reflector(s, mj, jb, w.vw.as<double>(), w.ldv, w.smat.as<double>(), w.lds, forward,
@@ -236,7 +244,7 @@ int qr_q_device(cudaStream_t s, size_t m, size_t n, const double* qr, size_t lda
     const size_t k = std::min(m, n);
     if (k == 0) return NA_OK;
     NAB_TRY(set_identity(s, q, ldq, m, k));
-    NAB_TRY(apply_q_blocks(s, m, k, qr, lda, diag, q, ldq, k, false, true));
+    NAB_TRY(apply_q_blocks(s, m, k, qr, lda, diag, q, ldq, k, false, true, nullptr));
     Scratch csign;
     NAB_TRY(csign.alloc((k + 2) * sizeof(double), s));
     NAB_TRY(qr_signs_from_diag(s, diag, k, csign.as<double>()));
@@ -248,7 +256,7 @@ int qr_q_tr_mul_device(cudaStream_t s, size_t m, size_t n, const double* qr, siz
                        double* b, size_t ldb, size_t nrhs) {
     const size_t k = std::min(m, n);
     if (k == 0 || nrhs == 0) return NA_OK;
-    NAB_TRY(apply_q_blocks(s, m, k, qr, lda, diag, b, ldb, nrhs, true, false));
+    NAB_TRY(apply_q_blocks(s, m, k, qr, lda, diag, b, ldb, nrhs, true, false, nullptr));
     Scratch csign;
     NAB_TRY(csign.alloc((k + 2) * sizeof(double), s));
     NAB_TRY(qr_signs_from_diag(s, diag, k, csign.as<double>()));
@@ -278,7 +286,7 @@ extern "C" {
 
 int na_qr_f64_dev(size_t m, size_t n, double* a, size_t lda, double* diag, void* stream) {
     NAB_TRY(ensure_init());
-    return qr_device(static_cast<cudaStream_t>(stream), m, n, a, lda, diag);
+    return qr_device(static_cast<cudaStream_t>(stream), m, n, a, lda, diag, nullptr);
 }
 
 int na_qr_f64(size_t m, size_t n, double* a, size_t lda, double* diag) {
@@ -291,7 +299,7 @@ int na_qr_f64(size_t m, size_t n, double* a, size_t lda, double* diag) {
     Scratch d, dd; size_t ldd;
     NAB_TRY(upload_matrix(s, d, ldd, a, lda, m, n));
     NAB_TRY(dd.alloc(k * sizeof(double), s));
-    NAB_TRY(qr_device(s, m, n, d.as<double>(), ldd, dd.as<double>()));
+    NAB_TRY(qr_device(s, m, n, d.as<double>(), ldd, dd.as<double>(), nullptr));
     NAB_TRY(download_matrix(s, a, lda, d.as<double>(), ldd, m, n));
     NAB_CUDA(cudaMemcpyAsync(diag, dd.p, k * sizeof(double), cudaMemcpyDeviceToHost, s));
     NAB_CUDA(cudaStreamSynchronize(s));

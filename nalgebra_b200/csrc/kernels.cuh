@@ -83,6 +83,12 @@ int trsm_left(cudaStream_t s, bool eff_lower, bool unit, size_t n, const double*
               const double* diag_abs, const double* inv_blocks, double* b, ptrdiff_t rsb, ptrdiff_t csb, size_t nrhs);
 void lu_set_lookahead(long v);
 int cholesky_device(cudaStream_t s, size_t n, double* a, size_t lda, int use_sub, double sub, size_t* fail_col);
+int cholesky_solve_device(cudaStream_t s, size_t n, const double* l, size_t lda, double* b, size_t ldb, size_t nrhs);
+int lu_device(cudaStream_t s, size_t M, size_t N, double* a, size_t lda, size_t* swaps, size_t* nswaps);
+int lu_device_async(cudaStream_t s, size_t M, size_t N, double* a, size_t lda, int* ipiv_dev);
+int qr_device(cudaStream_t s, size_t m, size_t n, double* a, size_t lda, double* diag, double* tau_out);
+int apply_q_blocks(cudaStream_t s, size_t m, size_t k, const double* qr, size_t lda, const double* diag,
+                   double* b, size_t ldb, size_t nb, bool forward, bool triangular_q, const double* lapack_tau);
 int upload_matrix(cudaStream_t s, Scratch& buf, size_t& ldd, const double* h, size_t ldh, size_t rows, size_t cols);
 int download_matrix(cudaStream_t s, double* h, size_t ldh, const double* d, size_t ldd, size_t rows, size_t cols);
 

@@ -663,3 +663,118 @@ def test_lu_16384_lookahead_and_plain_paths_agree(L):
                                      res[0][1].reshape(-1, 2), res[1][1].reshape(-1, 2))
         pytest.fail(f"pivot sequences differ: {rep}")
     assert (res[0][0] - res[1][0]).abs().max().item() <= 1e-7
+
+
+# ---- the LAPACK-symbol facade (nalgebra-lapack --features lapack-custom) against scipy's LAPACK ----------------------
+def _f(lib, name, *args):
+    """Fortran ABI: every argument by pointer."""
+    keep, ptrs = [], []
+    for a in args:
+        if isinstance(a, np.ndarray):
+            ptrs.append(C.c_void_p(a.ctypes.data)); keep.append(a)
+        elif isinstance(a, bytes):
+            b = C.create_string_buffer(a); keep.append(b); ptrs.append(C.cast(b, C.c_void_p))
+        elif isinstance(a, int):
+            v = C.c_int(a); keep.append(v); ptrs.append(C.cast(C.byref(v), C.c_void_p))
+        else:
+            raise TypeError(type(a))
+    getattr(lib, name)(*ptrs)
+    return keep
+
+
+def test_lapack_facade_vs_scipy(L, oracle):
+    """dpotrf_/dpotrs_/dpotri_, dgetrf_/dgetrs_/dgetri_/dlaswp_, dgeqrf_/dorgqr_/dormqr_, dtrtrs_ with the Fortran ABI and
+    LAPACK layouts, as nalgebra-lapack calls them (nalgebra-lapack/src/cholesky.rs:181-224, lu.rs:351-446, qr.rs:166-590)."""
+    import scipy.linalg.lapack as sl
+    for n in (1, 7, 130, 600):
+        spd = oracle.spd_wellcond(n, 5)
+        for uplo in (b"L", b"U"):
+            a = np.asfortranarray(spd.copy()); info = np.zeros(1, dtype=np.int32)
+            other = np.triu(a, 1) if uplo == b"L" else np.tril(a, -1)
+            _f(L, "dpotrf_", uplo, n, a, n, info)
+            ref, _ = sl.dpotrf(spd, lower=(uplo == b"L"), clean=False)
+            tri = np.tril if uplo == b"L" else np.triu
+            assert info[0] == 0 and np.abs(tri(a) - tri(ref)).max() <= 1e-11 * np.abs(ref).max(), (n, uplo)
+            assert np.array_equal(np.triu(a, 1) if uplo == b"L" else np.tril(a, -1), other)          # other triangle untouched
+            b = np.asfortranarray(oracle.uniform(n, 3, 7)); x = b.copy(order="F")
+            _f(L, "dpotrs_", uplo, n, 3, a, n, x, n, info)
+            assert info[0] == 0 and np.abs(spd @ x - b).max() <= 1e-9
+            inv = a.copy(order="F")
+            _f(L, "dpotri_", uplo, n, inv, n, info)
+            assert info[0] == 0 and np.abs(tri(inv) - tri(np.linalg.inv(spd))).max() <= 1e-10
+            assert np.array_equal(np.triu(inv, 1) if uplo == b"L" else np.tril(inv, -1), other)
+    bad = oracle.spd_wellcond(50, 5); bad[20, 20] = -1.0
+    a = np.asfortranarray(bad); info = np.zeros(1, dtype=np.int32)
+    _f(L, "dpotrf_", b"L", 50, a, 50, info)
+    assert info[0] == 21                                                       # leading minor of order 21 not positive definite
+
+    for (m, n) in ((1, 1), (5, 3), (3, 5), (130, 130), (700, 700), (300, 520)):
+        a0 = oracle.uniform(m, n, 6) - 0.3
+        a = np.asfortranarray(a0.copy()); ipiv = np.zeros(min(m, n), dtype=np.int32); info = np.zeros(1, dtype=np.int32)
+        _f(L, "dgetrf_", m, n, a, m, ipiv, info)
+        lu_ref, piv_ref, _ = sl.dgetrf(a0)
+        assert info[0] == 0 and np.array_equal(ipiv - 1, piv_ref), (m, n)           # same pivots as LAPACK (1-based on our side)
+        assert np.abs(a - lu_ref).max() <= 1e-10, (m, n)
+        if m == n:
+            b = np.asfortranarray(oracle.uniform(n, 4, 7))
+            for trans in (b"N", b"T"):
+                x = b.copy(order="F")
+                _f(L, "dgetrs_", trans, n, 4, a, n, ipiv, x, n, info)
+                op = a0 if trans == b"N" else a0.T
+                assert info[0] == 0 and np.abs(op @ x - b).max() <= 1e-8, (n, trans)
+            inv = a.copy(order="F"); work = np.zeros(1); 
+            _f(L, "dgetri_", n, inv, n, ipiv, work, -1, info); assert work[0] >= 1 and info[0] == 0       # workspace query
+            _f(L, "dgetri_", n, inv, n, ipiv, np.zeros(max(n, 1)), n, info)
+            assert info[0] == 0 and np.abs(inv @ a0 - np.eye(n)).max() <= 1e-8
+            c = np.asfortranarray(oracle.uniform(n, 5, 9)); c2 = c.copy(order="F")
+            _f(L, "dlaswp_", 5, c2, n, 1, n, ipiv, 1)
+            assert np.array_equal(c2, sl.dlaswp(c, piv_ref, k1=0, k2=n - 1))
+    sing = oracle.uniform(40, 40, 6); sing[:, 7] = 0.0
+    a = np.asfortranarray(sing); ipiv = np.zeros(40, dtype=np.int32); info = np.zeros(1, dtype=np.int32)
+    _f(L, "dgetrf_", 40, 40, a, 40, ipiv, info)
+    assert info[0] == 8                                                        # U(8,8) exactly zero
+
+    for (m, n) in ((1, 1), (7, 5), (130, 64), (600, 300), (300, 300), (2000, 260)):
+        a0 = oracle.uniform(m, n, 8) - 0.5
+        k = min(m, n)
+        a = np.asfortranarray(a0.copy()); tau = np.zeros(k); info = np.zeros(1, dtype=np.int32); work = np.zeros(1)
+        _f(L, "dgeqrf_", m, n, a, m, tau, work, -1, info); assert work[0] >= 1
+        _f(L, "dgeqrf_", m, n, a, m, tau, work, 1, info)
+        qr_ref, tau_ref, _, _ = sl.dgeqrf(a0)
+        assert info[0] == 0
+        # R equals LAPACK's up to the sign of a row: a column with nothing below its head (the last one of a square
+        # matrix) is skipped by dlarfg (tau = 0) but reflected here, as nalgebra does (householder.rs:19-53)
+        assert np.abs(np.abs(np.triu(a[:k])) - np.abs(np.triu(qr_ref[:k]))).max() <= 1e-10 * max(1.0, np.abs(qr_ref).max()), (m, n)
+        full = slice(0, k - 1) if m == n else slice(0, k)
+        if tau[full].size:
+            assert np.abs(tau[full] - tau_ref[full]).max() <= 1e-11
+            assert np.abs(np.tril(a, -1)[:, full] - np.tril(qr_ref, -1)[:, full]).max() <= 1e-10, (m, n)   # same reflector vectors
+        q = np.asfortranarray(a[:, :k].copy())
+        _f(L, "dorgqr_", m, k, k, q, m, tau, work, 1, info)
+        assert info[0] == 0 and np.abs(q.T @ q - np.eye(k)).max() <= 10 * m * EPS
+        assert np.abs(q @ np.triu(a[:k]) - a0).max() <= 10 * m * EPS * max(1.0, np.abs(a0).max()) * np.sqrt(n)
+        cmat = np.asfortranarray(oracle.uniform(m, 3, 4))
+        c1 = cmat.copy(order="F")
+        _f(L, "dormqr_", b"L", b"T", m, 3, k, a, m, tau, c1, m, work, 1, info)       # Q^T C: its first k rows are Q_k^T C
+        assert info[0] == 0 and np.abs(c1[:k] - q.T @ cmat).max() <= 1e-10
+        assert abs(np.linalg.norm(c1) - np.linalg.norm(cmat)) <= 1e-10 * np.linalg.norm(cmat)
+        _f(L, "dormqr_", b"L", b"N", m, 3, k, a, m, tau, c1, m, work, 1, info)       # Q (Q^T C) = C
+        assert info[0] == 0 and np.abs(c1 - cmat).max() <= 1e-10
+        cr = np.asfortranarray(oracle.uniform(4, m, 5)); c2 = cr.copy(order="F")
+        _f(L, "dormqr_", b"R", b"N", 4, m, k, a, m, tau, c2, 4, work, 1, info)       # C Q: its first k columns are C Q_k
+        assert info[0] == 0 and np.abs(c2[:, :k] - cr @ q).max() <= 1e-10
+        _f(L, "dormqr_", b"R", b"T", 4, m, k, a, m, tau, c2, 4, work, 1, info)
+        assert info[0] == 0 and np.abs(c2 - cr).max() <= 1e-10
+
+    n = 200
+    t = np.asfortranarray(oracle.uniform(n, n, 3) - 0.5 + 3 * np.eye(n)); b = np.asfortranarray(oracle.uniform(n, 3, 4))
+    for uplo in (b"L", b"U"):
+        for trans in (b"N", b"T"):
+            for diag in (b"N", b"U"):
+                x = b.copy(order="F"); info = np.zeros(1, dtype=np.int32)
+                _f(L, "dtrtrs_", uplo, trans, diag, n, 3, t, n, x, n, info)
+                ref, _ = sl.dtrtrs(t, b, lower=(uplo == b"L"), trans=(1 if trans == b"T" else 0), unitdiag=(diag == b"U"))
+                assert info[0] == 0 and np.abs(x - ref).max() <= 1e-9 * max(1.0, np.abs(ref).max()), (uplo, trans, diag)
+    t2 = t.copy(order="F"); t2[5, 5] = 0.0; x = b.copy(order="F"); info = np.zeros(1, dtype=np.int32)
+    _f(L, "dtrtrs_", b"L", b"N", b"N", n, 3, t2, n, x, n, info)
+    assert info[0] == 6 and np.array_equal(x, b)
