@@ -1,0 +1,156 @@
+//! nalgebra's dense hot path on a B200: `gemm`, `Cholesky`, `LU`, `QR` with the reference's names, argument
+//! meaning, in-place column-major storage and `Option` / `bool` error behaviour (src/base/blas.rs:729-746,
+//! src/linalg/{cholesky,lu,qr}.rs).  All arithmetic runs in libnalgebra_b200 (hand-written sm_100a CUDA);
+//! there is no CPU fallback -- a missing device is a panic with the library's message.
+use nalgebra::{DMatrix, DVector, Dyn, PermutationSequence};
+use nalgebra_b200_sys as sys;
+
+fn check(st: i32) -> i32 {
+    if st < 0 {
+        let msg = unsafe { std::ffi::CStr::from_ptr(sys::na_last_error()) }.to_string_lossy().into_owned();
+        panic!("libnalgebra_b200: {msg}");
+    }
+    st
+}
+
+/// `c.gemm(alpha, &a, &b, beta)` (blas.rs:729-746): views with any strides are accepted; `c` is not read when
+/// `beta == 0`.  Shape mismatches panic like the reference (blas_uninit.rs:244-252).
+pub fn gemm(c: &mut DMatrix<f64>, alpha: f64, a: &DMatrix<f64>, b: &DMatrix<f64>, beta: f64) {
+    assert_eq!(a.ncols(), b.nrows(), "gemm: dimensions mismatch for multiplication.");
+    assert_eq!((c.nrows(), c.ncols()), (a.nrows(), b.ncols()), "gemm: dimensions mismatch for addition.");
+    let (rsa, csa) = a.strides(); let (rsb, csb) = b.strides(); let (rsc, csc) = c.strides();
+    check(unsafe {
+        sys::na_dgemm(a.nrows(), a.ncols(), b.ncols(), alpha, a.as_ptr(), rsa as isize, csa as isize,
+                      b.as_ptr(), rsb as isize, csb as isize, beta, c.as_mut_ptr(), rsc as isize, csc as isize)
+    });
+}
+
+/// `a.tr_mul(&b)` / `gemm_tr`: the same kernel with A's strides swapped (ops.rs:674-779, blas.rs:770-803).
+pub fn tr_mul(a: &DMatrix<f64>, b: &DMatrix<f64>) -> DMatrix<f64> {
+    assert_eq!(a.nrows(), b.nrows(), "Matrix multiplication dimensions mismatch");
+    let mut out = DMatrix::<f64>::zeros(a.ncols(), b.ncols());
+    let (rsa, csa) = a.strides(); let (rsb, csb) = b.strides();
+    check(unsafe {
+        sys::na_dgemm(a.ncols(), a.nrows(), b.ncols(), 1.0, a.as_ptr(), csa as isize, rsa as isize,
+                      b.as_ptr(), rsb as isize, csb as isize, 0.0, out.as_mut_ptr(), 1, a.ncols() as isize)
+    });
+    out
+}
+
+/// `Cholesky{chol}`: L in the lower triangle incl. the diagonal; the strict upper triangle keeps the caller's data.
+pub struct Cholesky { chol: DMatrix<f64> }
+
+impl Cholesky {
+    /// `Cholesky::new` (cholesky.rs:196-198): `None` when a pivot is `<= 0` or NaN.
+    pub fn new(matrix: DMatrix<f64>) -> Option<Self> { Self::new_internal(matrix, None) }
+    /// `Cholesky::new_with_substitute` (cholesky.rs:217-219).
+    pub fn new_with_substitute(matrix: DMatrix<f64>, substitute: f64) -> Option<Self> { Self::new_internal(matrix, Some(substitute)) }
+    fn new_internal(mut m: DMatrix<f64>, sub: Option<f64>) -> Option<Self> {
+        assert!(m.is_square(), "The input matrix must be square.");
+        let n = m.nrows();
+        let mut fail = 0usize;
+        let st = check(unsafe { sys::na_cholesky_f64(n, m.as_mut_ptr(), n.max(1), sub.is_some() as i32, sub.unwrap_or(0.0), &mut fail) });
+        (st == sys::NA_OK).then_some(Self { chol: m })
+    }
+    pub fn l_dirty(&self) -> &DMatrix<f64> { &self.chol }
+    pub fn l(&self) -> DMatrix<f64> { self.chol.lower_triangle() }
+    /// `solve_mut` (cholesky.rs:122-129).
+    pub fn solve_mut(&self, b: &mut DMatrix<f64>) {
+        let n = self.chol.nrows();
+        assert_eq!(b.nrows(), n, "Cholesky solve matrix dimension mismatch.");
+        check(unsafe { sys::na_cholesky_solve_f64(n, self.chol.as_ptr(), n.max(1), b.as_mut_ptr(), n.max(1), b.ncols()) });
+    }
+    pub fn solve(&self, b: &DMatrix<f64>) -> DMatrix<f64> { let mut x = b.clone(); self.solve_mut(&mut x); x }
+    pub fn inverse(&self) -> DMatrix<f64> { let n = self.chol.nrows(); let mut x = DMatrix::identity(n, n); self.solve_mut(&mut x); x }
+    pub fn determinant(&self) -> f64 { let p: f64 = self.chol.diagonal().iter().product(); p * p }
+}
+
+/// `LU{lu, p}`: packed factors (strict lower = L, upper = U) and the row `PermutationSequence`.
+pub struct LU { lu: DMatrix<f64>, p: PermutationSequence<Dyn> }
+
+impl LU {
+    /// `LU::new` (lu.rs:93-122); never fails.
+    pub fn new(mut m: DMatrix<f64>) -> Self {
+        let (nr, nc) = m.shape();
+        let mn = nr.min(nc);
+        let mut swaps = vec![0usize; 2 * mn.max(1)];
+        let mut ns = 0usize;
+        check(unsafe { sys::na_lu_f64(nr, nc, m.as_mut_ptr(), nr.max(1), swaps.as_mut_ptr(), &mut ns) });
+        let mut p = PermutationSequence::identity_generic(Dyn(mn));
+        for s in 0..ns { p.append_permutation(swaps[2 * s], swaps[2 * s + 1]); }
+        Self { lu: m, p }
+    }
+    pub fn lu_internal(&self) -> &DMatrix<f64> { &self.lu }
+    pub fn p(&self) -> &PermutationSequence<Dyn> { &self.p }
+    pub fn u(&self) -> DMatrix<f64> { let mn = self.lu.nrows().min(self.lu.ncols()); self.lu.rows(0, mn).upper_triangle() }
+    pub fn l(&self) -> DMatrix<f64> {
+        let mn = self.lu.nrows().min(self.lu.ncols());
+        let mut l = self.lu.columns(0, mn).lower_triangle();
+        l.fill_diagonal(1.0);
+        l
+    }
+    /// `solve_mut` (lu.rs:242-260): `false` on an exactly-zero U[i,i] (b is then garbage, as in the reference).
+    /// The pair list is rebuilt by replaying the sequence on an index vector (nalgebra keeps `ipiv` private).
+    pub fn solve_mut(&self, b: &mut DMatrix<f64>) -> bool {
+        let n = self.lu.nrows();
+        assert_eq!(b.nrows(), n, "LU solve matrix dimension mismatch.");
+        assert!(self.lu.is_square(), "LU solve: unable to solve a non-square system.");
+        let mut idx = DVector::<f64>::from_fn(n, |i, _| i as f64);
+        self.p.permute_rows(&mut idx);
+        // recover the swaps (i, i2) in application order from the permuted index vector
+        let mut cur: Vec<usize> = (0..n).collect();
+        let mut pairs = Vec::new();
+        for i in 0..n {
+            let want = idx[i] as usize;
+            if cur[i] != want { let j = cur.iter().position(|&v| v == want).unwrap(); cur.swap(i, j); pairs.push(i); pairs.push(j); }
+        }
+        let st = check(unsafe { sys::na_lu_solve_f64(n, self.lu.as_ptr(), n.max(1), pairs.as_ptr(), pairs.len() / 2, b.as_mut_ptr(), n.max(1), b.ncols()) });
+        st != sys::NA_SINGULAR
+    }
+    pub fn solve(&self, b: &DMatrix<f64>) -> Option<DMatrix<f64>> { let mut x = b.clone(); self.solve_mut(&mut x).then_some(x) }
+    pub fn try_inverse(&self) -> Option<DMatrix<f64>> { let n = self.lu.nrows(); let mut x = DMatrix::identity(n, n); self.solve_mut(&mut x).then_some(x) }
+    pub fn determinant(&self) -> f64 { self.lu.diagonal().iter().product::<f64>() * self.p.determinant::<f64>() }
+    pub fn is_invertible(&self) -> bool { self.lu.diagonal().iter().all(|d| *d != 0.0) }
+}
+
+/// `QR{qr, diag}` in nalgebra's storage: column i, rows i.. = unit Householder axis; strict upper = R; R[i,i] = |diag[i]|.
+pub struct QR { qr: DMatrix<f64>, diag: DVector<f64> }
+
+impl QR {
+    /// `QR::new` (qr.rs:55-76); never fails.
+    pub fn new(mut m: DMatrix<f64>) -> Self {
+        let (nr, nc) = m.shape();
+        let mut diag = DVector::zeros(nr.min(nc));
+        check(unsafe { sys::na_qr_f64(nr, nc, m.as_mut_ptr(), nr.max(1), diag.as_mut_ptr()) });
+        Self { qr: m, diag }
+    }
+    pub fn qr_internal(&self) -> &DMatrix<f64> { &self.qr }
+    pub fn diag_internal(&self) -> &DVector<f64> { &self.diag }
+    pub fn r(&self) -> DMatrix<f64> {
+        let mn = self.diag.len();
+        let mut r = self.qr.rows(0, mn).upper_triangle();
+        for i in 0..mn { r[(i, i)] = self.diag[i].abs(); }
+        r
+    }
+    /// `q()` (qr.rs:108-129).
+    pub fn q(&self) -> DMatrix<f64> {
+        let (nr, nc) = self.qr.shape();
+        let mut q = DMatrix::zeros(nr, nr.min(nc));
+        check(unsafe { sys::na_qr_q_f64(nr, nc, self.qr.as_ptr(), nr.max(1), self.diag.as_ptr(), q.as_mut_ptr(), nr.max(1)) });
+        q
+    }
+    /// `q_tr_mul` (qr.rs:157-171).
+    pub fn q_tr_mul(&self, rhs: &mut DMatrix<f64>) {
+        let (nr, nc) = self.qr.shape();
+        assert_eq!(rhs.nrows(), nr);
+        check(unsafe { sys::na_qr_q_tr_mul_f64(nr, nc, self.qr.as_ptr(), nr.max(1), self.diag.as_ptr(), rhs.as_mut_ptr(), nr.max(1), rhs.ncols()) });
+    }
+    /// `solve_mut` (qr.rs:204-256): square systems; `false` when a diagonal entry of R is zero.
+    pub fn solve_mut(&self, b: &mut DMatrix<f64>) -> bool {
+        let n = self.qr.nrows();
+        assert!(self.qr.is_square(), "QR solve: unable to solve a non-square system.");
+        assert_eq!(b.nrows(), n, "QR solve matrix dimension mismatch.");
+        check(unsafe { sys::na_qr_solve_f64(n, self.qr.as_ptr(), n.max(1), self.diag.as_ptr(), b.as_mut_ptr(), n.max(1), b.ncols()) }) != sys::NA_SINGULAR
+    }
+    pub fn is_invertible(&self) -> bool { self.diag.iter().all(|d| *d != 0.0) }
+}

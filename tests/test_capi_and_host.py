@@ -132,3 +132,19 @@ def test_gemm_exchange_piece_order():
             n_local_local += classes.count(0)
         assert n_local_local > 0
 
+
+
+def test_rust_sys_crate_matches_header():
+    """rust/nalgebra-b200-sys/src/lib.rs cannot be compiled here (no cargo/rustc): at least every function it declares
+    must exist in include/nalgebra_b200.h with the same number of arguments."""
+    hdr = open(os.path.join(ROOT, "include", "nalgebra_b200.h")).read()
+    rs = open(os.path.join(ROOT, "rust", "nalgebra-b200-sys", "src", "lib.rs")).read()
+    decl = {m.group(1): m.group(2) for m in re.finditer(r"NAB_API\s+[\w\s\*]+?\b(na_\w+)\s*\(([^;]*?)\)\s*;", hdr, re.S)}
+    fns = re.findall(r"pub fn (na_\w+)\s*\(([^;]*?)\)\s*(?:->\s*[\w\*\s]+)?;", rs, re.S)
+    assert len(fns) >= 20
+    for name, args in fns:
+        assert name in decl, name
+        n_rs = 0 if not args.strip() else args.count(":")
+        c_args = decl[name].strip()
+        n_c = 0 if c_args in ("", "void") else c_args.count(",") + 1
+        assert n_rs == n_c, (name, n_rs, n_c)
