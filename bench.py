@@ -518,6 +518,26 @@ def factorization_extras(L, _capi, torch, dev, stream, N, cpu=True, e2e=True):
                          "config": "BASELINE configs[0]: 64 output tiles on 148 SMs, launch-bound"}
     del a, b, c, ha, hb, hc
 
+    # ---- f32 GEMM (matrixmultiply::sgemm's seam): tcgen05 kind::tf32, 3xTF32, TMEM accumulators
+    a = torch.rand(N * N, dtype=torch.float32, device=dev) - 0.5; b = torch.rand(N * N, dtype=torch.float32, device=dev) - 0.5
+    c = torch.empty(N * N, dtype=torch.float32, device=dev)
+    ms32, _ = dev_time(lambda: _capi.check(L.na_sgemm_dev(N, N, N, 1.0, a.data_ptr(), 1, N, b.data_ptr(), 1, N, 0.0, c.data_ptr(), 1, N, stream)), 3)
+    err32 = float((c.view(N, N).t()[:32].double() - a.view(N, N).t()[:32].double() @ b.view(N, N).t().double()).abs().max())
+    tf32_peak = None
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            tf32_peak = json.load(f)["bf16_tflops"] / 2.0          # kind::tf32 runs at half the bf16 rate; no TF32 entry in the file
+    except Exception:
+        tf32_peak = 2250.0 / 2.0
+    tf = 2.0 * N ** 3 / ms32 / 1e9
+    out["sgemm_n16384"] = {"ms": ms32, "gflops": tf * 1e3, "max_abs_err_vs_f64_sample": err32,
+                           "roofline": {"bound": "tensor", "achieved": 3.0 * tf, "peak": tf32_peak, "unit": "TFLOP/s", "frac": 3.0 * tf / tf32_peak,
+                                        "note": "3xTF32: three kind::tf32 MMAs per f32 product, so the tensor pipe does 3x the f32-equivalent flops; "
+                                                "peak = measured bf16 (MEASURED_PEAKS.json, burst) / 2; the SS-mode 128x128x8 MMA is shared-memory-bandwidth bound at ~1/2 of it"},
+                           "fp32_ffma_peak_tflops": 148 * 128 * 2 * 1.965e-3,
+                           "kernel": "sgemm_tcgen05_3xtf32_kernel (TMA + tcgen05.mma + TMEM), pack/split pass included"}
+    del a, b, c
+
     # ---- configs[2]: Cholesky
     A = torch.empty(N * N, dtype=torch.float64, device=dev)
     A0 = torch.empty(N * N, dtype=torch.float64, device=dev)

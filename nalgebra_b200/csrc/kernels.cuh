@@ -27,6 +27,10 @@ int fill_uniform(cudaStream_t s, double* a, size_t nrows, size_t ncols, size_t l
 int copy_strided(cudaStream_t s, double* dst, ptrdiff_t rsd, ptrdiff_t csd, const double* src, ptrdiff_t rss, ptrdiff_t css,
                  size_t rows, size_t cols);
 
+// ---- sgemm_tc.cu: C (column-major m x n) <- alpha*A*B + beta*C, tcgen05 kind::tf32 3xTF32; any operand strides
+int sgemm_tc_colmajor(cudaStream_t s, size_t m, size_t k, size_t n, float alpha, const float* a, ptrdiff_t rsa, ptrdiff_t csa,
+                      const float* b, ptrdiff_t rsb, ptrdiff_t csb, float beta, float* c, size_t ldc);
+
 // ---- panel_chol_tri.cu ---------------------------------------------------------------------------
 constexpr int kInvBlock = 128;     // diagonal-block size of POTF2 / TRTRI / the TRSM base case
 int potf2(cudaStream_t st, double* a, size_t lda, int n, int use_sub, double sub, size_t col0, unsigned long long* fail_col,

@@ -9,6 +9,8 @@
 #include <algorithm>
 #include <vector>
 
+#include <cstring>
+#include <cstdlib>
 #include "common.cuh"
 #include "kernels.cuh"
 
@@ -127,6 +129,17 @@ int sgemm_device(cudaStream_t s, size_t m, size_t k, size_t n, float alpha, cons
         return NA_OK;
     }
     if (m > 0x7fffff00ull || n > 0x7fffff00ull || k > 0x7fffff00ull) { set_error("sgemm: dimension exceeds 2^31"); return NA_EINVAL; }
+    // Tensor-core path (sgemm_tc.cu: TMA + tcgen05.mma kind::tf32, 3xTF32, TMEM accumulators) for everything but tiny
+    // products, where one FFMA tile kernel launch beats pack + TMA setup.  NAB_SGEMM=ffma / tc forces a path.
+    static const int force = [] { const char* e = getenv("NAB_SGEMM"); return !e ? 0 : (strcmp(e, "ffma") == 0 ? 1 : (strcmp(e, "tc") == 0 ? 2 : 0)); }();
+    const bool tiny = (double)m * (double)n * (double)k < 64.0 * 64.0 * 64.0;
+    if (force == 2 || (force == 0 && !tiny)) {
+        if (rsc == 1 && (csc >= (ptrdiff_t)m || n == 1))
+            return sgemm_tc_colmajor(s, m, k, n, alpha, a, rsa, csa, b, rsb, csb, beta, c, (size_t)(n == 1 ? std::max<ptrdiff_t>(csc, (ptrdiff_t)m) : csc));
+        if (csc == 1 && (rsc >= (ptrdiff_t)n || m == 1))       // row-major C: C^T = B^T A^T
+            return sgemm_tc_colmajor(s, n, k, m, alpha, b, csb, rsb, a, csa, rsa, beta, c, (size_t)(m == 1 ? std::max<ptrdiff_t>(rsc, (ptrdiff_t)n) : rsc));
+        // general C strides: fall through to the strided FFMA kernel (rare: views of views as the output)
+    }
     SgemmParams p;
     p.M = (int)m; p.N = (int)n; p.K = (int)k;
     p.A = a; p.rsa = rsa; p.csa = csa; p.B = b; p.rsb = rsb; p.csb = csb; p.C = c; p.rsc = rsc; p.csc = csc;
@@ -160,33 +173,53 @@ int na_sgemm(size_t m, size_t k, size_t n, float alpha, const float* a, ptrdiff_
     if ((m > 1 && rsc == 0) || (n > 1 && csc == 0)) { set_error("sgemm: c has a zero stride"); return NA_EINVAL; }
     std::lock_guard<std::mutex> lock(host_api_mutex());
     cudaStream_t s = ctx().stream;
-    // gather every operand into a dense column-major host buffer, run with unit row stride on the device
-    auto gather = [](std::vector<float>& dst, const float* src, ptrdiff_t rs, ptrdiff_t cs, size_t rows, size_t cols) {
-        dst.resize(rows * cols);
-        for (size_t j = 0; j < cols; ++j)
-            for (size_t i = 0; i < rows; ++i) dst[i + j * rows] = src[(ptrdiff_t)i * rs + (ptrdiff_t)j * cs];
+    // Unit-stride views (column- or row-major: everything nalgebra's VecStorage and its transposed views produce) are
+    // staged with one 2-D copy each and keep their strides on the device (the pack pass of the tensor-core path reads
+    // any strides); only views with two non-unit strides are gathered on the host.
+    struct StagedF {
+        Scratch buf; ptrdiff_t rs = 1, cs = 0; std::vector<float> tmp;
     };
-    std::vector<float> ha, hb, hc;
-    Scratch da, db, dc;
-    NAB_TRY(dc.alloc(m * n * sizeof(float), s));
-    if (k) {
-        gather(ha, a, rsa, csa, m, k); gather(hb, b, rsb, csb, k, n);
-        NAB_TRY(da.alloc(m * k * sizeof(float), s));
-        NAB_TRY(db.alloc(k * n * sizeof(float), s));
-        NAB_CUDA(cudaMemcpyAsync(da.p, ha.data(), m * k * sizeof(float), cudaMemcpyHostToDevice, s));
-        NAB_CUDA(cudaMemcpyAsync(db.p, hb.data(), k * n * sizeof(float), cudaMemcpyHostToDevice, s));
+    auto stage_in = [&](StagedF& st, const float* h, ptrdiff_t rs, ptrdiff_t cs, size_t rows, size_t cols, bool upload) -> int {
+        if (rs == 1 && (cs >= (ptrdiff_t)rows || cols == 1)) {
+            st.rs = 1; st.cs = (ptrdiff_t)rows;
+            NAB_TRY(st.buf.alloc(rows * cols * sizeof(float), s));
+            if (upload) NAB_CUDA(cudaMemcpy2DAsync(st.buf.p, rows * 4, h, (cols == 1 ? rows : (size_t)cs) * 4, rows * 4, cols, cudaMemcpyHostToDevice, s));
+            return NA_OK;
+        }
+        if (cs == 1 && (rs >= (ptrdiff_t)cols || rows == 1)) {
+            st.rs = (ptrdiff_t)cols; st.cs = 1;
+            NAB_TRY(st.buf.alloc(rows * cols * sizeof(float), s));
+            if (upload) NAB_CUDA(cudaMemcpy2DAsync(st.buf.p, cols * 4, h, (rows == 1 ? cols : (size_t)rs) * 4, cols * 4, rows, cudaMemcpyHostToDevice, s));
+            return NA_OK;
+        }
+        st.rs = 1; st.cs = (ptrdiff_t)rows;
+        NAB_TRY(st.buf.alloc(rows * cols * sizeof(float), s));
+        if (upload) {
+            st.tmp.resize(rows * cols);
+            for (size_t j = 0; j < cols; ++j)
+                for (size_t i = 0; i < rows; ++i) st.tmp[i + j * rows] = h[(ptrdiff_t)i * rs + (ptrdiff_t)j * cs];
+            NAB_CUDA(cudaMemcpyAsync(st.buf.p, st.tmp.data(), rows * cols * sizeof(float), cudaMemcpyHostToDevice, s));
+        }
+        return NA_OK;
+    };
+    StagedF sa, sb, sc;
+    if (k) { NAB_TRY(stage_in(sa, a, rsa, csa, m, k, true)); NAB_TRY(stage_in(sb, b, rsb, csb, k, n, true)); }
+    NAB_TRY(stage_in(sc, c, rsc, csc, m, n, beta != 0.f));        // C is not read (nor uploaded) when beta == 0
+    NAB_TRY(sgemm_device(s, m, k, n, alpha, sa.buf.as<float>(), sa.rs, sa.cs, sb.buf.as<float>(), sb.rs, sb.cs, beta,
+                         sc.buf.as<float>(), sc.rs, sc.cs));
+    if (sc.rs == 1 && rsc == 1 && (csc >= (ptrdiff_t)m || n == 1)) {
+        NAB_CUDA(cudaMemcpy2DAsync(c, (n == 1 ? m : (size_t)csc) * 4, sc.buf.p, m * 4, m * 4, n, cudaMemcpyDeviceToHost, s));
+        NAB_CUDA(cudaStreamSynchronize(s));
+    } else if (sc.cs == 1 && csc == 1) {
+        NAB_CUDA(cudaMemcpy2DAsync(c, (m == 1 ? n : (size_t)rsc) * 4, sc.buf.p, n * 4, n * 4, m, cudaMemcpyDeviceToHost, s));
+        NAB_CUDA(cudaStreamSynchronize(s));
+    } else {
+        std::vector<float> hc(m * n);
+        NAB_CUDA(cudaMemcpyAsync(hc.data(), sc.buf.p, m * n * sizeof(float), cudaMemcpyDeviceToHost, s));
+        NAB_CUDA(cudaStreamSynchronize(s));
+        for (size_t j = 0; j < n; ++j)
+            for (size_t i = 0; i < m; ++i) c[(ptrdiff_t)i * rsc + (ptrdiff_t)j * csc] = hc[i + j * m];
     }
-    if (beta != 0.f) {
-        gather(hc, c, rsc, csc, m, n);
-        NAB_CUDA(cudaMemcpyAsync(dc.p, hc.data(), m * n * sizeof(float), cudaMemcpyHostToDevice, s));
-    }
-    NAB_TRY(sgemm_device(s, m, k, n, alpha, da.as<float>(), 1, (ptrdiff_t)m, db.as<float>(), 1, (ptrdiff_t)k, beta,
-                         dc.as<float>(), 1, (ptrdiff_t)m));
-    hc.resize(m * n);
-    NAB_CUDA(cudaMemcpyAsync(hc.data(), dc.p, m * n * sizeof(float), cudaMemcpyDeviceToHost, s));
-    NAB_CUDA(cudaStreamSynchronize(s));
-    for (size_t j = 0; j < n; ++j)
-        for (size_t i = 0; i < m; ++i) c[(ptrdiff_t)i * rsc + (ptrdiff_t)j * csc] = hc[i + j * m];
     return NA_OK;
 }
 

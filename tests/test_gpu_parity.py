@@ -144,7 +144,7 @@ def test_gemm_host_pipelined_path(nab):
             assert np.abs(c - ref).max() <= gemm_tol(a, b, k), (m, k, n, alpha, beta)
 
 
-def test_sgemm_vs_oracle(nab, oracle):
+def test_sgemm_ffma_small_path_vs_oracle(nab, oracle):
     a = (oracle.uniform(130, 70, 1) - 0.5).astype(np.float32)
     b = (oracle.uniform(70, 90, 2) - 0.5).astype(np.float32)
     c0 = oracle.uniform(130, 90, 3).astype(np.float32)
@@ -778,3 +778,64 @@ def test_lapack_facade_vs_scipy(L, oracle):
     t2 = t.copy(order="F"); t2[5, 5] = 0.0; x = b.copy(order="F"); info = np.zeros(1, dtype=np.int32)
     _f(L, "dtrtrs_", b"L", b"N", b"N", n, 3, t2, n, x, n, info)
     assert info[0] == 6 and np.array_equal(x, b)
+
+
+# ---- f32 GEMM on tcgen05 (kind::tf32, 3xTF32, TMEM accumulators) ---------------------------------------------------------
+EPS32 = float(np.finfo(np.float32).eps)
+
+
+@pytest.mark.parametrize("shape", [(1, 1, 1), (2, 3, 4), (7, 5, 3), (64, 64, 64), (65, 130, 31), (128, 128, 128), (129, 257, 100),
+                                   (300, 200, 150), (513, 1000, 257), (1024, 1024, 1024)])
+@pytest.mark.parametrize("alpha,beta", [(1.0, 0.0), (1.5, 0.5)])
+def test_sgemm_tc_vs_f64_all_layouts(nab, oracle, shape, alpha, beta):
+    """na_sgemm (matrixmultiply::sgemm's seam, blas_uninit.rs:276-291) over the layout matrix of the f64 test: every
+    combination of column-/row-major A, B, C.  Gate: |C - C_f64| <= 4*k*eps32*|A||B| (north_star, f32); the 3xTF32 split
+    must in fact deliver f32-class accuracy, so a 100x tighter bound is asserted as well."""
+    m, k, n = shape
+    a64 = oracle.uniform(m, k, 1) - 0.5; b64 = oracle.uniform(k, n, 2) - 0.5; c64 = oracle.uniform(m, n, 3) - 0.5
+    a32, b32, c32 = a64.astype(np.float32), b64.astype(np.float32), c64.astype(np.float32)
+    ref = alpha * (a32.astype(np.float64) @ b32.astype(np.float64)) + (beta * c32.astype(np.float64) if beta else 0.0)
+    tol = 4 * k * EPS32 * np.linalg.norm(a32) * np.linalg.norm(b32) + 1e-30
+    for la in "FC":
+        for lb in "FC":
+            for lc in "FC":
+                a = np.array(a32, order=la); b = np.array(b32, order=lb)
+                c = np.array(c32 if beta else np.full((m, n), np.nan, dtype=np.float32), order=lc)
+                nab.gemm_f32(alpha, a, b, beta, c)
+                err = np.abs(c.astype(np.float64) - ref).max()
+                assert err <= tol, (shape, la, lb, lc, err, tol)
+                assert err <= 0.01 * tol + 8 * EPS32 * np.abs(ref).max(), (shape, la, lb, lc, err)
+
+
+def test_sgemm_tc_views_and_k_zero(nab, oracle):
+    a = (oracle.uniform(200, 300, 1) - 0.5).astype(np.float32); b = (oracle.uniform(300, 150, 2) - 0.5).astype(np.float32)
+    # strided views (every other row / column), transposed operand, negative stride
+    av, bv = a[::2, 1::2], b[1::2, ::3]
+    c = np.zeros((100, 50), dtype=np.float32, order="F")
+    nab.gemm_f32(1.0, av, bv, 0.0, c)
+    assert np.abs(c - av.astype(np.float64) @ bv.astype(np.float64)).max() <= 1e-4
+    c2 = np.zeros((100, 50), dtype=np.float32, order="F")
+    nab.gemm_f32(1.0, av[::-1], bv, 0.0, c2)
+    assert np.array_equal(c2, c[::-1])
+    c3 = np.ones((4, 5), dtype=np.float32, order="F")
+    nab.gemm_f32(1.0, np.zeros((4, 0), dtype=np.float32), np.zeros((0, 5), dtype=np.float32), 0.5, c3)
+    assert np.array_equal(c3, np.full((4, 5), 0.5, dtype=np.float32))
+
+
+def test_sgemm_tc_8192_device(L):
+    """8192^3 on the device: linearity C(2A, B) == 2 C(A, B) bit for bit (scaling by 2 is exact in every stage of the 3xTF32
+    pipeline), and a sampled comparison against float64."""
+    import torch
+    from nalgebra_b200 import _capi
+    n = 8192
+    dev = torch.device("cuda:0"); s = torch.cuda.current_stream().cuda_stream
+    A = torch.rand(n * n, dtype=torch.float32, device=dev) - 0.5; B = torch.rand(n * n, dtype=torch.float32, device=dev) - 0.5
+    Cd = torch.empty(n * n, dtype=torch.float32, device=dev); C2 = torch.empty_like(Cd)
+    _capi.check(L.na_sgemm_dev(n, n, n, 1.0, A.data_ptr(), 1, n, B.data_ptr(), 1, n, 0.0, Cd.data_ptr(), 1, n, s))
+    A2 = A * 2
+    _capi.check(L.na_sgemm_dev(n, n, n, 1.0, A2.data_ptr(), 1, n, B.data_ptr(), 1, n, 0.0, C2.data_ptr(), 1, n, s))
+    assert torch.equal(C2, Cd * 2)
+    rows = torch.arange(0, n, 997, device=dev)
+    ref = (A.view(n, n).t()[rows].double() @ B.view(n, n).t().double())          # column-major buffers viewed transposed
+    got = Cd.view(n, n).t()[rows].double()
+    assert (got - ref).abs().max().item() <= 3e-4                                 # f32-class: K accumulated in 256-wide TMEM chunks, summed in registers
