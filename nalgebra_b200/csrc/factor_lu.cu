@@ -243,9 +243,9 @@ static int lu_lookahead(LuCtx c, size_t N, size_t mn) {
         // starts when that panel is done and takes the whole GPU: the rp SMs reserved for the latency-bound
         // panel chain (~5.3 us per column whatever its height) idle only while the panel actually runs.
         const size_t x0 = jn + jbn, nx = N - x0, m2 = c.M - jn;
-        // panel duration model (per column: leaf + recursion nodes), measured per 512 columns: shared-memory leaf
-        // 2.3 .. 4.0 ms, register-resident leaf 1.4 .. 2.2 ms
-        const double t_panel = (double)jbn * (reg_leaf ? (tp0 > 0 ? tp0 : 2.7e-6) + (tp1 > 0 ? tp1 : 1.6e-6) * (double)m2 / 16384.0
+        // panel duration model (per column: leaf + in-panel updates), measured per 512 columns: shared-memory leaf
+        // 2.3 .. 4.0 ms, register-resident leaf 1.06 ms (m = 512) .. 1.8 ms (m >= 7000, where the leaf is exchange-bound)
+        const double t_panel = (double)jbn * (reg_leaf ? (tp0 > 0 ? tp0 : 2.0e-6) + (tp1 > 0 ? tp1 : 1.2e-6) * std::min(1.0, (double)m2 / 7000.0)
                                                        : 4.5e-6 + 2.5e-6 * (double)m2 / 16384.0);
         // SMs for the panel chain: what the GETF2 leaf needs at this height; more once the whole bulk update fits
         // beside the panel anyway.

@@ -42,7 +42,7 @@ struct Getf2RegParams {
     int rows_cta;                  // rows per CTA (<= 256 * RPT)
     int j0;                        // global row/col offset of the panel (for ipiv values)
     int* ipiv;                     // ipiv[j0 + c] = global pivot row of column c
-    double2* xch;                  // [2][G][W + 2] 16-byte words: 32-byte header + the candidate's row entries, by column parity
+    double2* xch;                  // [2][G][slot]: 32-byte header + 32-byte words of three row entries, by column parity
     int seq0;                      // sequence numbers already consumed in this workspace
     int* list;                     // optional: [0] = count (zeroed by the host), then dest[kRegListMax], src[kRegListMax]:
                                    // the rows this leaf moved, as global row indices ("row dest <- old row src")
@@ -71,13 +71,21 @@ __device__ __forceinline__ void lu_ld_header(const double2* p, double& x0, doubl
     asm volatile("ld.relaxed.gpu.global.v4.f64 {%0, %1, %2, %3}, [%4];" : "=d"(x0), "=d"(packed), "=d"(x1), "=d"(seq) : "l"(p) : "memory");
 }
 
+// 32-byte row word {v0, v1, v2, (double)seq}: three consecutive entries of a published candidate row
+__device__ __forceinline__ void lu_st_row3(double2* p, double v0, double v1, double v2, double seq) {
+    asm volatile("st.global.v4.f64 [%0], {%1, %2, %3, %4};" ::"l"(p), "d"(v0), "d"(v1), "d"(v2), "d"(seq) : "memory");
+}
+__device__ __forceinline__ void lu_ld_row3(const double2* p, double& v0, double& v1, double& v2, double& seq) {
+    asm volatile("ld.relaxed.gpu.global.v4.f64 {%0, %1, %2, %3}, [%4];" : "=d"(v0), "=d"(v1), "=d"(v2), "=d"(seq) : "l"(p) : "memory");
+}
+
 // warp_best with a short path: when a single lane holds the largest high key word (the usual case: distinct
 // |values|) it is the winner and its fields are fetched with independent shuffles -- one redux + one vote +
 // shuffles instead of four dependent redux operations.
 __device__ __forceinline__ void warp_best_fast(double& v, int& r, int& tag) {
     const unsigned FULL = 0xffffffffu;
-    const unsigned long long kb = v >= 0.0 ? (unsigned long long)__double_as_longlong(v) + 2ull : (v == -1.0 ? 1ull : 0ull);
-    const unsigned hi = (unsigned)(kb >> 32);
+    // keys are |x| >= 0, +inf, or the markers -1 / -2: hi32 + 2 / 1 / 0 is monotone in the key
+    const unsigned hi = v >= 0.0 ? (unsigned)__double2hiint(v) + 2u : (v == -1.0 ? 1u : 0u);
     const unsigned mhi = __reduce_max_sync(FULL, hi);
     const unsigned m = __ballot_sync(FULL, hi == mhi);
     if (__popc(m) == 1) {
@@ -88,7 +96,7 @@ __device__ __forceinline__ void warp_best_fast(double& v, int& r, int& tag) {
     }
 }
 
-// y + (-p) * l with two roundings (unfused, like the reference's axpy), as ONE opaque operation: written as separate
+// y + np * l with two roundings (unfused, like the reference's axpy), as ONE opaque operation: written as separate
 // __dmul_rn / __dadd_rn the compiler hoists all the products of a window ahead of the adds and spills.
 __device__ __forceinline__ double mul_add_unfused(double np, double l, double y) {
     double r;
@@ -98,16 +106,23 @@ __device__ __forceinline__ double mul_add_unfused(double np, double l, double y)
 
 template <int W, int RPT>
 struct Getf2Reg {
-    static constexpr int SL = W + 2;        // slot, in 16-byte words: 2 (header) + W row entries
+    static constexpr int NW3 = (W + 2) / 3;            // 32-byte row words per published row (entries 2.. of the window)
+    static constexpr int SL = 2 * (1 + NW3);           // slot, in 16-byte units: header + row words (32 bytes each)
     static constexpr int ROWS = kRegThreads * RPT;
 
     struct Smem {
-        alignas(16) double prow[2][2 * W];  // pivot row of column c in prow[c & 1][c..W); double-buffered (the next row is
-                                            // written while slow warps still read this one); [W, 2W) stays zero
-        double ret_u[W][W];                 // U rows of the pivot rows this CTA owned (row c: entries c..)
-        double lbuf[W][ROWS];               // finished multipliers: lbuf[c][row] = L(row, c)
+        // Pivot row of column c, entries c.., double-buffered by column parity (the next row is written while slow
+        // warps still read this one), and kept TWICE: prow_a[i] = entry i, prow_b[i + 1] = entry i.  The bulk update
+        // reads entries in pairs (c+3, c+4), (c+5, c+6), ...: whichever copy makes the first pair 16-byte aligned is
+        // used, so one code path serves both parities of c.
+        alignas(16) double prow_a[2][2 * W + 2];
+        alignas(16) double prow_b[2][2 * W + 2];
+        alignas(16) double zero_row[2 * W + 2];  // stands in for the pivot row of a skipped (all-zero) column
+        double stage[2][W];                     // G == 1: the candidate row, written by its owner
+        double ret_u[W][W];                     // U rows of the pivot rows this CTA owned (row c: entries c..)
+        double lbuf[W][ROWS];                   // finished multipliers: lbuf[c][row] = L(row, c)
         double red_v[8]; int red_r[8], red_t[8];                        // per-warp local candidates
-        double gred_v[8], gred_x0[8], gred_x1[8]; int gred_r[8], gred_c[8];   // per-warp partial reductions of the G headers
+        double gred_v[8], gred_x0[8], gred_x1[8], gred_inv[8]; int gred_r[8], gred_c[8];   // per-warp partial reductions of the G headers
     };
 
     const Getf2RegParams& p;
@@ -164,62 +179,73 @@ struct Getf2Reg {
             if (i == oi) lu_st_header(slot(cn, cta), x[i][0], pack_seq_row(iseq, lpos), W > 1 ? x[i][W > 1 ? 1 : 0] : 0.0, (double)iseq);
     }
 
-    // The owner of the local candidate publishes the rest of its row: window entries 2..WN-1 = columns cn+2.. (the
-    // header carries entries 0 and 1).  G == 1: entries 0.. go straight into prow.  Entries beyond column W-1 are
-    // padding and are not sent.
+    // The owner of the local candidate publishes the rest of its row.  G > 1: window entries 2.. (columns cn+2..; the
+    // header carries entries 0 and 1) as 32-byte words of three entries + the sequence number.  G == 1: entries 0..
+    // into the staging row.  Entries beyond column W-1 are padding; whole words beyond it are not sent.
     template <int WN>
     __device__ __forceinline__ void publish_row(int cn) {
         if (!is_owner()) return;
         const int oi = ltag / kRegThreads;
         const double seq = (double)(p.seq0 + cn + 1);
-        double2* my = slot(cn, cta) + 2 + cn;
-        double* pr = sm.prow[cn & 1] + cn;
+        double2* my = slot(cn, cta) + 2;
+        double* st = sm.stage[cn & 1];
         const int nvalid = W - cn;
 #pragma unroll
         for (int i = 0; i < RPT; ++i) {
             if (i != oi) continue;
+            if (G > 1) {
 #pragma unroll
-            for (int k = 0; k < WN; ++k) {
-                if (k >= nvalid) break;
-                if (G > 1) { if (k >= 2) lu_st_pair(my + k, x[i][k], seq); }
-                else pr[k] = x[i][k];
+                for (int g = 0; 2 + 3 * g < WN; ++g) {
+                    if (2 + 3 * g >= nvalid) break;
+                    const int k = 2 + 3 * g;
+                    lu_st_row3(my + 2 * g, x[i][k], k + 1 < WN ? x[i][k + 1 < WN ? k + 1 : k] : 0.0, k + 2 < WN ? x[i][k + 2 < WN ? k + 2 : k] : 0.0, seq);
+                }
+            } else {
+#pragma unroll
+                for (int k = 0; k < WN; ++k) {
+                    if (k >= nvalid) break;
+                    st[cn + k] = x[i][k];
+                }
             }
         }
     }
 
-    // Receives column c: the global winner (position gpos, CTA gcta) and its entries x0 (column c: the pivot) and
-    // x1 (column c+1).  G > 1: from the G headers, one exchange; the rest of the winner's row is fetched by step()
-    // while the latency-critical part of the column runs.
-    __device__ __forceinline__ void receive(int c, int& gpos, int& gcta, double& x0, double& x1) {
+    // Receives column c: the global winner (position gpos, CTA gcta), its entries x0 (column c: the pivot) and x1
+    // (column c+1), and inv = 1/x0 (IEEE-rounded, as gauss_step computes it; 1 when the column is skipped).  G > 1: from
+    // the G headers, one exchange; every polling thread also takes the reciprocal of the header it read, so the division
+    // overlaps the reductions instead of following them.
+    __device__ __forceinline__ void receive(int c, int& gpos, int& gcta, double& x0, double& x1, double& inv) {
         if (G > 1) {
             const unsigned FULL = 0xffffffffu;
             const int iseq = p.seq0 + c + 1;
             const double dseq = (double)iseq;
-            double gv = -2.0, h0 = 0.0, h1 = 0.0; int gr = kNoRow, gc = kNoRow;
+            double gv = -2.0, h0 = 0.0, h1 = 0.0, hi = 1.0; int gr = kNoRow, gc = kNoRow;
             if (tid < G) {
                 const double2* h = slot(c, tid);
                 double packed, s2;
                 do { lu_ld_header(h, h0, packed, h1, s2); } while ((int)(__double_as_longlong(packed) >> 32) != iseq || s2 != dseq);
                 gr = (int)(__double_as_longlong(packed) & 0xffffffffLL); gc = tid;
                 gv = gr == kNoRow ? -2.0 : pivot_key(h0, gr == c);
+                hi = h0 != 0.0 ? __drcp_rn(h0) : 1.0;
             }
             const int nw = (G + 31) >> 5;
             if (warp < nw) {
                 int src = lane;
                 warp_best_fast(gv, gr, src);                  // src = lane that read the winning header
                 src &= 31;
-                h0 = __shfl_sync(FULL, h0, src); h1 = __shfl_sync(FULL, h1, src); gc = __shfl_sync(FULL, gc, src);
-                if (lane == 0) { sm.gred_v[warp] = gv; sm.gred_r[warp] = gr; sm.gred_c[warp] = gc; sm.gred_x0[warp] = h0; sm.gred_x1[warp] = h1; }
+                h0 = __shfl_sync(FULL, h0, src); h1 = __shfl_sync(FULL, h1, src); hi = __shfl_sync(FULL, hi, src); gc = __shfl_sync(FULL, gc, src);
+                if (lane == 0) { sm.gred_v[warp] = gv; sm.gred_r[warp] = gr; sm.gred_c[warp] = gc; sm.gred_x0[warp] = h0; sm.gred_x1[warp] = h1; sm.gred_inv[warp] = hi; }
             }
             __syncthreads();
             gv = lane < nw ? sm.gred_v[lane] : -2.0; gr = lane < nw ? sm.gred_r[lane] : kNoRow;
             int src = lane;
             warp_best_fast(gv, gr, src);                      // every warp reduces the <= 5 partial winners itself
             src &= 7;
-            gpos = gr; gcta = sm.gred_c[src]; x0 = sm.gred_x0[src]; x1 = sm.gred_x1[src];
+            gpos = gr; gcta = sm.gred_c[src]; x0 = sm.gred_x0[src]; x1 = sm.gred_x1[src]; inv = sm.gred_inv[src];
         } else {
-            __syncthreads();                                  // the owner's publish_row wrote prow
-            gpos = lpos; gcta = 0; x0 = sm.prow[c & 1][c]; x1 = sm.prow[c & 1][c + 1];    // [W] is zero padding
+            __syncthreads();                                  // the owner's publish_row wrote the staging row
+            gpos = lpos; gcta = 0; x0 = sm.stage[c & 1][c]; x1 = c + 1 < W ? sm.stage[c & 1][c + 1 < W ? c + 1 : c] : 0.0;
+            inv = x0 != 0.0 ? __drcp_rn(x0) : 1.0;
         }
     }
 
@@ -227,91 +253,79 @@ struct Getf2Reg {
     template <int WIN>
     __device__ __forceinline__ void step(int c) {
         int gpos, gcta;
-        double x0, x1;
+        double x0, x1, inv;
         RPROF(0);
-        receive(c, gpos, gcta, x0, x1);
+        receive(c, gpos, gcta, x0, x1, inv);
         RPROF(1);
-        // rest of the winner's row (columns c+2..): requested now, stored to prow just before the next barrier
-        const bool rload = G > 1 && tid >= c + 2 && tid < W;
-        const double2* rp = slot(c, gcta) + 2 + tid;
+        // Rest of the winner's row (window entries 2.. = columns c+2..): requested now, stored to the two prow copies just
+        // before the next barrier.  G > 1: thread g fetches the 32-byte word g; G == 1: thread t copies staging entry c + t.
+        constexpr int NG = WIN > 2 ? (WIN - 2 + 2) / 3 : 0;
+        const int nvalid = W - c;                            // real (non-padding) window entries
+        const bool rload = G > 1 && tid < NG && 2 + 3 * tid < nvalid;
+        const double2* rp = slot(c, gcta) + 2 + 2 * tid;
         const double dseq = (double)(p.seq0 + c + 1);
-        double ra = 0.0, rs = 0.0;
-        if (rload) lu_ld_pair_raw(rp, ra, rs);
+        double r0 = 0.0, r1 = 0.0, r2 = 0.0, rs = 0.0;
+        if (rload) lu_ld_row3(rp, r0, r1, r2, rs);
         const bool elim = x0 != 0.0;                         // lu.rs:107-110: an all-zero column is skipped (then gpos == c)
         if (cta == 0 && tid == 0) p.ipiv[p.j0 + c] = p.j0 + (elim ? gpos : c);
         // The winner retires into position c: its U entries are the pivot row everybody holds (kept by the owning
         // CTA in ret_u), its L entries are already in lbuf.  The row that sat at position c moves to the winner's
         // old position.  Retired (and padding) rows keep being "updated" below -- their window is dead, so the
-        // update needs no predicate.
+        // update needs no predicate.  A skipped column runs the same code with inv = 1 and a zero pivot row
+        // (x + 0 * l = x; only the sign of a zero may differ from an untouched entry).
         double l[RPT];
-        const double inv = elim ? __drcp_rn(x0) : 1.0;       // IEEE-rounded 1/diag, as gauss_step computes it
+        const double nx1 = elim ? -x1 : 0.0;
 #pragma unroll
         for (int i = 0; i < RPT; ++i) {
             const int pi = pos[i];
             pos[i] = pi == gpos ? -2 - c : (pi == c ? gpos : pi);
-            l[i] = elim ? __dmul_rn(x[i][0], inv) : x[i][0];
+            l[i] = __dmul_rn(x[i][0], inv);
             sm.lbuf[c][i * kRegThreads + tid] = l[i];
             // column c+1 first (unfused mul/add like the reference): its candidates leave before the bulk update
-            if constexpr (WIN > 1) x[i][0] = elim ? __dadd_rn(__dmul_rn(-x1, l[i]), x[i][1]) : x[i][1];
+            if constexpr (WIN > 1) x[i][0] = __dadd_rn(__dmul_rn(nx1, l[i]), x[i][1]);
         }
         const bool more = WIN > 1 && c + 1 < ncol;
         RPROF(2);
         if (more) cand_local(c + 1);
+        double* pa = sm.prow_a[c & 1];
+        double* pb = sm.prow_b[c & 1];
         if (G > 1) {
-            if (rload) { while (rs != dseq) lu_ld_pair_raw(rp, ra, rs); sm.prow[c & 1][tid] = ra; }
-            if (tid == c) sm.prow[c & 1][c] = x0;
-            if (tid == c + 1) sm.prow[c & 1][c + 1] = c + 1 < W ? x1 : 0.0;     // c + 1 == W is the zero padding
+            if (rload) {
+                while (rs != dseq) lu_ld_row3(rp, r0, r1, r2, rs);
+                const int i0 = c + 2 + 3 * tid;
+                pa[i0] = r0; pb[i0 + 1] = r0;
+                pa[i0 + 1] = r1; pb[i0 + 2] = r1;             // entries beyond W-1 land in the padding of the 2W + 2 arrays
+                pa[i0 + 2] = r2; pb[i0 + 3] = r2;
+            }
+            if (tid == 0) { pa[c] = x0; pb[c + 1] = x0; pa[c + 1] = x1; pb[c + 2] = x1; }
+        } else if (tid < nvalid) {
+            const double v = sm.stage[c & 1][c + tid];
+            pa[c + tid] = v; pb[c + tid + 1] = v;
         }
         __syncthreads();
         if (more) cand_reduce();
-        const double* prow = sm.prow[c & 1] + c;             // prow[k] = pivot row entry of column c + k
+        const double* prow = elim ? pa + c : sm.zero_row;    // prow[k] = pivot row entry of column c + k
         if constexpr (WIN > 2) {
-            const double p2 = prow[2];
+            const double p2 = -prow[2];
 #pragma unroll
-            for (int i = 0; i < RPT; ++i) x[i][1] = elim ? __dadd_rn(__dmul_rn(-p2, l[i]), x[i][2]) : x[i][2];
+            for (int i = 0; i < RPT; ++i) x[i][1] = __dadd_rn(__dmul_rn(p2, l[i]), x[i][2]);
         }
         if (more && G > 1) publish_header(c + 1);
         RPROF(3);
-        if (gcta == cta && tid >= c && tid < W) sm.ret_u[c][tid] = prow[tid - c];
+        if (gcta == cta && tid >= c && tid < W) sm.ret_u[c][tid] = pa[tid];
         if constexpr (WIN > 3) {
-            if (elim) {
-                const uint32_t pa = (uint32_t)__cvta_generic_to_shared(prow);
-                // x[k] <- x[k+1] - prow[k+1] * l, k = 2 .. WIN-2; prow[k+1] is 16-byte aligned when c + k + 1 is even
-                if (c & 1) {
+            // x[k] <- x[k+1] - prow[k+1] * l, k = 2 .. WIN-2, the pivot row read in aligned pairs (entries c+3, c+4), ...
+            // from the copy whose alignment fits: prow_a when c + 3 is even, prow_b (shifted by one) when it is odd
+            const double2* pp = reinterpret_cast<const double2*>(!elim ? sm.zero_row : ((c & 1) ? pa + c + 3 : pb + c + 4));
 #pragma unroll
-                    for (int k = 2; k + 1 < WIN; k += 2) {
-                        double pa0, pa1;
-                        asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(pa0), "=d"(pa1) : "r"(pa + (k + 1) * 8));
+            for (int k = 2; k + 1 < WIN; k += 2) {
+                const double2 pv = pp[(k - 2) >> 1];
 #pragma unroll
-                        for (int i = 0; i < RPT; ++i) x[i][k] = __dadd_rn(__dmul_rn(-pa0, l[i]), x[i][k + 1]);
-                        if (k + 2 < WIN) {
+                for (int i = 0; i < RPT; ++i) x[i][k] = mul_add_unfused(-pv.x, l[i], x[i][k + 1]);
+                if (k + 2 < WIN) {
 #pragma unroll
-                            for (int i = 0; i < RPT; ++i) x[i][k + 1] = __dadd_rn(__dmul_rn(-pa1, l[i]), x[i][k + 2]);
-                        }
-                    }
-                } else {
-                    {
-                        const double pk = prow[3];
-#pragma unroll
-                        for (int i = 0; i < RPT; ++i) x[i][2] = __dadd_rn(__dmul_rn(-pk, l[i]), x[i][3]);
-                    }
-#pragma unroll
-                    for (int k = 3; k + 1 < WIN; k += 2) {
-                        double pa0, pa1;
-                        asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(pa0), "=d"(pa1) : "r"(pa + (k + 1) * 8));
-#pragma unroll
-                        for (int i = 0; i < RPT; ++i) x[i][k] = __dadd_rn(__dmul_rn(-pa0, l[i]), x[i][k + 1]);
-                        if (k + 2 < WIN) {
-#pragma unroll
-                            for (int i = 0; i < RPT; ++i) x[i][k + 1] = __dadd_rn(__dmul_rn(-pa1, l[i]), x[i][k + 2]);
-                        }
-                    }
+                    for (int i = 0; i < RPT; ++i) x[i][k + 1] = mul_add_unfused(-pv.y, l[i], x[i][k + 2]);
                 }
-            } else {
-#pragma unroll
-                for (int k = 2; k + 1 < WIN; ++k)
-#pragma unroll
-                    for (int i = 0; i < RPT; ++i) x[i][k] = x[i][k + 1];
             }
         }
         RPROF(4);
@@ -338,7 +352,10 @@ __global__ void __launch_bounds__(kRegThreads, 1) getf2_reg_kernel(const Getf2Re
     const int tid = threadIdx.x;
     const int r_begin = blockIdx.x * p.rows_cta;
     const int nrows = max(0, min(p.rows_cta, p.m - r_begin));
-    for (int k = tid; k < 2 * W; k += kRegThreads) { sm.prow[0][W + (k % W)] = 0.0; sm.prow[1][W + (k % W)] = 0.0; }
+    for (int k = tid; k < 2 * W + 2; k += kRegThreads) {
+        sm.prow_a[0][k] = 0.0; sm.prow_a[1][k] = 0.0; sm.prow_b[0][k] = 0.0; sm.prow_b[1][k] = 0.0; sm.zero_row[k] = 0.0;
+    }
+    __syncthreads();
     double x[RPT][W];
     int pos[RPT];
 #pragma unroll
