@@ -38,9 +38,9 @@ static int build_s_from_v(cudaStream_t s, size_t mc, size_t w, const double* v, 
 }
 
 struct QrWork {
-    Scratch tau, vw, smat, wk, csign, ws_geqr2, ws_gram;
+    Scratch tau, vw, smat, wk, csign, ws_geqr2, ws_gram, ws_larfb;
     size_t ldv = 0, lds = 0, ldw = 0;
-    int seq_state = 0;
+    int seq_state = 0, seq_larfb = 0;
     int init(cudaStream_t s, size_t m, size_t ncols_max, size_t k) {
         ldv = round_up(m, 2); lds = QR_NB; ldw = QR_NB;
         NAB_TRY(tau.alloc(std::max<size_t>(k, 1) * sizeof(double), s));
@@ -52,21 +52,31 @@ struct QrWork {
         NAB_CUDA(cudaMemsetAsync(ws_geqr2.p, 0, geqr2_workspace_bytes(), s));
         NAB_TRY(ws_gram.alloc(extract_v_gram_workspace_bytes(), s));
         NAB_CUDA(cudaMemsetAsync(ws_gram.p, 0, extract_v_gram_workspace_bytes(), s));
+        NAB_TRY(ws_larfb.alloc(larfb_fused_workspace_bytes(), s));
+        NAB_CUDA(cudaMemsetAsync(ws_larfb.p, 0, larfb_fused_workspace_bytes(), s));
         return NA_OK;
     }
 };
 
 // One outer panel: leaves of kQrLeaf columns (cooperative GEQR2), each applied to the rest of the panel as a
-// 32-wide block reflector.  vleaf / sleaf / wkleaf: leaf-level workspaces.
+// 32-wide block reflector: one fused cooperative kernel (panel_qr_fused.cu) when the leaf is tall enough for its two
+// grid-wide hand-offs to pay, the GEMM sequence otherwise.  vleaf / sleaf / wkleaf: leaf-level workspaces of the
+// latter.  max_ctas: SMs the panel chain may occupy (0 = all).
+static bool qr_fused_enabled() {
+    static bool v = [] { const char* e = getenv("NAB_QR_FUSED"); return e ? atoi(e) != 0 : true; }();
+    return v;
+}
 static int qr_panel(cudaStream_t s, QrWork& w, size_t m, double* a, size_t lda, double* tau, size_t j, size_t jb,
-                    double* vleaf, double* sleaf, double* wkleaf) {
+                    double* vleaf, double* sleaf, double* wkleaf, int max_ctas = 0) {
     const size_t W = kQrLeaf;
     for (size_t l = 0; l < jb; l += W) {
         const size_t lw = std::min(W, jb - l), jl = j + l, ml = m - jl;
         double* apanel = a + jl + jl * lda;
         NAB_TRY(geqr2_panel(s, apanel, lda, ml, lw, tau + jl, w.ws_geqr2.p, &w.seq_state));
         const size_t nc = (j + jb) - (jl + lw);          // rest of the outer panel
-        if (nc > 0) {
+        if (nc > 0 && nc <= 224 && ml >= 2048 && qr_fused_enabled()) {
+            NAB_TRY(larfb_leaf_fused(s, apanel, lda, ml, lw, nc, tau + jl, w.ws_larfb.p, &w.seq_larfb, max_ctas));
+        } else if (nc > 0) {
             NAB_TRY(extract_v_gram(s, vleaf, w.ldv, apanel, lda, ml, lw, tau + jl, sleaf, w.lds, w.ws_gram.p));
             NAB_TRY(apply_block_reflector(s, ml, lw, vleaf, w.ldv, sleaf, w.lds, true, apanel + lw * lda, lda, nc, wkleaf, w.ldw));
         }
@@ -153,7 +163,7 @@ static int qr_lookahead(cudaStream_t sp, QrWork& w, size_t m, size_t n, double* 
         if (jbn == 0) { if (nx) { cudaEventRecord(ev_u, su); bulk_pending = true; } break; }
         cudaEvent_t t_p = tr.mark(sp);
         set_gemm_sm_limit(rp);
-        st = qr_panel(sp, w, m, a, lda, tau, jn, jbn, w.vw.as<double>(), w.smat.as<double>(), w.wk.as<double>());
+        st = qr_panel(sp, w, m, a, lda, tau, jn, jbn, w.vw.as<double>(), w.smat.as<double>(), w.wk.as<double>(), rp);
         set_gemm_sm_limit(0);
         if (st != NA_OK) break;
         tr.add("panel", jn, t_p, tr.mark(sp));

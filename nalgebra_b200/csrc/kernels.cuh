@@ -74,6 +74,10 @@ int build_s(cudaStream_t st, double* g, size_t ldg, size_t w, const double* tau)
 size_t extract_v_gram_workspace_bytes();
 int extract_v_gram(cudaStream_t st, double* vw, size_t ldv, const double* a, size_t lda, size_t m, size_t w, const double* tau,
                    double* smat, size_t lds, void* ws);
+// panel_qr_fused.cu: C <- (I - V T^T V^T) C for a leaf (reflector vectors in columns [0, w) of a_leaf, C right of them), one launch
+size_t larfb_fused_workspace_bytes();
+int larfb_leaf_fused(cudaStream_t st, double* a_leaf, size_t lda, size_t ml, size_t w, size_t nc, const double* tau, void* ws, int* seq,
+                     int max_ctas);
 int tau_from_diag(cudaStream_t st, double* tau_out, const double* diag, size_t n);
 int qr_convert_to_nalgebra(cudaStream_t st, double* a, size_t lda, size_t m, size_t n, const double* tau, double* csign, double* diag);
 int qr_signs_from_diag(cudaStream_t st, const double* diag, size_t k, double* csign);
