@@ -83,7 +83,25 @@ struct CholCtx {
     double* inv;                      // [n/128][128*128] inverses of L's diagonal blocks
     unsigned long long* fail;         // device: first failing column (init ~0)
     size_t col_offset = 0;            // added to the reported failing column (block-cyclic drivers: global column)
+    const struct HostSink* sink = nullptr;   // host-pointer call: finished column blocks stream out behind the panels
 };
+
+// The host-pointer entry point hands this to the look-ahead driver: as soon as panel j is final (nothing touches the
+// columns of L left of the trailing matrix again) its lower trapezoid goes back over PCIe on a copy stream while the
+// trailing update and the next panels run.  Only the lower triangle crosses the bus, in both directions.
+struct HostSink {
+    double* h; size_t ldh;
+    cudaStream_t sc;                  // copy stream
+    cudaEvent_t ev;                   // reused: record on the compute stream, wait on the copy stream
+};
+static int sink_panel(const CholCtx& c, cudaStream_t sp, size_t n, size_t j, size_t jb) {
+    if (!c.sink) return NA_OK;
+    NAB_CUDA(cudaEventRecord(c.sink->ev, sp));
+    NAB_CUDA(cudaStreamWaitEvent(c.sink->sc, c.sink->ev, 0));
+    NAB_CUDA(cudaMemcpy2DAsync(c.sink->h + j + j * c.sink->ldh, c.sink->ldh * 8, c.a + j + j * c.lda, c.lda * 8, (n - j) * 8, jb,
+                               cudaMemcpyDeviceToHost, c.sink->sc));
+    return NA_OK;
+}
 
 static int chol_rec(const CholCtx& c, size_t j0, size_t n) {
     if (n == 0) return NA_OK;
@@ -176,6 +194,7 @@ static int chol_lookahead(const CholCtx& c, size_t n) {
     cudaEvent_t t_first = tr.mark(sp);
     if (st == NA_OK) st = chol_panel(c, sp, n, 0, std::min(NB, n), 0, tmp.as<double>(), ldt);
     tr.add("panel", 0, t_first, tr.mark(sp));
+    if (st == NA_OK) st = sink_panel(c, sp, n, 0, std::min(NB, n));
     for (size_t j = 0; st == NA_OK && j + NB < n; j += NB) {
         const size_t jb = NB, jn = j + jb, jbn = std::min(NB, n - jn);
         const double* pj = c.a + j * c.lda;               // panel j: columns [j, j+jb)
@@ -233,6 +252,8 @@ static int chol_lookahead(const CholCtx& c, size_t n) {
         st = chol_panel(c, sp, n, jn, jbn, rp, tmp.as<double>(), ldt);
         if (st != NA_OK) break;
         tr.add("panel", jn, t_p, tr.mark(sp));
+        st = sink_panel(c, sp, n, jn, jbn);
+        if (st != NA_OK) break;
         if (tr.on) fprintf(stderr, "chol_trace j=%6zu rp=%d wa=%zu rr=%zu\n", j, rp, wa, rr);
         if (rr > 0) {
             if (wa < rr) {
@@ -255,16 +276,21 @@ static int chol_lookahead(const CholCtx& c, size_t n) {
 
 // Everything but the status read-back: enqueues the factorization on `s`; the first failing column (offset by
 // col_offset) is atomicMin'ed into the device word *fail_dev, which the caller initialised to ~0.
-int cholesky_device_async(cudaStream_t s, size_t n, double* a, size_t lda, int use_sub, double sub,
-                          unsigned long long* fail_dev, size_t col_offset) {
+static int cholesky_device_async_sink(cudaStream_t s, size_t n, double* a, size_t lda, int use_sub, double sub,
+                                      unsigned long long* fail_dev, size_t col_offset, const HostSink* sink) {
     if (n == 0) return NA_OK;
     if (lda < n) { set_error("cholesky: lda < n"); return NA_EINVAL; }
     Scratch inv;
     NAB_TRY(inv.alloc(ceil_div(n, IBs) * IBs * IBs * sizeof(double), s));
-    CholCtx c{s, a, lda, use_sub, sub, inv.as<double>(), fail_dev, col_offset};
+    CholCtx c{s, a, lda, use_sub, sub, inv.as<double>(), fail_dev, col_offset, sink};
     if (n <= 2 * CHOL_NB) NAB_TRY(chol_rec(c, 0, n));
     else NAB_TRY(chol_lookahead(c, n));
     return NA_OK;
+}
+
+int cholesky_device_async(cudaStream_t s, size_t n, double* a, size_t lda, int use_sub, double sub,
+                          unsigned long long* fail_dev, size_t col_offset) {
+    return cholesky_device_async_sink(s, n, a, lda, use_sub, sub, fail_dev, col_offset, nullptr);
 }
 
 int cholesky_device(cudaStream_t s, size_t n, double* a, size_t lda, int use_sub, double sub, size_t* fail_col) {
@@ -335,13 +361,44 @@ int na_cholesky_f64(size_t n, double* a, size_t lda, int use_sub, double sub, si
     if (!a || lda < n) { set_error("cholesky: bad arguments"); return NA_EINVAL; }
     std::lock_guard<std::mutex> lock(host_api_mutex());
     cudaStream_t s = ctx().stream;
-    Scratch d; size_t ldd;
-    NAB_TRY(upload_matrix(s, d, ldd, a, lda, n, n));
-    int st = cholesky_device(s, n, d.as<double>(), ldd, use_sub, sub, fail_col);
-    if (st < 0) return st;
-    NAB_TRY(download_matrix(s, a, lda, d.as<double>(), ldd, n, n));
+    if (n <= 2 * CHOL_NB) {           // small: one upload, factor, one download
+        Scratch d; size_t ldd;
+        NAB_TRY(upload_matrix(s, d, ldd, a, lda, n, n));
+        int st = cholesky_device(s, n, d.as<double>(), ldd, use_sub, sub, fail_col);
+        if (st < 0) return st;
+        NAB_TRY(download_matrix(s, a, lda, d.as<double>(), ldd, n, n));
+        NAB_CUDA(cudaStreamSynchronize(s));
+        return st;
+    }
+    // Large: only the lower triangle crosses PCIe (the reference never reads or writes the strict upper one,
+    // cholesky.rs:221-272), as column-block trapezoids; finished panels stream back behind the factorization
+    // (overlap needs pinned host memory, na_host_alloc_pinned).
+    StreamGuard sc;
+    EventGuard ev;
+    NAB_TRY(sc.create()); NAB_TRY(ev.create());
+    Scratch d, flag;
+    const size_t ldd = round_up(n, 2), NB = CHOL_NB;
+    NAB_TRY(d.alloc(ldd * n * sizeof(double), s));
+    NAB_TRY(flag.alloc(sizeof(unsigned long long), s));
+    NAB_CUDA(cudaMemsetAsync(flag.p, 0xff, sizeof(unsigned long long), s));
+    for (size_t j = 0; j < n; j += NB) {
+        const size_t jb = std::min(NB, n - j);
+        NAB_CUDA(cudaMemcpy2DAsync(d.as<double>() + j + j * ldd, ldd * 8, a + j + j * lda, lda * 8, (n - j) * 8, jb, cudaMemcpyHostToDevice, s));
+    }
+    HostSink sink{a, lda, sc.s, ev.e};
+    {
+        const int st = cholesky_device_async_sink(s, n, d.as<double>(), ldd, use_sub, sub, flag.as<unsigned long long>(), 0, &sink);
+        if (st < 0) { cudaStreamSynchronize(s); cudaStreamSynchronize(sc.s); return st; }    // copies still read `d`
+    }
+    unsigned long long h = 0;
+    NAB_CUDA(cudaMemcpyAsync(&h, flag.p, sizeof(h), cudaMemcpyDeviceToHost, s));
     NAB_CUDA(cudaStreamSynchronize(s));
-    return st;
+    NAB_CUDA(cudaStreamSynchronize(sc.s));
+    if (h != ~0ull) {
+        if (fail_col) *fail_col = (size_t)h;
+        return NA_NOT_PD;
+    }
+    return NA_OK;
 }
 
 int na_cholesky_solve_f64_dev(size_t n, const double* l, size_t lda, double* b, size_t ldb, size_t nrhs, void* stream) {

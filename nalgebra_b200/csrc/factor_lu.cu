@@ -69,6 +69,11 @@ static size_t lu_flat() {
     return v;
 }
 
+static bool lu_rank_update_enabled() {
+    static bool v = [] { const char* e = getenv("NAB_LU_RANKK"); return e ? atoi(e) != 0 : true; }();
+    return v;
+}
+
 static int lu_swaps_from_leaf(const LuCtx& c, const int* list, size_t k0, size_t K, double* cols, size_t ncols) {
     if (ncols == 0 || K == 0) return NA_OK;
     if (list) return rowperm_apply_lists(c.s, cols, c.lda, ncols, std::min<size_t>(2 * K, kRegListMax), list, list + 1, list + 1 + kRegListMax);
@@ -93,9 +98,14 @@ static int lu_panel_flat(const LuCtx& c, size_t j0, size_t nc) {
             cudaEvent_t t2 = c.tl ? c.tl->mark(c.s) : nullptr;
             NAB_TRY(trsm_unit_lower_small(c.s, kk, akk, c.lda, a12, c.lda, n2));
             cudaEvent_t t3 = c.tl ? c.tl->mark(c.s) : nullptr;
-            if (mk > wk)
-                NAB_TRY(dgemm_device(c.s, false, mk - wk, wk, n2, -1.0, akk + wk, 1, (ptrdiff_t)c.lda, a12, 1, (ptrdiff_t)c.lda, 1.0,
-                                     a12 + wk, 1, (ptrdiff_t)c.lda));
+            if (mk > wk) {
+                // rank-wk update of the rest of the panel: streaming DMMA kernel (K <= 64 is a bandwidth problem), GEMM engine otherwise
+                int ru = lu_rank_update_enabled() ? rank_update_small_k(c.s, mk - wk, wk, n2, akk + wk, c.lda, a12, c.lda, a12 + wk, c.lda, c.getf2_limit) : 1;
+                if (ru < 0) return ru;
+                if (ru == 1)
+                    NAB_TRY(dgemm_device(c.s, false, mk - wk, wk, n2, -1.0, akk + wk, 1, (ptrdiff_t)c.lda, a12, 1, (ptrdiff_t)c.lda, 1.0,
+                                         a12 + wk, 1, (ptrdiff_t)c.lda));
+            }
             if (c.tl) {
                 cudaEvent_t t4 = c.tl->mark(c.s);
                 c.tl->add("f.swap", jk, t1, t2); c.tl->add("f.trsm", jk, t2, t3); c.tl->add("f.gemm", jk, t3, t4);
@@ -186,6 +196,12 @@ static int lu_right_update(const LuCtx& c, cudaStream_t st, size_t j, size_t jb,
     return NA_OK;
 }
 
+// most SMs the panel chain may take once the whole bulk update fits beside it (the in-panel updates scale with it)
+static int lu_rp_cap() {
+    static int v = [] { const char* e = getenv("NAB_LU_RPCAP"); return e ? atoi(e) : 112; }();
+    return v;
+}
+
 static bool lu_split() {
     static bool v = [] { const char* e = getenv("NAB_LU_SPLIT"); return e ? atoi(e) != 0 : true; }();
     return v;
@@ -252,7 +268,7 @@ static int lu_lookahead(LuCtx c, size_t N, size_t mn) {
         int rp = leaf_ctas(m2);
         {
             const double bulk_flops = 2.0 * (double)m2 * (double)jb * (double)nx;
-            for (int r = rp; r <= std::min(72, sms / 2); r += 4)
+            for (int r = rp; r <= std::min(lu_rp_cap(), sms - 16); r += 4)
                 if (bulk_flops / ((sms - r) * kSmFlops) <= t_panel) rp = r;
         }
         size_t wa = nx;

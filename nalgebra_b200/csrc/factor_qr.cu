@@ -41,6 +41,34 @@ struct QrWork {
     Scratch tau, vw, smat, wk, csign, ws_geqr2, ws_gram, ws_larfb;
     size_t ldv = 0, lds = 0, ldw = 0;
     int seq_state = 0, seq_larfb = 0;
+    // storage conversion (and, for the host-pointer call, the download) of finished outer panels on a side stream
+    StreamGuard sc;
+    EventGuard ev_c;
+    bool convert = false;             // false: the caller wants the classical form (tau_out)
+    const QrHostSink* sink = nullptr;
+    double* a = nullptr; size_t lda = 0, m = 0, n = 0, k = 0;
+    double* diag = nullptr;
+    size_t converted = 0;             // columns [0, converted) are done
+    // Panel [j, j + jb) is final and nothing reads its classical form any more (the trailing updates use the clean
+    // copy of V): convert it -- and every column left of it not yet converted -- behind the event recorded on `after`.
+    int finish_columns(cudaStream_t after, size_t upto) {
+        if (!convert || upto <= converted) return NA_OK;
+        NAB_CUDA(cudaEventRecord(ev_c, after));
+        NAB_CUDA(cudaStreamWaitEvent(sc, ev_c, 0));
+        NAB_TRY(qr_convert_columns(sc, a, lda, m, k, converted, upto - converted, tau.as<double>(), csign.as<double>(), diag));
+        if (sink)
+            NAB_CUDA(cudaMemcpy2DAsync(sink->h + converted * sink->ldh, sink->ldh * 8, a + converted * lda, lda * 8, m * 8, upto - converted,
+                                       cudaMemcpyDeviceToHost, sc));
+        converted = upto;
+        return NA_OK;
+    }
+    // the caller's stream continues after everything queued on the side stream
+    int join(cudaStream_t s) {
+        if (!convert) return NA_OK;
+        NAB_CUDA(cudaEventRecord(ev_c, sc));
+        NAB_CUDA(cudaStreamWaitEvent(s, ev_c, 0));
+        return NA_OK;
+    }
     int init(cudaStream_t s, size_t m, size_t ncols_max, size_t k) {
         ldv = round_up(m, 2); lds = QR_NB; ldw = QR_NB;
         NAB_TRY(tau.alloc(std::max<size_t>(k, 1) * sizeof(double), s));
@@ -133,6 +161,7 @@ static int qr_lookahead(cudaStream_t sp, QrWork& w, size_t m, size_t n, double* 
         const size_t jbn = jn < k ? std::min(QR_NB, k - jn) : 0;
         if (jn >= n) break;                                   // nothing right of this panel
         st = prep(j, jb, par);
+        if (st == NA_OK) st = w.finish_columns(sp, jn);       // panel j is final; the updates read the clean copy of V
         if (st != NA_OK) break;
         if (bulk_pending) cudaStreamWaitEvent(sp, ev_u, 0);
         // la(j): the next panel's columns (or, after the last panel, nothing)
@@ -191,7 +220,7 @@ static int qr_lookahead(cudaStream_t sp, QrWork& w, size_t m, size_t n, double* 
 // diag: DEVICE pointer, min(m,n) entries (nalgebra storage).  tau_out != nullptr instead: stop before the storage
 // conversion -- `a` then holds the classical / LAPACK geqrf form (R on and above the diagonal, the reflector vectors v
 // with implicit unit head below it) and tau_out (DEVICE, min(m,n)) the scalar factors.
-int qr_device(cudaStream_t s, size_t m, size_t n, double* a, size_t lda, double* diag, double* tau_out) {
+int qr_device(cudaStream_t s, size_t m, size_t n, double* a, size_t lda, double* diag, double* tau_out, const QrHostSink* sink) {
     const size_t k = std::min(m, n);
     if (k == 0) return NA_OK;
     if (lda < m) { set_error("qr: lda < m"); return NA_EINVAL; }
@@ -200,9 +229,16 @@ int qr_device(cudaStream_t s, size_t m, size_t n, double* a, size_t lda, double*
     NAB_TRY(w.init(s, m, n, k));
     double* tau = w.tau.as<double>();
     double* vw = w.vw.as<double>();
+    if (!tau_out) {
+        // nalgebra's storage is produced panel by panel on a side stream while the factorization goes on
+        NAB_TRY(w.sc.create()); NAB_TRY(w.ev_c.create());
+        w.convert = true; w.sink = sink;
+        w.a = a; w.lda = lda; w.m = m; w.n = n; w.k = k; w.diag = diag;
+    }
     auto finish = [&]() -> int {
         if (tau_out) { NAB_CUDA(cudaMemcpyAsync(tau_out, tau, k * sizeof(double), cudaMemcpyDeviceToDevice, s)); return NA_OK; }
-        return qr_convert_to_nalgebra(s, a, lda, m, n, tau, w.csign.as<double>(), diag);
+        NAB_TRY(w.finish_columns(s, n));                      // whatever is left: the last panel, columns right of min(m, n)
+        return w.join(s);
     };
     if (qr_lookahead_enabled() && k >= 4 * QR_NB && m >= 8192 && n <= m) {
         NAB_TRY(qr_lookahead(s, w, m, n, a, lda, tau, k));
@@ -216,6 +252,7 @@ int qr_device(cudaStream_t s, size_t m, size_t n, double* a, size_t lda, double*
             double* apanel = a + j + j * lda;
             NAB_TRY(extract_v(s, vw, w.ldv, apanel, lda, mj, jb, tau + j, 0));
             NAB_TRY(build_s_from_v(s, mj, jb, vw, w.ldv, tau + j, w.smat.as<double>(), w.lds));
+            NAB_TRY(w.finish_columns(s, j + jb));             // the updates below read the clean copy of V, not the panel
             NAB_TRY(apply_block_reflector(s, mj, jb, vw, w.ldv, w.smat.as<double>(), w.lds, true,
                                           apanel + jb * lda, lda, nt, w.wk.as<double>(), w.ldw));
         }
@@ -309,8 +346,10 @@ int na_qr_f64(size_t m, size_t n, double* a, size_t lda, double* diag) {
     Scratch d, dd; size_t ldd;
     NAB_TRY(upload_matrix(s, d, ldd, a, lda, m, n));
     NAB_TRY(dd.alloc(k * sizeof(double), s));
-    NAB_TRY(qr_device(s, m, n, d.as<double>(), ldd, dd.as<double>(), nullptr));
-    NAB_TRY(download_matrix(s, a, lda, d.as<double>(), ldd, m, n));
+    // finished column blocks go back over PCIe behind the factorization (overlap needs pinned host memory)
+    QrHostSink sink{a, lda};
+    const int st = qr_device(s, m, n, d.as<double>(), ldd, dd.as<double>(), nullptr, &sink);
+    if (st < 0) { cudaStreamSynchronize(s); return st; }
     NAB_CUDA(cudaMemcpyAsync(diag, dd.p, k * sizeof(double), cudaMemcpyDeviceToHost, s));
     NAB_CUDA(cudaStreamSynchronize(s));
     return NA_OK;

@@ -63,6 +63,11 @@ int iota_int(cudaStream_t st, int* p, size_t n, int offset);
 // B (n1 x nrhs, column-major) <- L^-1 B, L = unit lower triangle of l (n1 <= 128); one launch, no inverse blocks
 int trsm_unit_lower_small(cudaStream_t st, size_t n1, const double* l, size_t ldl, double* b, size_t ldb, size_t nrhs);
 
+// ---- panel_update.cu: C -= A * B for a tall C and K = 16 / 32 / 64 (bandwidth-bound; DMMA fragments from global memory).
+// Returns 1 (nothing done) for other K; max_ctas = SMs it may occupy (0 = all)
+int rank_update_small_k(cudaStream_t st, size_t m, size_t k, size_t n, const double* a, size_t lda, const double* b, size_t ldb, double* c,
+                        size_t ldc, int max_ctas);
+
 // ---- panel_qr.cu ---------------------------------------------------------------------------------
 constexpr int kQrLeaf = 32;        // GEQR2 leaf panel width
 size_t geqr2_workspace_bytes();
@@ -80,6 +85,8 @@ int larfb_leaf_fused(cudaStream_t st, double* a_leaf, size_t lda, size_t ml, siz
                      int max_ctas);
 int tau_from_diag(cudaStream_t st, double* tau_out, const double* diag, size_t n);
 int qr_convert_to_nalgebra(cudaStream_t st, double* a, size_t lda, size_t m, size_t n, const double* tau, double* csign, double* diag);
+int qr_convert_columns(cudaStream_t st, double* a, size_t lda, size_t m, size_t k, size_t j0, size_t ncols, const double* tau, double* csign,
+                       double* diag);
 int qr_signs_from_diag(cudaStream_t st, const double* diag, size_t k, double* csign);
 int scale_signs(cudaStream_t st, double* b, size_t ldb, size_t rows, size_t cols, const double* csign, size_t k, bool by_cols);
 
@@ -94,7 +101,9 @@ int cholesky_device(cudaStream_t s, size_t n, double* a, size_t lda, int use_sub
 int cholesky_solve_device(cudaStream_t s, size_t n, const double* l, size_t lda, double* b, size_t ldb, size_t nrhs);
 int lu_device(cudaStream_t s, size_t M, size_t N, double* a, size_t lda, size_t* swaps, size_t* nswaps);
 int lu_device_async(cudaStream_t s, size_t M, size_t N, double* a, size_t lda, int* ipiv_dev);
-int qr_device(cudaStream_t s, size_t m, size_t n, double* a, size_t lda, double* diag, double* tau_out);
+// sink (optional): host matrix that receives every column block as soon as it is final (host-pointer entry point)
+struct QrHostSink { double* h; size_t ldh; };
+int qr_device(cudaStream_t s, size_t m, size_t n, double* a, size_t lda, double* diag, double* tau_out, const QrHostSink* sink = nullptr);
 int apply_q_blocks(cudaStream_t s, size_t m, size_t k, const double* qr, size_t lda, const double* diag,
                    double* b, size_t ldb, size_t nb, bool forward, bool triangular_q, const double* lapack_tau);
 int upload_matrix(cudaStream_t s, Scratch& buf, size_t& ldd, const double* h, size_t ldh, size_t rows, size_t cols);

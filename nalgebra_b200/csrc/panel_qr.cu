@@ -469,18 +469,44 @@ int tau_from_diag(cudaStream_t st, double* tau_out, const double* diag, size_t n
 // Storage conversion (classical -> nalgebra) and sign bookkeeping.
 // csign[i] = c_i for i = 0..k (c_0 = 1; c_{i+1} = sign(beta_i) when reflected else c_i).
 // ------------------------------------------------------------------------------------------------
-__global__ void qr_signs_from_beta_kernel(const double* __restrict__ a, long long lda, const double* __restrict__ tau, int k,
-                                          double* __restrict__ csign, double* __restrict__ diag) {
-    if (blockIdx.x == 0 && threadIdx.x == 0) {
-        double c = 1.0;
-        csign[0] = c;
-        for (int i = 0; i < k; ++i) {
-            const double beta = a[i + (long long)i * lda];
-            const bool refl = tau[i] != 0.0;
-            diag[i] = refl ? c * beta : 0.0;
-            if (refl) c = (beta < 0.0) ? -1.0 : 1.0;
-            csign[i + 1] = c;
+// One CTA: beta_i / tau_i are fetched by all threads a chunk at a time (a single thread walking the diagonal pays one
+// L2 round trip per column: 850 us at k = 4096), thread 0 runs the sign recurrence over the chunk in shared memory,
+// then all threads form diag.
+constexpr int kSignChunk = 2048;
+// Columns [j0, j0 + k): the sign entering column j0 is csign[j0] (1 for j0 == 0), left there by the previous call.
+__global__ void __launch_bounds__(1024) qr_signs_from_beta_kernel(const double* __restrict__ a, long long lda, const double* __restrict__ tau, int j0, int k,
+                                                                  double* __restrict__ csign, double* __restrict__ diag) {
+    __shared__ double beta_s[kSignChunk];
+    __shared__ signed char refl_s[kSignChunk];
+    __shared__ double c_s[kSignChunk + 1];
+    __shared__ double carry;
+    if (threadIdx.x == 0) {
+        if (j0 == 0) csign[0] = 1.0;
+        carry = j0 == 0 ? 1.0 : csign[j0];
+    }
+    __syncthreads();
+    for (int i0 = j0; i0 < j0 + k; i0 += kSignChunk) {
+        const int n = min(kSignChunk, j0 + k - i0);
+        for (int t = threadIdx.x; t < n; t += blockDim.x) {
+            beta_s[t] = a[(i0 + t) + (long long)(i0 + t) * lda];
+            refl_s[t] = tau[i0 + t] != 0.0;
         }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            double c = carry;
+            c_s[0] = c;
+            for (int t = 0; t < n; ++t) {
+                if (refl_s[t]) c = (beta_s[t] < 0.0) ? -1.0 : 1.0;
+                c_s[t + 1] = c;
+            }
+            carry = c;
+        }
+        __syncthreads();
+        for (int t = threadIdx.x; t < n; t += blockDim.x) {
+            diag[i0 + t] = refl_s[t] ? c_s[t] * beta_s[t] : 0.0;
+            csign[i0 + t + 1] = c_s[t + 1];
+        }
+        __syncthreads();
     }
 }
 // csign from nalgebra's diag: c_{i+1} = c_i * signum(diag_i) when diag_i != 0 else c_i.
@@ -494,32 +520,50 @@ __global__ void qr_signs_from_diag_kernel(const double* __restrict__ diag, int k
         }
     }
 }
-__global__ void qr_convert_kernel(double* __restrict__ a, long long lda, long long m, long long n, int k,
-                                  const double* __restrict__ tau, const double* __restrict__ csign, const double* __restrict__ diag) {
-    const long long total = m * n;
-    for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
-        const long long i = idx % m, j = idx / m;
-        double* e = a + i + j * lda;
-        if (i >= j) {                      // axis part of column j (j < k guaranteed since i < m, j <= i)
-            if (j >= k) continue;
-            const double t = tau[j];
-            if (t == 0.0) { *e = 0.0; continue; }
-            const double f = ((diag[j] < 0.0) ? 1.0 : -1.0) * sqrt(0.5 * t);      // -sign(diag_j)*sqrt(tau/2)
-            *e = (i == j) ? f : f * *e;
+// grid = (row blocks of 2048, columns): eight rows per thread, loads before stores, no 64-bit divisions
+__global__ void __launch_bounds__(256) qr_convert_kernel(double* __restrict__ a, long long lda, long long m, long long j0, int k,
+                                                         const double* __restrict__ tau, const double* __restrict__ csign, const double* __restrict__ diag) {
+    const long long j = j0 + blockIdx.y;
+    const long long i0 = (long long)blockIdx.x * 2048 + threadIdx.x;
+    double* col = a + j * lda;
+    const bool has_axis = j < k;
+    const double t = has_axis ? tau[j] : 0.0;
+    const double f = has_axis && t != 0.0 ? ((diag[j] < 0.0) ? 1.0 : -1.0) * sqrt(0.5 * t) : 0.0;      // -sign(diag_j)*sqrt(tau/2)
+    double v[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) { const long long i = i0 + 256 * u; v[u] = i < m ? col[i] : 0.0; }
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+        const long long i = i0 + 256 * u;
+        if (i >= m) continue;
+        if (i >= j) {                      // axis part of column j
+            if (!has_axis) continue;
+            col[i] = (t == 0.0) ? 0.0 : (i == j ? f : f * v[u]);
         } else {                           // strict upper: row i < k
-            *e = csign[i + 1] * *e;
+            col[i] = csign[i + 1] * v[u];
         }
     }
 }
-int qr_convert_to_nalgebra(cudaStream_t st, double* a, size_t lda, size_t m, size_t n, const double* tau, double* csign, double* diag) {
-    const size_t k = std::min(m, n);
-    if (k == 0) return NA_OK;
-    qr_signs_from_beta_kernel<<<1, 32, 0, st>>>(a, (long long)lda, tau, (int)k, csign, diag);
-    NAB_LAUNCH_CHECK();
-    qr_convert_kernel<<<(int)std::min<size_t>(ceil_div(m * n, 256), (size_t)ctx().sm_count * 16), 256, 0, st>>>(
-        a, (long long)lda, (long long)m, (long long)n, (int)k, tau, csign, diag);
-    NAB_LAUNCH_CHECK();
+// Columns [j0, j0 + ncols) of the classical storage -> nalgebra's, all rows.  The columns must be final, and so must
+// csign[0 .. min(j0 + ncols, k)] -- call this panel by panel, left to right (each call extends csign / diag by the
+// reflectors among its columns).  k = min(m, n) of the whole matrix.
+int qr_convert_columns(cudaStream_t st, double* a, size_t lda, size_t m, size_t k, size_t j0, size_t ncols, const double* tau, double* csign,
+                       double* diag) {
+    if (ncols == 0 || m == 0) return NA_OK;
+    if (j0 < k) {
+        qr_signs_from_beta_kernel<<<1, 1024, 0, st>>>(a, (long long)lda, tau, (int)j0, (int)(std::min(k, j0 + ncols) - j0), csign, diag);
+        NAB_LAUNCH_CHECK();
+    }
+    for (size_t c0 = j0; c0 < j0 + ncols; c0 += 65535) {            // gridDim.y limit
+        const size_t ncol = std::min<size_t>(65535, j0 + ncols - c0);
+        qr_convert_kernel<<<dim3((unsigned)ceil_div(m, (size_t)2048), (unsigned)ncol), 256, 0, st>>>(
+            a, (long long)lda, (long long)m, (long long)c0, (int)k, tau, csign, diag);
+        NAB_LAUNCH_CHECK();
+    }
     return NA_OK;
+}
+int qr_convert_to_nalgebra(cudaStream_t st, double* a, size_t lda, size_t m, size_t n, const double* tau, double* csign, double* diag) {
+    return qr_convert_columns(st, a, lda, m, std::min(m, n), 0, n, tau, csign, diag);
 }
 int qr_signs_from_diag(cudaStream_t st, const double* diag, size_t k, double* csign) {
     qr_signs_from_diag_kernel<<<1, 32, 0, st>>>(diag, (int)k, csign);

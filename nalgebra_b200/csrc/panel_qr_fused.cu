@@ -22,8 +22,8 @@
 #include <algorithm>
 
 #include "common.cuh"
+#include "dmma_stream.cuh"
 #include "kernels.cuh"
-#include "ptx.cuh"
 
 namespace nab {
 
@@ -59,8 +59,18 @@ __device__ __forceinline__ void flag_wait(const int* f, int v) {
 // Both products run on the FP64 tensor pipe (mma.sync m8n8k4, ptx::dmma884) with fragments loaded straight from global
 // memory: a fragment is 4 consecutive rows x 8 columns (or 8 rows x 4 columns), i.e. whole 32-byte sectors, so no
 // shared-memory staging and no barrier inside the streaming loops.
+#ifdef NAB_LARFB_PROF
+__device__ long long g_larfb_prof[16];
+#define LF_T(i) do { __syncthreads(); if (threadIdx.x == 0 && blockIdx.x == 1) { long long t_ = clock64(); atomicAdd((unsigned long long*)&g_larfb_prof[i], (unsigned long long)(t_ - lf_t0)); lf_t0 = t_; } } while (0)
+#else
+#define LF_T(i) do { } while (0)
+#endif
+
 __global__ void __launch_bounds__(lf::T, 1) larfb_leaf_fused_kernel(const LarfbParams p) {
     using namespace lf;
+#ifdef NAB_LARFB_PROF
+    long long lf_t0 = clock64();
+#endif
     extern __shared__ __align__(16) double sm[];
     double* red = sm;                                // phase 1: [8 warps][W][RLD] partial tiles
     double* Ws = sm;                                 // later:   [W][NCXP] totals, then X
@@ -72,22 +82,43 @@ __global__ void __launch_bounds__(lf::T, 1) larfb_leaf_fused_kernel(const LarfbP
     const int G = gridDim.x, cta = blockIdx.x;
     const int w = p.w, nc = p.nc, ncx = nc + W;
     const long long lda = p.lda;
-    const int rows_w = p.rows_cta >> 3;              // rows per warp, multiple of 8
-    const int rw0 = cta * p.rows_cta + warp * rows_w;
-    const int rw_n = max(0, min(rows_w, p.ml - rw0));   // valid rows of this warp's slice
+    const int r_cta = cta * p.rows_cta;                              // the CTA's slab of rows
+    const int slab_n = max(0, min(p.rows_cta, p.ml - r_cta));        // valid rows in it
     if (tid < W) tau_s[tid] = tid < w ? p.tau[tid] : 0.0;
     __syncthreads();
-    const bool top = rw0 < W;                        // the slice touches the triangle above the reflectors' unit heads
+    const bool top = cta == 0;                       // the slab holds the triangle above the reflectors' unit heads
     const double* vbase = p.a;
     double* cbase = p.a + (long long)w * lda;
 
-    // ---- phase 1: partial [W | G] = V^T [C | V] over this CTA's rows; warp = row slice, loop over 32-column groups
+    // ---- phase 1: partial [W | G] = V^T [C | V] over this CTA's rows, one 32-column group of [C | V] at a time.  The
+    // slab is cut into 16-row batches (four DMMA k-steps), warp w taking batches w, w + 8, ...: the CTA reads 128
+    // consecutive rows of the same columns at a time.  A batch (16 V + 16 C fragment loads per thread) is in flight while
+    // the previous one is in the tensor pipe; the first batch of the next group is requested before the cross-warp
+    // reduction of the current one.
     {
         bool nz[4];                                  // reflector 8 mt + g8 is present (tau != 0)
 #pragma unroll
         for (int mt = 0; mt < 4; ++mt) nz[mt] = tau_s[8 * mt + g8] != 0.0;
         const int n_cg = (nc + 31) >> 5;             // groups of C columns; group n_cg is V itself
         double* mypart = p.part + (size_t)cta * (W * NCX);
+        const double* vq = vbase + r_cta + q4 + (long long)g8 * lda;
+        const double* cq = cbase + r_cta + q4 + (long long)g8 * lda;
+        const int r_first = 16 * warp;
+        double cav[4][4], cbv[4][4], nav[4][4], nbv[4][4];
+        auto load_batch = [&](double (&av)[4][4], double (&bv)[4][4], int grp, int r0) {
+            const bool vgrp = grp == n_cg;
+#pragma unroll
+            for (int s4 = 0; s4 < 4; ++s4) {
+                const int r = r0 + 4 * s4;
+                const bool rok = r + q4 < slab_n;
+#pragma unroll
+                for (int mt = 0; mt < 4; ++mt) av[s4][mt] = (rok && nz[mt]) ? vq[r + (long long)(8 * mt) * lda] : 0.0;
+#pragma unroll
+                for (int nt = 0; nt < 4; ++nt)
+                    bv[s4][nt] = (rok && !vgrp && 32 * grp + 8 * nt + g8 < nc) ? __ldcg(cq + r + (long long)(32 * grp + 8 * nt) * lda) : 0.0;
+            }
+        };
+        load_batch(cav, cbv, 0, r_first);
         for (int grp = 0; grp <= n_cg; ++grp) {
             double acc[4][4][2];
 #pragma unroll
@@ -95,34 +126,32 @@ __global__ void __launch_bounds__(lf::T, 1) larfb_leaf_fused_kernel(const LarfbP
 #pragma unroll
                 for (int nt = 0; nt < 4; ++nt) acc[mt][nt][0] = acc[mt][nt][1] = 0.0;
             const bool vgrp = grp == n_cg;
-            const double* cg = cbase + (long long)(32 * grp + g8) * lda;
-            bool cok[4];
+            for (int r0 = r_first; r0 < slab_n; r0 += 128) {
+                if (r0 + 128 < slab_n) load_batch(nav, nbv, grp, r0 + 128);
+                else if (!vgrp) load_batch(nav, nbv, grp + 1, r_first);
 #pragma unroll
-            for (int nt = 0; nt < 4; ++nt) cok[nt] = !vgrp && 32 * grp + 8 * nt + g8 < nc;
-#pragma unroll 2
-            for (int r = 0; r < rw_n; r += 4) {
-                const int row = rw0 + r + q4;
-                const bool rok = r + q4 < rw_n;
-                double av[4], bv[4];
+                for (int s4 = 0; s4 < 4; ++s4) {
+                    if (top && r0 < W) {
+                        const int row = r0 + 4 * s4 + q4;
 #pragma unroll
-                for (int mt = 0; mt < 4; ++mt) av[mt] = (rok && nz[mt]) ? vbase[row + (long long)(8 * mt + g8) * lda] : 0.0;
-#pragma unroll
-                for (int nt = 0; nt < 4; ++nt) bv[nt] = (rok && cok[nt]) ? cg[row + (long long)(8 * nt) * lda] : 0.0;
-                if (top) {
-#pragma unroll
-                    for (int mt = 0; mt < 4; ++mt) {
-                        const int col = 8 * mt + g8;
-                        if (row < col) av[mt] = 0.0; else if (row == col) av[mt] = nz[mt] ? 1.0 : 0.0;
+                        for (int mt = 0; mt < 4; ++mt) {
+                            const int col = 8 * mt + g8;
+                            if (row < col) cav[s4][mt] = 0.0; else if (row == col) cav[s4][mt] = nz[mt] ? 1.0 : 0.0;
+                        }
                     }
+                    if (vgrp) {
+#pragma unroll
+                        for (int nt = 0; nt < 4; ++nt) cbv[s4][nt] = cav[s4][nt];
+                    }
+#pragma unroll
+                    for (int mt = 0; mt < 4; ++mt)
+#pragma unroll
+                        for (int nt = 0; nt < 4; ++nt) ptx::dmma884(acc[mt][nt][0], acc[mt][nt][1], cav[s4][mt], cbv[s4][nt]);
                 }
-                if (vgrp) {
 #pragma unroll
-                    for (int nt = 0; nt < 4; ++nt) bv[nt] = av[nt];
-                }
+                for (int s4 = 0; s4 < 4; ++s4)
 #pragma unroll
-                for (int mt = 0; mt < 4; ++mt)
-#pragma unroll
-                    for (int nt = 0; nt < 4; ++nt) ptx::dmma884(acc[mt][nt][0], acc[mt][nt][1], av[mt], bv[nt]);
+                    for (int t = 0; t < 4; ++t) { cav[s4][t] = nav[s4][t]; cbv[s4][t] = nbv[s4][t]; }
             }
             // the eight warps' tiles are added in warp order
             double* mine = red + warp * (W * RLD);
@@ -144,6 +173,7 @@ __global__ void __launch_bounds__(lf::T, 1) larfb_leaf_fused_kernel(const LarfbP
             __syncthreads();
         }
     }
+    LF_T(0);
     // ---- hand-off 1: publish the partial, then CTA g sums slice g of all partials in CTA order (four quarter sums
     // of consecutive CTAs, added in order: a fixed summation shape for a given grid)
     if (tid == 0) flag_set(p.flags + cta, p.seq);
@@ -183,6 +213,7 @@ __global__ void __launch_bounds__(lf::T, 1) larfb_leaf_fused_kernel(const LarfbP
         __syncthreads();
         if (tid == 0) flag_set(p.flags + G + cta, p.seq);
     }
+    LF_T(1);
     // ---- hand-off 2: everybody takes the totals once every reducer is done
     if (tid < G) flag_wait(p.flags + G + tid, p.seq);
     __syncthreads();
@@ -191,6 +222,7 @@ __global__ void __launch_bounds__(lf::T, 1) larfb_leaf_fused_kernel(const LarfbP
         Ws[i * NCXP + c] = __ldcg(p.total + i * NCX + c);
     }
     __syncthreads();
+    LF_T(2);
     // ---- phase 3: S = triu(G, 1) + diag(1 / tau) (tau = 0 -> 1: that column of V is zero); solve S^T X = W
     for (int idx = tid; idx < W * W; idx += T) {
         const int i = idx >> 5, j = idx & 31;
@@ -215,56 +247,30 @@ __global__ void __launch_bounds__(lf::T, 1) larfb_leaf_fused_kernel(const LarfbP
         for (int i = 0; i < W; ++i) Ws[i * NCXP + tid] = xv[i];
     }
     __syncthreads();
-    // ---- phase 4: C -= V X on the warp's row slice, 8-row tiles, last rows first (the most recently read lines are
-    // the likeliest L2 hits); 8 column tiles (16 loads per thread) in flight while the previous batch is in the pipe
+    LF_T(3);
+    // ---- phase 4: C -= V X on the warp's row slice (dmma_stream.cuh), last rows first: the most recently read lines
+    // are the likeliest L2 hits
     {
         bool nzk[8];                                 // reflector 4 ks + q4 present
 #pragma unroll
         for (int ks = 0; ks < 8; ++ks) nzk[ks] = tau_s[4 * ks + q4] != 0.0;
-        const int ntiles = (nc + 7) >> 3, nbatch = (ntiles + 7) >> 3;
-        for (int r = ((rw_n + 7) & ~7) - 8; r >= 0; r -= 8) {
-            const int row = rw0 + r + g8;
-            const bool rok = r + g8 < rw_n;
-            double na[8];                            // -V(row, 4 ks + q4)
+        const double* vrow = vbase + r_cta + g8 + (long long)q4 * lda;
+        auto load_a = [&](double (&na)[8], int r) {
+            const bool rok = r + g8 < slab_n;
 #pragma unroll
-            for (int ks = 0; ks < 8; ++ks) na[ks] = (rok && nzk[ks]) ? -vbase[row + (long long)(4 * ks + q4) * lda] : 0.0;
-            if (top) {
+            for (int ks = 0; ks < 8; ++ks) na[ks] = (rok && nzk[ks]) ? -vrow[r + (long long)(4 * ks) * lda] : 0.0;
+            if (top && r < W) {
+                const int row = r + g8;
 #pragma unroll
                 for (int ks = 0; ks < 8; ++ks) {
                     const int col = 4 * ks + q4;
                     if (row < col) na[ks] = 0.0; else if (row == col) na[ks] = nzk[ks] ? -1.0 : 0.0;
                 }
             }
-            double* crow = cbase + row + (long long)(2 * q4) * lda;
-            double cur[8][2], nxt[8][2];
-            auto load = [&](double (&dst)[8][2], int b) {
-#pragma unroll
-                for (int t = 0; t < 8; ++t) {
-                    const int c = 8 * (8 * b + t) + 2 * q4;
-                    dst[t][0] = (rok && c < nc) ? crow[(long long)(8 * (8 * b + t)) * lda] : 0.0;
-                    dst[t][1] = (rok && c + 1 < nc) ? crow[(long long)(8 * (8 * b + t) + 1) * lda] : 0.0;
-                }
-            };
-            load(cur, 0);
-            for (int b = 0; b < nbatch; ++b) {
-                if (b + 1 < nbatch) load(nxt, b + 1);
-#pragma unroll
-                for (int t = 0; t < 8; ++t) {
-                    const double* xb = Ws + q4 * NCXP + 8 * (8 * b + t) + g8;      // columns < 256 + 4: inside the padded rows
-#pragma unroll
-                    for (int ks = 0; ks < 8; ++ks) ptx::dmma884(cur[t][0], cur[t][1], na[ks], xb[(4 * ks) * NCXP]);
-                }
-#pragma unroll
-                for (int t = 0; t < 8; ++t) {
-                    const int c = 8 * (8 * b + t) + 2 * q4;
-                    if (rok && c < nc) crow[(long long)(8 * (8 * b + t)) * lda] = cur[t][0];
-                    if (rok && c + 1 < nc) crow[(long long)(8 * (8 * b + t) + 1) * lda] = cur[t][1];
-                }
-#pragma unroll
-                for (int t = 0; t < 8; ++t) { cur[t][0] = nxt[t][0]; cur[t][1] = nxt[t][1]; }
-            }
-        }
+        };
+        dmma_stream_update<8, NCXP, true>(cbase + r_cta, lda, slab_n, nc, Ws, lane, warp, T / 32, load_a);
     }
+    LF_T(4);
 }
 
 constexpr size_t kLarfbMaxCtas = 160;
@@ -303,3 +309,11 @@ int larfb_leaf_fused(cudaStream_t st, double* a_leaf, size_t lda, size_t ml, siz
 }
 
 }  // namespace nab
+
+#if defined(NAB_LARFB_PROF) && defined(NAB_DEBUG_HOOKS)   // debug build only (nalgebra_b200/build.py)
+extern "C" __attribute__((visibility("default"))) int na_debug_larfb_prof(long long* out, int reset) {
+    cudaMemcpyFromSymbol(out, nab::g_larfb_prof, sizeof(long long) * 16);
+    if (reset) { long long z[16] = {0}; cudaMemcpyToSymbol(nab::g_larfb_prof, z, sizeof(z)); }
+    return 0;
+}
+#endif
