@@ -193,6 +193,23 @@ NAB_API int na_qr_q_tr_mul_f64_dev(size_t m, size_t n, const double* qr, size_t 
 /* QR::solve_mut (qr.rs:204-256), square only.  NA_SINGULAR == `false` (a zero in diag). */
 NAB_API int na_qr_solve_f64(size_t n, const double* qr, size_t lda, const double* diag, double* b, size_t ldb, size_t nrhs);
 
+/* ---- seam 2: the factorizations that pivot on the largest entry of the trailing matrix ------------ */
+/* FullPivLU::new (src/linalg/full_piv_lu.rs:56-91): P A Q = L U.  Pivot of step i = icamax_full of the trailing
+ * matrix (src/base/min_max.rs:146-167: column-major scan, strict >); whole columns and whole rows are swapped, the
+ * elimination is lu::gauss_step(_swap) (IEEE reciprocal, unfused multiply-add), so `a` and both sequences are
+ * bit-identical to the reference's.  An exactly zero pivot stops the factorization (:73-76).  p_swaps / q_swaps: room for
+ * 2*min(m,n) entries each, PermutationSequence pairs (i, i2) with i != i2 only, unused entries 0. */
+NAB_API int na_full_piv_lu_f64(size_t m, size_t n, double* a, size_t lda, size_t* p_swaps, size_t* np, size_t* q_swaps, size_t* nq);
+/* a: DEVICE; the four outputs are HOST pointers; synchronises `stream` before returning. */
+NAB_API int na_full_piv_lu_f64_dev(size_t m, size_t n, double* a, size_t lda, size_t* p_swaps, size_t* np, size_t* q_swaps, size_t* nq,
+                                   void* stream);
+/* ColPivQR::new (src/linalg/col_piv_qr.rs:56-93): A P = Q R, the pivot column of step i is the column of icamax_full of the
+ * trailing matrix; storage as na_qr_f64 (unit Householder axes below the diagonal, diag = signed norms), so na_qr_q_f64 /
+ * na_qr_q_tr_mul_f64 apply to it unchanged.  p_swaps: room for 2*min(m,n) entries. */
+NAB_API int na_col_piv_qr_f64(size_t m, size_t n, double* a, size_t lda, double* diag, size_t* p_swaps, size_t* np);
+/* a, diag: DEVICE; p_swaps / np: HOST; synchronises `stream` before returning. */
+NAB_API int na_col_piv_qr_f64_dev(size_t m, size_t n, double* a, size_t lda, double* diag, size_t* p_swaps, size_t* np, void* stream);
+
 /* ---- triangular solves (src/linalg/solve.rs:55-182) ---------------------------------------- */
 /* op(T) x = b in place on b (n x nrhs).  lower: 1 = lower, 0 = upper triangle of `t` is used.
  * trans: 0 = T, 1 = T^T.  unit_diag: 1 = implicit unit diagonal (solve_lower_triangular_with_diag_mut

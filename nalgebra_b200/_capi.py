@@ -58,6 +58,10 @@ SIGNATURES = {
     "na_qr_q_tr_mul_f64": (_int, [_sz, _sz, _p, _sz, _p, _p, _sz, _sz]),
     "na_qr_q_tr_mul_f64_dev": (_int, [_sz, _sz, _p, _sz, _p, _p, _sz, _sz, _p]),
     "na_qr_solve_f64": (_int, [_sz, _p, _sz, _p, _p, _sz, _sz]),
+    "na_full_piv_lu_f64": (_int, [_sz, _sz, _p, _sz, _p, _p, _p, _p]),
+    "na_full_piv_lu_f64_dev": (_int, [_sz, _sz, _p, _sz, _p, _p, _p, _p, _p]),
+    "na_col_piv_qr_f64": (_int, [_sz, _sz, _p, _sz, _p, _p, _p]),
+    "na_col_piv_qr_f64_dev": (_int, [_sz, _sz, _p, _sz, _p, _p, _p, _p]),
     "na_set_gemm_sm_limit": (_int, [_int]),
     "na_trsm_f64_dev": (_int, [_int, _int, _int, _int, _sz, _sz, _p, _sz, _p, _sz, _p]),
     "na_permute_rows_f64_dev": (_int, [_sz, _p, _sz, _sz, _p, _sz, _int, _p]),

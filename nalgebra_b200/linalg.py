@@ -490,6 +490,173 @@ class QR:
 
 
 # ---------------------------------------------------------------------------------------------
+# FullPivLU  (src/linalg/full_piv_lu.rs)
+# ---------------------------------------------------------------------------------------------
+class FullPivLU:
+    """``FullPivLU{lu, p, q}``: P * matrix * Q = L U, packed like ``LU``; ``p`` row and ``q`` column swaps."""
+
+    def __init__(self, lu: np.ndarray, p: PermutationSequence, q: PermutationSequence):
+        self.lu, self._p, self._q = lu, p, q
+
+    @classmethod
+    def new(cls, matrix) -> "FullPivLU":                              # :56-91
+        m = _owned(matrix)
+        nrows, ncols = m.shape
+        mn = min(nrows, ncols)
+        ps = np.zeros(2 * max(mn, 1), dtype=np.uint64); qs = np.zeros(2 * max(mn, 1), dtype=np.uint64)
+        np_, nq = C.c_size_t(0), C.c_size_t(0)
+        check(_capi.lib().na_full_piv_lu_f64(nrows, ncols, m.ctypes.data, max(nrows, 1), ps.ctypes.data, C.addressof(np_),
+                                             qs.ctypes.data, C.addressof(nq)))
+        return cls(m, PermutationSequence(ps[: 2 * np_.value].copy(), mn), PermutationSequence(qs[: 2 * nq.value].copy(), mn))
+
+    def lu_internal(self) -> np.ndarray:                              # :94
+        return self.lu
+
+    def l(self) -> np.ndarray:                                        # :101-111
+        m, n = self.lu.shape
+        mn = min(m, n)
+        return np.asfortranarray(np.tril(self.lu[:, :mn], -1) + np.eye(m, mn))
+
+    def u(self) -> np.ndarray:                                        # :115-122
+        m, n = self.lu.shape
+        return np.asfortranarray(np.triu(self.lu[: min(m, n), :]))
+
+    def p(self) -> PermutationSequence:                               # :126
+        return self._p
+
+    def q(self) -> PermutationSequence:                               # :133
+        return self._q
+
+    def unpack(self):                                                 # :139-155
+        return self._p, self.l(), self.u(), self._q
+
+    def is_invertible(self) -> bool:                                  # :238-246
+        if self.lu.shape[0] != self.lu.shape[1]:
+            raise ValueError("FullPivLU: unable to test the invertibility of a non-square matrix.")
+        dim = self.lu.shape[0]
+        return bool(self.lu[dim - 1, dim - 1] != 0.0)
+
+    def solve_mut(self, b: np.ndarray) -> bool:                       # :189-215
+        n = self.lu.shape[0]
+        if b.shape[0] != n:
+            raise ValueError("FullPivLU solve matrix dimension mismatch.")
+        if self.lu.shape[0] != self.lu.shape[1]:
+            raise ValueError("FullPivLU solve: unable to solve a non-square system.")
+        if not self.is_invertible():
+            return False
+        x = _owned(b)
+        self._p.permute_rows(x)
+        lib = _capi.lib()
+        check(lib.na_tri_solve_f64(1, 0, 1, n, self.lu.ctypes.data, max(n, 1), x.ctypes.data, max(n, 1), x.shape[1]))
+        check(lib.na_tri_solve_f64(0, 0, 0, n, self.lu.ctypes.data, max(n, 1), x.ctypes.data, max(n, 1), x.shape[1]))
+        self._q.inv_permute_rows(x)
+        b[...] = x.reshape(b.shape, order="F")
+        return True
+
+    def solve(self, b):                                               # :168-183
+        res = np.array(b, dtype=np.float64, order="F", copy=True)
+        return res if self.solve_mut(res) else None
+
+    def try_inverse(self):                                            # :220-234
+        if self.lu.shape[0] != self.lu.shape[1]:
+            raise ValueError("FullPivLU inverse: unable to compute the inverse of a non-square matrix.")
+        res = np.asfortranarray(np.eye(self.lu.shape[0]))
+        return res if self.solve_mut(res) else None
+
+    def determinant(self) -> float:                                   # :250-270
+        if self.lu.shape[0] != self.lu.shape[1]:
+            raise ValueError("FullPivLU determinant: unable to compute the determinant of a non-square matrix.")
+        dim = self.lu.shape[0]
+        res = float(self.lu[dim - 1, dim - 1])
+        if res == 0.0:
+            return 0.0
+        for i in range(dim - 1):
+            res *= float(self.lu[i, i])
+        return res * self._p.determinant() * self._q.determinant()
+
+
+# ---------------------------------------------------------------------------------------------
+# ColPivQR  (src/linalg/col_piv_qr.rs)
+# ---------------------------------------------------------------------------------------------
+class ColPivQR:
+    """``ColPivQR{col_piv_qr, p, diag}``: matrix * P = Q R, storage as ``QR``."""
+
+    def __init__(self, col_piv_qr: np.ndarray, p: PermutationSequence, diag: np.ndarray):
+        self.col_piv_qr, self._p, self.diag = col_piv_qr, p, diag
+
+    @classmethod
+    def new(cls, matrix) -> "ColPivQR":                               # :59-93
+        m = _owned(matrix)
+        nrows, ncols = m.shape
+        mn = min(nrows, ncols)
+        diag = np.zeros(max(mn, 1))
+        ps = np.zeros(2 * max(mn, 1), dtype=np.uint64)
+        np_ = C.c_size_t(0)
+        check(_capi.lib().na_col_piv_qr_f64(nrows, ncols, m.ctypes.data, max(nrows, 1), diag.ctypes.data, ps.ctypes.data, C.addressof(np_)))
+        return cls(m, PermutationSequence(ps[: 2 * np_.value].copy(), mn), diag[:mn].copy())
+
+    def col_piv_qr_internal(self) -> np.ndarray:                      # :176
+        return self.col_piv_qr
+
+    def r(self) -> np.ndarray:                                        # :97-108
+        m, n = self.col_piv_qr.shape
+        mn = min(m, n)
+        res = np.triu(self.col_piv_qr[:mn, :])
+        res[np.arange(mn), np.arange(mn)] = np.abs(self.diag)
+        return np.asfortranarray(res)
+
+    unpack_r = r
+
+    def q(self) -> np.ndarray:                                        # :129-150
+        return QR(self.col_piv_qr, self.diag).q()
+
+    def p(self) -> PermutationSequence:                               # :154
+        return self._p
+
+    def unpack(self):                                                 # :159-173
+        return self.q(), self.r(), self._p
+
+    def q_tr_mul(self, rhs: np.ndarray) -> None:                      # :181-199
+        QR(self.col_piv_qr, self.diag).q_tr_mul(rhs)
+
+    def is_invertible(self) -> bool:                                  # :307-320
+        if self.col_piv_qr.shape[0] != self.col_piv_qr.shape[1]:
+            raise ValueError("ColPivQR: unable to test the invertibility of a non-square matrix.")
+        return bool(np.all(self.diag != 0.0))
+
+    def solve_mut(self, b: np.ndarray) -> bool:                       # :227-247
+        n = self.col_piv_qr.shape[0]
+        if b.shape[0] != n:
+            raise ValueError("ColPivQR solve matrix dimension mismatch.")
+        if self.col_piv_qr.shape[0] != self.col_piv_qr.shape[1]:
+            raise ValueError("ColPivQR solve: unable to solve a non-square system.")
+        x = _owned(b)
+        st = check(_capi.lib().na_qr_solve_f64(n, self.col_piv_qr.ctypes.data, max(n, 1), np.ascontiguousarray(self.diag).ctypes.data,
+                                               x.ctypes.data, max(n, 1), x.shape[1]))
+        self._p.inv_permute_rows(x)
+        b[...] = x.reshape(b.shape, order="F")
+        return st != NA_SINGULAR
+
+    def solve(self, b):                                               # :205-221
+        res = np.array(b, dtype=np.float64, order="F", copy=True)
+        return res if self.solve_mut(res) else None
+
+    def try_inverse(self):                                            # :288-303
+        if self.col_piv_qr.shape[0] != self.col_piv_qr.shape[1]:
+            raise ValueError("ColPivQR inverse: unable to compute the inverse of a non-square matrix.")
+        res = np.asfortranarray(np.eye(self.col_piv_qr.shape[0]))
+        return res if self.solve_mut(res) else None
+
+    def determinant(self) -> float:                                   # :324-337
+        if self.col_piv_qr.shape[0] != self.col_piv_qr.shape[1]:
+            raise ValueError("ColPivQR determinant: unable to compute the determinant of a non-square matrix.")
+        res = 1.0
+        for d in self.diag:
+            res *= float(d)
+        return res * self._p.determinant()
+
+
+# ---------------------------------------------------------------------------------------------
 # triangular solves  (src/linalg/solve.rs)
 # ---------------------------------------------------------------------------------------------
 def _tri_solve(t, b, lower: bool, trans: bool, unit: bool):

@@ -72,6 +72,10 @@ def lib() -> C.CDLL:
         _lib.na_oracle_try_invert_f64.restype = _int
         _lib.na_oracle_qr_f64.argtypes = [_sz, _sz, _p, _sz, _p]
         _lib.na_oracle_qr_f64.restype = None
+        _lib.na_oracle_full_piv_lu_f64.argtypes = [_sz, _sz, _p, _sz, _p, _p, _p, _p]
+        _lib.na_oracle_full_piv_lu_f64.restype = None
+        _lib.na_oracle_col_piv_qr_f64.argtypes = [_sz, _sz, _p, _sz, _p, _p, _p]
+        _lib.na_oracle_col_piv_qr_f64.restype = None
         _lib.na_oracle_qr_q_f64.argtypes = [_sz, _sz, _p, _sz, _p, _p, _sz]
         _lib.na_oracle_qr_q_f64.restype = None
         _lib.na_oracle_qr_r_f64.argtypes = [_sz, _sz, _p, _sz, _p, _p, _sz]
@@ -251,6 +255,28 @@ def qr(a):
     diag = np.zeros(max(min(m, n), 1))
     lib().na_oracle_qr_f64(m, n, _ptr(a), max(m, 1), _ptr(diag))
     return a, diag[: min(m, n)]
+
+
+def full_piv_lu(a):
+    """``FullPivLU::new``: returns (packed lu, p swaps, q swaps) -- swaps as (len, 2) uint64 arrays."""
+    a = _f(a)
+    m, n = a.shape
+    mn = min(m, n)
+    ps = np.zeros(2 * max(mn, 1), dtype=np.uint64); qs = np.zeros(2 * max(mn, 1), dtype=np.uint64)
+    np_, nq = C.c_size_t(0), C.c_size_t(0)
+    lib().na_oracle_full_piv_lu_f64(m, n, _ptr(a), max(m, 1), _ptr(ps), C.addressof(np_), _ptr(qs), C.addressof(nq))
+    return a, ps[: 2 * np_.value].reshape(-1, 2).copy(), qs[: 2 * nq.value].reshape(-1, 2).copy()
+
+
+def col_piv_qr(a):
+    """``ColPivQR::new``: returns (packed col_piv_qr, diag, p swaps)."""
+    a = _f(a)
+    m, n = a.shape
+    mn = min(m, n)
+    diag = np.zeros(max(mn, 1)); ps = np.zeros(2 * max(mn, 1), dtype=np.uint64)
+    np_ = C.c_size_t(0)
+    lib().na_oracle_col_piv_qr_f64(m, n, _ptr(a), max(m, 1), _ptr(diag), _ptr(ps), C.addressof(np_))
+    return a, diag[:mn], ps[: 2 * np_.value].reshape(-1, 2).copy()
 
 
 def qr_q(qr_packed, diag):

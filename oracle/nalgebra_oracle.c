@@ -568,3 +568,70 @@ int na_oracle_qr_solve_f64(size_t n, const double* qr, size_t lda, const double*
     }
     return 1;
 }
+
+/* ------------------------------------------------------------------------------------------ */
+/* Factorizations that pivot on the largest entry of the trailing matrix                        */
+/* ------------------------------------------------------------------------------------------ */
+
+/* src/base/min_max.rs:146-167: column-major scan, strict >, first maximum wins. */
+static void icamax_full(size_t m, size_t n, const double* a, size_t lda, size_t* pi, size_t* pj) {
+    double the_max = fabs(a[0]);
+    size_t bi = 0, bj = 0;
+    for (size_t j = 0; j < n; ++j)
+        for (size_t i = 0; i < m; ++i) {
+            double val = fabs(A_(a, lda, i, j));
+            if (val > the_max) { the_max = val; bi = i; bj = j; }
+        }
+    *pi = bi; *pj = bj;
+}
+
+/* src/base/edition.rs swap_columns: whole columns. */
+static void swap_columns(double* a, size_t lda, size_t nrows, size_t c1, size_t c2) {
+    if (c1 == c2) return;
+    for (size_t i = 0; i < nrows; ++i) { double t = A_(a, lda, i, c1); A_(a, lda, i, c1) = A_(a, lda, i, c2); A_(a, lda, i, c2) = t; }
+}
+
+/* src/linalg/full_piv_lu.rs:56-91.  p / q: PermutationSequence pairs (append_permutation keeps i != i2 only). */
+void na_oracle_full_piv_lu_f64(size_t m, size_t n, double* a, size_t lda, size_t* p_swaps, size_t* np, size_t* q_swaps, size_t* nq) {
+    size_t mn = m < n ? m : n, lp = 0, lq = 0;
+    for (size_t i = 0; i < 2 * mn; ++i) { p_swaps[i] = 0; q_swaps[i] = 0; }
+    for (size_t i = 0; i < mn; ++i) {
+        size_t pi, pj;
+        icamax_full(m - i, n - i, &A_(a, lda, i, i), lda, &pi, &pj);              /* :69 */
+        size_t row_piv = pi + i, col_piv = pj + i;
+        double diag = A_(a, lda, row_piv, col_piv);
+        if (diag == 0.0) break;                                                   /* :73-76 */
+        swap_columns(a, lda, m, i, col_piv);                                      /* :78 */
+        if (i != col_piv) { q_swaps[2 * lq] = i; q_swaps[2 * lq + 1] = col_piv; ++lq; }
+        if (row_piv != i) {
+            p_swaps[2 * lp] = i; p_swaps[2 * lp + 1] = row_piv; ++lp;             /* :82 */
+            swap_rows(a, lda, i, i, row_piv);                                     /* :83 columns ..i */
+            gauss_step(m, n, a, lda, diag, i, row_piv, 1);
+        } else {
+            gauss_step(m, n, a, lda, diag, i, row_piv, 0);
+        }
+    }
+    *np = lp; *nq = lq;
+}
+
+/* src/linalg/col_piv_qr.rs:56-93 -> householder.rs:61-85 (shift = 0, bilateral = None). */
+void na_oracle_col_piv_qr_f64(size_t m, size_t n, double* a, size_t lda, double* diag, size_t* p_swaps, size_t* np) {
+    size_t mn = m < n ? m : n, lp = 0;
+    for (size_t i = 0; i < 2 * mn; ++i) p_swaps[i] = 0;
+    for (size_t i = 0; i < mn; ++i) {
+        size_t pi, pj;
+        icamax_full(m - i, n - i, &A_(a, lda, i, i), lda, &pi, &pj);              /* :74 */
+        size_t col_piv = pj + i;
+        swap_columns(a, lda, m, i, col_piv);                                      /* :76 */
+        if (i != col_piv) { p_swaps[2 * lp] = i; p_swaps[2 * lp + 1] = col_piv; ++lp; }
+        int not_zero;
+        double* axis = &A_(a, lda, i, i);
+        double refl_norm = reflection_axis_mut(m - i, axis, &not_zero);
+        if (not_zero) {
+            double sign = signum(refl_norm);
+            if (i + 1 < n) reflect_with_sign(m - i, axis, &A_(a, lda, i, i + 1), lda, n - i - 1, sign);
+        }
+        diag[i] = refl_norm;
+    }
+    *np = lp;
+}

@@ -96,6 +96,11 @@ int na_oracle_solve_lower_f64(size_t n, const double* a, size_t lda, double* b, 
 int na_oracle_solve_upper_f64(size_t n, const double* a, size_t lda, double* b, size_t ldb, size_t nrhs);
 int na_oracle_solve_lower_with_diag_f64(size_t n, const double* a, size_t lda, double diag, double* b, size_t ldb, size_t nrhs);
 
+/* src/linalg/full_piv_lu.rs:56-91 (icamax_full: src/base/min_max.rs:146-167).  p_swaps / q_swaps: 2*min(m,n) entries each. */
+void na_oracle_full_piv_lu_f64(size_t m, size_t n, double* a, size_t lda, size_t* p_swaps, size_t* np, size_t* q_swaps, size_t* nq);
+/* src/linalg/col_piv_qr.rs:56-93.  Storage as na_oracle_qr_f64. */
+void na_oracle_col_piv_qr_f64(size_t m, size_t n, double* a, size_t lda, double* diag, size_t* p_swaps, size_t* np);
+
 #ifdef __cplusplus
 }
 #endif
