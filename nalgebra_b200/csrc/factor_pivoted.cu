@@ -28,7 +28,7 @@ namespace nab {
 namespace pv {
 constexpr int T = 256;
 
-struct Cand { double key; long long pos; };          // key: |value| (-1: can never win); pos = row + col * m (column-major order)
+struct Cand { double key; long long pos; double val; };   // key: |value| (-1: can never win); pos = row + col * m (column-major order); val: the entry itself
 
 // icamax_full's rule: strict > in a column-major scan = the largest key, the lowest position among equals.  NaN never
 // compares greater, so it only "wins" when it is the first element scanned (then nothing replaces it): first_nan_key.
@@ -40,38 +40,40 @@ __device__ __forceinline__ double cand_key(double v, bool first) {
 __device__ __forceinline__ bool cand_better(double k1, long long p1, double k2, long long p2) {
     return k1 > k2 || (k1 == k2 && p1 < p2);
 }
-__device__ __forceinline__ void warp_best(double& k, long long& p) {
+__device__ __forceinline__ void warp_best(double& k, long long& p, double& v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
         const double k2 = __shfl_xor_sync(0xffffffffu, k, o);
         const long long p2 = __shfl_xor_sync(0xffffffffu, p, o);
-        if (cand_better(k2, p2, k, p)) { k = k2; p = p2; }
+        const double v2 = __shfl_xor_sync(0xffffffffu, v, o);
+        if (cand_better(k2, p2, k, p)) { k = k2; p = p2; v = v2; }
     }
 }
 // CTA-wide winner -> cand[cta]
-__device__ __forceinline__ void block_publish(double k, long long p, Cand* cand, double* sk, long long* sp) {
+__device__ __forceinline__ void block_publish(double k, long long p, double v, Cand* cand, double* sk, long long* sp) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    warp_best(k, p);
-    if (lane == 0) { sk[warp] = k; sp[warp] = p; }
+    double* sv = sk + T / 32;
+    warp_best(k, p, v);
+    if (lane == 0) { sk[warp] = k; sp[warp] = p; sv[warp] = v; }
     __syncthreads();
     if (warp == 0) {
-        k = lane < T / 32 ? sk[lane] : -2.0; p = lane < T / 32 ? sp[lane] : 0x7fffffffffffffffll;
-        warp_best(k, p);
-        if (lane == 0) { cand[blockIdx.x].key = k; cand[blockIdx.x].pos = p; }
+        k = lane < T / 32 ? sk[lane] : -2.0; p = lane < T / 32 ? sp[lane] : 0x7fffffffffffffffll; v = lane < T / 32 ? sv[lane] : 0.0;
+        warp_best(k, p, v);
+        if (lane == 0) { cand[blockIdx.x].key = k; cand[blockIdx.x].pos = p; cand[blockIdx.x].val = v; }
     }
     __syncthreads();
 }
 // every CTA: the same winner out of the G candidates (after a grid barrier)
-__device__ __forceinline__ long long grid_winner(const Cand* cand, int G, long long* s_pos) {
+__device__ __forceinline__ long long grid_winner(const Cand* cand, int G, long long* s_pos, double* s_val) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     if (warp == 0) {
-        double k = -2.0; long long p = 0x7fffffffffffffffll;
+        double k = -2.0, v = 0.0; long long p = 0x7fffffffffffffffll;
         for (int g = lane; g < G; g += 32) {
             const double k2 = __ldcg(&cand[g].key); const long long p2 = __ldcg(&cand[g].pos);
-            if (cand_better(k2, p2, k, p)) { k = k2; p = p2; }
+            if (cand_better(k2, p2, k, p)) { k = k2; p = p2; v = __ldcg(&cand[g].val); }
         }
-        warp_best(k, p);
-        if (lane == 0) *s_pos = p;
+        warp_best(k, p, v);
+        if (lane == 0) { *s_pos = p; *s_val = v; }
     }
     __syncthreads();
     return *s_pos;
@@ -84,19 +86,25 @@ struct PivotedParams {
     int* p_col;            // [min(m,n)] pivot column of step i
     double* diag;          // [min(m,n)] ColPivQR: signed norms
     pv::Cand* cand;        // [G]
-    double* hh;            // ColPivQR: [4] scalars of the current reflector (sign, not_zero), published by CTA 0
+    double* hh;            // ColPivQR: [2][2] (sign, reflected) of the current reflector by step parity, published by CTA 0
     int* steps_done;       // FullPivLU: number of elimination steps before an exactly zero pivot stopped it
 };
 
 // ------------------------------------------------------------------------------------------------------------------
-// FullPivLU
+// FullPivLU.  Two grid barriers per step:
+//   phase S: the column swap i <-> pc and the row swap i <-> pr in one go (rows outside {i, pr} of the two columns,
+//            columns outside {i, pc} of the two rows, and the four corner elements by one thread), plus the scaling of
+//            the PREVIOUS pivot column by its reciprocal pivot (its unscaled entries were what the update read);
+//   phase U: rank-1 update of the trailing matrix in the reference's arithmetic fused with the search for the next
+//            pivot; a candidate carries its signed value, so the pivot never has to be read back from the matrix.
 // ------------------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(pv::T, 1) full_piv_lu_kernel(const PivotedParams p) {
     using namespace pv;
     cg::grid_group grid = cg::this_grid();
-    __shared__ double sk[T / 32];
+    __shared__ double sk[2 * (T / 32)];
     __shared__ long long sp[T / 32];
     __shared__ long long s_pos;
+    __shared__ double s_val;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int G = gridDim.x, cta = blockIdx.x;
     const int m = p.m, n = p.n, mn = min(m, n);
@@ -107,66 +115,87 @@ __global__ void __launch_bounds__(pv::T, 1) full_piv_lu_kernel(const PivotedPara
 
     // pivot of step 0: the whole matrix
     {
-        double bk = -2.0; long long bp = 0x7fffffffffffffffll;
+        double bk = -2.0, bv = 0.0; long long bp = 0x7fffffffffffffffll;
         for (int j = gwarp; j < n; j += nwarps)
             for (int r = lane; r < m; r += 32) {
-                const double k = cand_key(a[r + j * lda], r == 0 && j == 0);
+                const double x = a[r + j * lda];
+                const double k = cand_key(x, r == 0 && j == 0);
                 const long long pos = r + (long long)j * m;
-                if (cand_better(k, pos, bk, bp)) { bk = k; bp = pos; }
+                if (cand_better(k, pos, bk, bp)) { bk = k; bp = pos; bv = x; }
             }
-        block_publish(bk, bp, p.cand, sk, sp);
+        block_publish(bk, bp, bv, p.cand, sk, sp);
     }
     grid.sync();
     int i = 0;
+    double inv_prev = 1.0;                                          // reciprocal pivot of step i - 1
     for (; i < mn; ++i) {
-        const long long pos = grid_winner(p.cand, G, &s_pos);
+        const long long pos = grid_winner(p.cand, G, &s_pos, &s_val);
         const int pr = (int)(pos % m), pc = (int)(pos / m);
-        const double diag = a[pr + pc * lda];                       // still unswapped: nobody writes before the barrier below
+        const double diag = s_val;                                  // the candidate carries the entry: no read-back, no barrier
         if (diag == 0.0) break;                                     // full_piv_lu.rs:73-76: the rest of the matrix is zero
         if (gtid == 0) { p.p_row[i] = pr; p.p_col[i] = pc; }
-        grid.sync();                                                // everyone holds diag before the swaps move it
-        // ---- phase A: whole columns i <-> pc (full_piv_lu.rs:78)
+        // ---- phase S
         if (pc != i)
             for (long long r = gtid; r < m; r += nthreads) {
+                if (r == i || r == pr) continue;
                 const double t = a[r + i * lda]; a[r + i * lda] = a[r + pc * lda]; a[r + pc * lda] = t;
             }
+        for (long long j = gtid; j < n; j += nthreads) {
+            if (j == i || j == pc) continue;
+            double t1 = a[i + j * lda], t2 = a[pr + j * lda];
+            if (j == i - 1) { t1 = __dmul_rn(t1, inv_prev); t2 = __dmul_rn(t2, inv_prev); }      // multipliers of step i - 1
+            if (pr != i) { a[i + j * lda] = t2; a[pr + j * lda] = t1; }
+            else if (j == i - 1) a[i + j * lda] = t1;
+        }
+        if (gtid == nthreads - 1) {                                 // the corners: column swap, then row swap
+            const double oii = a[i + i * lda], oip = a[i + pc * lda], opi = a[pr + i * lda], opp = a[pr + pc * lda];
+            a[i + i * lda] = opp; a[i + pc * lda] = opi; a[pr + i * lda] = oip; a[pr + pc * lda] = oii;
+        }
+        if (i > 0)
+            for (long long r = i + 1 + gtid; r < m; r += nthreads)
+                if (r != pr) a[r + (i - 1) * lda] = __dmul_rn(a[r + (i - 1) * lda], inv_prev);
         grid.sync();
-        // ---- phase B: rows i <-> pr in every column (columns ..i: swap_rows, full_piv_lu.rs:82; columns i..: gauss_step_swap)
-        if (pr != i)
-            for (long long j = gtid; j < n; j += nthreads) {
-                const double t = a[i + j * lda]; a[i + j * lda] = a[pr + j * lda]; a[pr + j * lda] = t;
-            }
-        grid.sync();
-        // ---- phase C: multipliers (one warp group writes them), rank-1 update of the trailing matrix in the reference's
-        // arithmetic, and the search for the next pivot in the same pass
+        // ---- phase U: eight rows per lane in flight
         const double inv_diag = 1.0 / diag;                         // lu.rs:345
-        const double* ci = a + i * lda;                             // column i, unscaled until the end of this phase
-        double bk = -2.0; long long bp = 0x7fffffffffffffffll;
+        const double* ci = a + i * lda;                             // column i: unscaled until the next phase S
+        double bk = -2.0, bv = 0.0; long long bp = 0x7fffffffffffffffll;
         for (int j = i + 1 + gwarp; j < n; j += nwarps) {
             double* cj = a + j * lda;
             const double npiv = -cj[i];                             // -pivot_row[k]   (lu.rs:353-356)
-            for (int r = i + 1 + lane; r < m; r += 32) {
-                const double coeff = __dmul_rn(ci[r], inv_diag);    // coeffs *= inv_diag (the stored value, recomputed)
-                const double v = __dadd_rn(__dmul_rn(npiv, coeff), cj[r]);   // axpy: a * x + y, never fused
-                cj[r] = v;
-                const double k = cand_key(v, r == i + 1 && j == i + 1);
-                const long long pos2 = r + (long long)j * m;
-                if (cand_better(k, pos2, bk, bp)) { bk = k; bp = pos2; }
+            for (int r0 = i + 1 + lane; r0 < m; r0 += 256) {
+                double x[8], y[8];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) { const int r = r0 + 32 * u; x[u] = r < m ? ci[r] : 0.0; y[u] = r < m ? cj[r] : 0.0; }
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    const int r = r0 + 32 * u;
+                    if (r < m) {
+                        const double coeff = __dmul_rn(x[u], inv_diag);                  // coeffs *= inv_diag (the value the reference stores)
+                        const double v = __dadd_rn(__dmul_rn(npiv, coeff), y[u]);        // axpy: a * x + y, never fused
+                        cj[r] = v;
+                        const double k = cand_key(v, r == i + 1 && j == i + 1);
+                        const long long pos2 = r + (long long)j * m;
+                        if (cand_better(k, pos2, bk, bp)) { bk = k; bp = pos2; bv = v; }
+                    }
+                }
             }
         }
-        block_publish(bk, bp, p.cand, sk, sp);
-        grid.sync();                                                // all reads of the unscaled column i are done
-        for (long long r = i + 1 + gtid; r < m; r += nthreads) a[r + i * lda] = __dmul_rn(a[r + i * lda], inv_diag);
-        // (no barrier needed here: the next step's phases A/B only start after its own first grid.sync, and the winner
-        // reduction above reads cand[], which nobody writes until the next phase C)
+        block_publish(bk, bp, bv, p.cand, sk, sp);
+        inv_prev = inv_diag;
+        grid.sync();
     }
+    // the last pivot column's multipliers
+    if (i > 0)
+        for (long long r = i + gtid; r < m; r += nthreads) a[r + (i - 1) * lda] = __dmul_rn(a[r + (i - 1) * lda], inv_prev);
     if (gtid == 0) *p.steps_done = i;
-    // steps that never happened: identity
-    for (long long s = i + gtid; s < mn; s += nthreads) { p.p_row[s] = (int)s; p.p_col[s] = (int)s; }
+    for (long long s = i + gtid; s < mn; s += nthreads) { p.p_row[s] = (int)s; p.p_col[s] = (int)s; }      // steps that never happened
 }
 
 // ------------------------------------------------------------------------------------------------------------------
-// ColPivQR
+// ColPivQR.  Two grid barriers per step:
+//   phase H: CTA 0 turns the pivot column (still at its old place pc) into the unit axis of the reflection, written to
+//            column i while the old column i moves to pc; the other CTAs swap the finished rows ..i of the two columns;
+//   phase R: reflection of the columns right of i fused with the search for the next pivot.
 // ------------------------------------------------------------------------------------------------------------------
 __device__ __forceinline__ double block_sum(double v, double* sred) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -184,9 +213,10 @@ __device__ __forceinline__ double block_sum(double v, double* sred) {
 __global__ void __launch_bounds__(pv::T, 1) col_piv_qr_kernel(const PivotedParams p) {
     using namespace pv;
     cg::grid_group grid = cg::this_grid();
-    __shared__ double sk[T / 32];
+    __shared__ double sk[2 * (T / 32)];
     __shared__ long long sp[T / 32];
     __shared__ long long s_pos;
+    __shared__ double s_val;
     __shared__ double sred[T / 32];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int G = gridDim.x, cta = blockIdx.x;
@@ -196,82 +226,139 @@ __global__ void __launch_bounds__(pv::T, 1) col_piv_qr_kernel(const PivotedParam
     const int gwarp = cta * (T / 32) + warp, nwarps = G * (T / 32);
     const long long gtid = (long long)cta * T + tid, nthreads = (long long)G * T;
     {
-        double bk = -2.0; long long bp = 0x7fffffffffffffffll;
+        double bk = -2.0, bv = 0.0; long long bp = 0x7fffffffffffffffll;
         for (int j = gwarp; j < n; j += nwarps)
             for (int r = lane; r < m; r += 32) {
-                const double k = cand_key(a[r + j * lda], r == 0 && j == 0);
+                const double x = a[r + j * lda];
+                const double k = cand_key(x, r == 0 && j == 0);
                 const long long pos = r + (long long)j * m;
-                if (cand_better(k, pos, bk, bp)) { bk = k; bp = pos; }
+                if (cand_better(k, pos, bk, bp)) { bk = k; bp = pos; bv = x; }
             }
-        block_publish(bk, bp, p.cand, sk, sp);
+        block_publish(bk, bp, bv, p.cand, sk, sp);
     }
     grid.sync();
     for (int i = 0; i < mn; ++i) {
-        const long long pos = grid_winner(p.cand, G, &s_pos);
+        const long long pos = grid_winner(p.cand, G, &s_pos, &s_val);
         const int pc = (int)(pos / m);
         if (gtid == 0) p.p_col[i] = pc;
-        // ---- phase A: whole columns i <-> pc (col_piv_qr.rs:76)
-        if (pc != i)
-            for (long long r = gtid; r < m; r += nthreads) {
-                const double t = a[r + i * lda]; a[r + i * lda] = a[r + pc * lda]; a[r + pc * lda] = t;
-            }
-        grid.sync();
-        // ---- phase H (CTA 0): column i, rows i.. -> unit axis of the reflection (householder.rs:19-53)
+        double* hh = p.hh + 2 * (i & 1);
+        // ---- phase H
         if (cta == 0) {
-            double* col = a + i + i * lda;
+            // column pc, rows i.. -> unit axis (householder.rs:19-53) stored in column i; old column i -> column pc.
+            // Up to 16 entries per thread live in registers (one round of loads for the three passes); longer columns
+            // are re-read.
+            double* ci = a + i + i * lda;
+            double* cp = a + i + pc * lda;
             const int len = m - i;
+            constexpr int R = 16;
+            const bool in_regs = len <= R * T;
+            double xr[R], oi[R];
+#pragma unroll
+            for (int u = 0; u < R; ++u) {
+                const int r = tid + u * T;
+                xr[u] = (in_regs && r < len) ? cp[r] : 0.0;
+                oi[u] = (in_regs && r < len && pc != i) ? ci[r] : 0.0;
+            }
             double s = 0.0;
-            for (int r = tid; r < len; r += T) { const double x = col[r]; s = fma(x, x, s); }
+            if (in_regs) {
+#pragma unroll
+                for (int u = 0; u < R; ++u) s = fma(xr[u], xr[u], s);
+            } else {
+                for (int r = tid; r < len; r += T) { const double x = cp[r]; s = fma(x, x, s); }
+            }
             const double sq = block_sum(s, sred);
             const double nrm = sqrt(sq);
-            const double x0 = col[0];
+            const double x0 = cp[0];
             const double modulus = x0 >= 0.0 ? x0 : -x0, sign = x0 >= 0.0 ? 1.0 : -1.0;      // simba to_exp
             const double signed_norm = sign * nrm;
             const double factor = (sq + modulus * nrm) * 2.0;
-            __syncthreads();                                        // everyone has read col[0]
+            __syncthreads();                                        // cp[0] has been read by everyone before it may change
             if (factor != 0.0) {
                 const double sf = sqrt(factor);
                 double s2 = 0.0;
-                for (int r = tid; r < len; r += T) {
-                    const double v = (r == 0 ? x0 + signed_norm : col[r]) / sf;           // unscale_mut
-                    col[r] = v;
-                    s2 = fma(v, v, s2);
+                if (in_regs) {
+#pragma unroll
+                    for (int u = 0; u < R; ++u) {
+                        const int r = tid + u * T;
+                        xr[u] = r < len ? (r == 0 ? x0 + signed_norm : xr[u]) / sf : 0.0;    // unscale_mut
+                        s2 = fma(xr[u], xr[u], s2);
+                    }
+                } else {
+                    for (int r = tid; r < len; r += T) {
+                        const double v = (r == 0 ? x0 + signed_norm : cp[r]) / sf;
+                        s2 = fma(v, v, s2);
+                    }
                 }
                 const double nn = sqrt(block_sum(s2, sred));        // normalize_mut
-                for (int r = tid; r < len; r += T) col[r] = col[r] / nn;
-                if (tid == 0) { p.diag[i] = -signed_norm; p.hh[0] = signbit(-signed_norm) ? -1.0 : 1.0; p.hh[1] = 1.0; }   // signum of the returned norm; reflected
+                if (in_regs) {
+#pragma unroll
+                    for (int u = 0; u < R; ++u) {
+                        const int r = tid + u * T;
+                        if (r < len) { ci[r] = xr[u] / nn; if (pc != i) cp[r] = oi[u]; }
+                    }
+                } else {
+                    for (int r = tid; r < len; r += T) {
+                        const double old_i = ci[r];
+                        const double v = (r == 0 ? x0 + signed_norm : cp[r]) / sf;
+                        ci[r] = v / nn;
+                        if (pc != i) cp[r] = old_i;
+                    }
+                }
+                if (tid == 0) { p.diag[i] = -signed_norm; hh[0] = signbit(-signed_norm) ? -1.0 : 1.0; hh[1] = 1.0; }   // signum of the returned norm; reflected
             } else {
-                if (tid == 0) { col[0] = x0 + signed_norm; p.diag[i] = signed_norm; p.hh[0] = 1.0; p.hh[1] = 0.0; }
+                // an all-zero column is not reflected (householder.rs:36-48); it still changes places with column i
+                for (int r = tid; r < len; r += T) {
+                    const double old_i = ci[r];
+                    ci[r] = r == 0 ? x0 + signed_norm : cp[r];
+                    if (pc != i) cp[r] = old_i;
+                }
+                if (tid == 0) { p.diag[i] = signed_norm; hh[0] = 1.0; hh[1] = 0.0; }
+            }
+            if (G == 1 && pc != i)
+                for (int r = tid; r < i; r += T) { const double t = a[r + i * lda]; a[r + i * lda] = a[r + pc * lda]; a[r + pc * lda] = t; }
+        } else if (pc != i) {
+            for (long long r = gtid - T; r < i; r += nthreads - T) {                      // rows ..i of the two columns
+                const double t = a[r + i * lda]; a[r + i * lda] = a[r + pc * lda]; a[r + pc * lda] = t;
             }
         }
         grid.sync();
         // ---- phase R: reflect the columns right of i (rows i..) and search the next pivot (rows / columns i + 1..)
-        const double sign = __ldcg(p.hh + 0);
-        const bool reflected = __ldcg(p.hh + 1) != 0.0;
+        const double sign = __ldcg(hh + 0);
+        const bool reflected = __ldcg(hh + 1) != 0.0;
         const double* axis = a + i + i * lda;
         const int len = m - i;
-        double bk = -2.0; long long bp = 0x7fffffffffffffffll;
+        double bk = -2.0, bv = 0.0; long long bp = 0x7fffffffffffffffll;
         for (int j = i + 1 + gwarp; j < n; j += nwarps) {
             double* cj = a + i + j * lda;
             double factor = 0.0;
             if (reflected) {
                 double d = 0.0;
+#pragma unroll 8
                 for (int r = lane; r < len; r += 32) d = fma(axis[r], cj[r], d);
 #pragma unroll
                 for (int o = 16; o > 0; o >>= 1) d += __shfl_xor_sync(0xffffffffu, d, o);
                 factor = d * (sign * -2.0);                          // reflection.rs:76-79, bias = 0
             }
-            for (int r = lane; r < len; r += 32) {
-                double v = cj[r];
-                if (reflected) { v = __dadd_rn(__dmul_rn(factor, axis[r]), __dmul_rn(sign, v)); cj[r] = v; }   // axpy(factor, axis, sign)
-                if (r >= 1) {
-                    const double k = cand_key(v, r == 1 && j == i + 1);
-                    const long long pos2 = (i + r) + (long long)j * m;
-                    if (cand_better(k, pos2, bk, bp)) { bk = k; bp = pos2; }
+            for (int r0 = lane; r0 < len; r0 += 256) {
+                double x[8], y[8];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) { const int r = r0 + 32 * u; x[u] = r < len ? axis[r] : 0.0; y[u] = r < len ? cj[r] : 0.0; }
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    const int r = r0 + 32 * u;
+                    if (r < len) {
+                        double v = y[u];
+                        if (reflected) { v = __dadd_rn(__dmul_rn(factor, x[u]), __dmul_rn(sign, v)); cj[r] = v; }   // axpy(factor, axis, sign)
+                        if (r >= 1) {
+                            const double k = cand_key(v, r == 1 && j == i + 1);
+                            const long long pos2 = (i + r) + (long long)j * m;
+                            if (cand_better(k, pos2, bk, bp)) { bk = k; bp = pos2; bv = v; }
+                        }
+                    }
                 }
             }
         }
-        block_publish(bk, bp, p.cand, sk, sp);
+        block_publish(bk, bp, bv, p.cand, sk, sp);
         grid.sync();
     }
 }
@@ -310,7 +397,7 @@ int col_piv_qr_device(cudaStream_t s, size_t m, size_t n, double* a, size_t lda,
     const int G = pivoted_grid((const void*)col_piv_qr_kernel, m, n);
     Scratch cand, hh;
     NAB_TRY(cand.alloc((size_t)G * sizeof(pv::Cand), s));
-    NAB_TRY(hh.alloc(4 * sizeof(double), s));
+    NAB_TRY(hh.alloc(4 * sizeof(double), s));      // (sign, reflected) x step parity
     PivotedParams p{a, (long long)lda, (int)m, (int)n, nullptr, p_col, diag, cand.as<pv::Cand>(), hh.as<double>(), nullptr};
     void* args[] = {(void*)&p};
     NAB_CUDA(cudaLaunchCooperativeKernel((void*)col_piv_qr_kernel, dim3((unsigned)G), dim3(pv::T), args, 0, s));
