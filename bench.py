@@ -559,8 +559,9 @@ def factorization_extras(L, _capi, torch, dev, stream, N, cpu=True, e2e=True):
             _capi.check(L.na_cholesky_f64(N, hA.data_ptr(), N, 0, 0.0, C.addressof(fail)))
             return (time.perf_counter() - t0) * 1e3
         msh = min(chol_h() for _ in range(2))
-        out["cholesky_n16384"]["e2e"] = {"ms": msh, "gflops": fl / msh / 1e6, "h2d_bytes": N * N * 8, "d2h_bytes": N * N * 8,
-                                         "api": "na_cholesky_f64 (host pointer, pinned)"}
+        tri_bytes = sum((N - j) * min(512, N - j) for j in range(0, N, 512)) * 8     # lower triangle as 512-column trapezoids, each way
+        out["cholesky_n16384"]["e2e"] = {"ms": msh, "gflops": fl / msh / 1e6, "h2d_bytes": tri_bytes, "d2h_bytes": tri_bytes,
+                                         "api": "na_cholesky_f64 (host pointer, pinned): lower triangle only, finished panels stream back behind the factorization"}
         del hA, hA0
     if "cholesky" in base:
         out["cholesky_n16384"]["cpu_baseline"] = base["cholesky"]
@@ -628,10 +629,38 @@ def factorization_extras(L, _capi, torch, dev, stream, N, cpu=True, e2e=True):
             return (time.perf_counter() - t0) * 1e3
         msh = min(qr_h() for _ in range(2))
         out["qr_65536x4096"]["e2e"] = {"ms": msh, "gflops": fl / msh / 1e6, "h2d_bytes": m * n * 8, "d2h_bytes": m * n * 8 + n * 8,
-                                       "api": "na_qr_f64 (host pointer, pinned)"}
+                                       "api": "na_qr_f64 (host pointer, pinned): finished outer panels are converted and streamed back behind the factorization"}
         del hA, hA0
     if "qr" in base:
         out["qr_65536x4096"]["cpu_baseline"] = base["qr"]
+    del A, A0
+
+    # ---- FullPivLU / ColPivQR -- one pass over the trailing matrix per step (Level-2, memory-bound)
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            hbm_peak = json.load(f)["hbm_gbs"]; peak_src = "measured (MEASURED_PEAKS.json, copy bandwidth)"
+    except Exception:
+        hbm_peak = 6650.0; peak_src = "fallback (B200_PROFILING.md)"
+    n4 = 4096
+    A0 = torch.empty(n4 * n4, dtype=torch.float64, device=dev); A = torch.empty_like(A0); dg = torch.empty(n4, dtype=torch.float64, device=dev)
+    _capi.check(L.na_fill_uniform_dev(A0.data_ptr(), n4, n4, n4, 6, stream))
+    ps = (C.c_size_t * (2 * n4))(); qs = (C.c_size_t * (2 * n4))(); n_p = C.c_size_t(0); n_q = C.c_size_t(0)
+    def fplu():
+        A.copy_(A0)
+        _capi.check(L.na_full_piv_lu_f64_dev(n4, n4, A.data_ptr(), n4, ps, C.addressof(n_p), qs, C.addressof(n_q), stream))
+    def cpqr():
+        A.copy_(A0)
+        _capi.check(L.na_col_piv_qr_f64_dev(n4, n4, A.data_ptr(), n4, dg.data_ptr(), ps, C.addressof(n_p), stream))
+    alg_bytes = 16.0 * n4 ** 3 / 3.0            # every step reads and writes the (n - i)^2 trailing matrix once
+    for key, fn, what in (("full_piv_lu_n4096", fplu, "full_piv_lu_kernel"), ("col_piv_qr_n4096", cpqr, "col_piv_qr_kernel")):
+        ms, _ = dev_time(fn, 2)
+        gbs = alg_bytes / ms / 1e6
+        out[key] = {"ms": ms, "us_per_step": ms * 1e3 / n4,
+                    "roofline": {"bound": "hbm", "achieved": gbs, "peak": hbm_peak, "unit": "GB/s", "frac": gbs / hbm_peak, "traffic": None,
+                                 "kernel": what, "peak_source": peak_src,
+                                 "algorithmic_bytes_per_launch": alg_bytes,
+                                 "note": "16 n^3 / 3 bytes: one read + one write of the trailing matrix per elimination step; "
+                                         "two grid barriers per step bound the small-n end"}}
     return out
 
 

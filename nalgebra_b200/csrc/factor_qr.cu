@@ -9,6 +9,7 @@
 #include <algorithm>
 #include <cstdio>
 #include <cstdlib>
+#include <cstring>
 
 #include "common.cuh"
 #include "kernels.cuh"
@@ -94,13 +95,25 @@ static bool qr_fused_enabled() {
     static bool v = [] { const char* e = getenv("NAB_QR_FUSED"); return e ? atoi(e) != 0 : true; }();
     return v;
 }
+// NAB_QR_LEAF=smem keeps the shared-memory GEQR2 leaf everywhere (A/B timing); default: the register-resident leaf
+// (panel_qr_reg.cu) wherever its grid (512 rows per CTA) fits the SMs the panel may use.
+static bool qr_reg_leaf_enabled() {
+    static bool v = [] { const char* e = getenv("NAB_QR_LEAF"); return !(e && strcmp(e, "smem") == 0); }();
+    return v;
+}
+static bool qr_use_reg_leaf(size_t ml, int max_ctas) {
+    if (!qr_reg_leaf_enabled() || ml < 4096) return false;
+    const int g = geqr2_reg_grid(ml);
+    return g > 0 && (max_ctas == 0 || g <= max_ctas);
+}
 static int qr_panel(cudaStream_t s, QrWork& w, size_t m, double* a, size_t lda, double* tau, size_t j, size_t jb,
                     double* vleaf, double* sleaf, double* wkleaf, int max_ctas = 0) {
     const size_t W = kQrLeaf;
     for (size_t l = 0; l < jb; l += W) {
         const size_t lw = std::min(W, jb - l), jl = j + l, ml = m - jl;
         double* apanel = a + jl + jl * lda;
-        NAB_TRY(geqr2_panel(s, apanel, lda, ml, lw, tau + jl, w.ws_geqr2.p, &w.seq_state));
+        if (qr_use_reg_leaf(ml, max_ctas)) NAB_TRY(geqr2_panel_reg(s, apanel, lda, ml, lw, tau + jl, w.ws_geqr2.p, &w.seq_state));
+        else NAB_TRY(geqr2_panel(s, apanel, lda, ml, lw, tau + jl, w.ws_geqr2.p, &w.seq_state));
         const size_t nc = (j + jb) - (jl + lw);          // rest of the outer panel
         if (nc > 0 && nc <= 224 && ml >= 2048 && qr_fused_enabled()) {
             NAB_TRY(larfb_leaf_fused(s, apanel, lda, ml, lw, nc, tau + jl, w.ws_larfb.p, &w.seq_larfb, max_ctas));
@@ -172,10 +185,15 @@ static int qr_lookahead(cudaStream_t sp, QrWork& w, size_t m, size_t n, double* 
         cudaEventRecord(ev_p, sp);
         const size_t x0 = jn + jbn, nx = n - x0, mj = m - j;
         // SMs of the panel chain = the cooperative GEQR2 grid of the next panel's first (tallest) leaf
-        const int rp = jbn ? std::min(sms - 16, geqr2_grid(m - jn, std::min<size_t>(kQrLeaf, jbn)) + 2) : 0;
+        // (the register-resident leaf takes one CTA per 512 rows: nearly the whole GPU for a 65536-row panel, which then
+        // runs much faster than beside a large bulk share)
+        const int rp = !jbn ? 0
+                     : qr_use_reg_leaf(m - jn, 0) ? std::min(sms - 8, geqr2_reg_grid(m - jn) + 2)
+                                                  : std::min(sms - 16, geqr2_grid(m - jn, std::min<size_t>(kQrLeaf, jbn)) + 2);
         size_t wa = nx;
         if (jbn && nx) {
-            const double t_panel = (double)jbn / 32.0 * 0.44e-3;              // measured: ~3.5 ms per 256 columns
+            // measured per 256 columns: ~3.5 ms with the shared-memory leaf beside the bulk update, ~2.3 ms with the register leaf
+            const double t_panel = (double)jbn / 32.0 * (qr_use_reg_leaf(m - jn, 0) ? 0.28e-3 : 0.44e-3);
             const double target = t_panel * (sms - rp) * 0.18e12;
             wa = round_up((size_t)(target / (4.0 * (double)mj * (double)jb)) + 1, 128);
             if (wa + 256 >= nx) wa = nx;
@@ -240,7 +258,10 @@ int qr_device(cudaStream_t s, size_t m, size_t n, double* a, size_t lda, double*
         NAB_TRY(w.finish_columns(s, n));                      // whatever is left: the last panel, columns right of min(m, n)
         return w.join(s);
     };
-    if (qr_lookahead_enabled() && k >= 4 * QR_NB && m >= 8192 && n <= m) {
+    // Look-ahead pays when the panel leaves SMs to the bulk update (shared-memory leaf: ~98 CTAs at 65536 rows).  The
+    // register-resident leaf takes nearly the whole GPU and is 2x faster, so the plain loop is the better schedule with it
+    // (65536 x 4096: 102 ms against 112 ms with look-ahead and 106 ms with the shared-memory leaf + look-ahead).
+    if (qr_lookahead_enabled() && k >= 4 * QR_NB && m >= 8192 && n <= m && !qr_use_reg_leaf(m, 0)) {
         NAB_TRY(qr_lookahead(s, w, m, n, a, lda, tau, k));
         return finish();
     }

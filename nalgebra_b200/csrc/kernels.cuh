@@ -73,6 +73,9 @@ constexpr int kQrLeaf = 32;        // GEQR2 leaf panel width
 size_t geqr2_workspace_bytes();
 int geqr2_grid(size_t m, size_t w);       // CTAs (= SMs) the cooperative GEQR2 launch of an m x w panel occupies
 int geqr2_panel(cudaStream_t st, double* a_panel, size_t lda, size_t m, size_t w, double* tau, void* ws, int* seq_state);
+// register-resident leaf (panel_qr_reg.cu): 512 rows per CTA; grid 0 = the panel does not fit the SMs
+int geqr2_reg_grid(size_t m);
+int geqr2_panel_reg(cudaStream_t st, double* a_panel, size_t lda, size_t m, size_t w, double* tau, void* ws, int* seq_state);
 int extract_v(cudaStream_t st, double* vw, size_t ldv, const double* a, size_t lda, size_t m, size_t w, const double* tau, int mode);
 int build_s(cudaStream_t st, double* g, size_t ldg, size_t w, const double* tau);
 // leaf panels (w <= 32): clean V into vw and S = triu(V^T V, 1) + diag(1/tau) into smat, one launch

@@ -14,6 +14,7 @@
 
 #include "common.cuh"
 #include "kernels.cuh"
+#include "panel_qr.cuh"
 
 namespace nab {
 
@@ -32,39 +33,7 @@ namespace nab {
 // need until the sequence number matches.  Two buffers (by column parity) are enough because a CTA
 // cannot publish column c+2 before every CTA has published c+1, i.e. finished reading c.
 // ------------------------------------------------------------------------------------------------
-struct Geqr2Params {
-    double* a; long long lda;
-    int m, w, rp;
-    double* tau;               // [w] out
-    double2* xch;              // [2][G][32]  (partial sum, seq) pairs, slot j = column j (slot c = sigma)
-    double2* rowc;             // [2][32]     (a[c, j], seq) pairs published by the owner of row c
-    double2* totx;             // [2][32]     (T_j, seq) totals published by the reducer CTA of slot j (two-stage exchange)
-    int seq0;                  // sequence numbers already consumed in this workspace
-};
-
-__device__ __forceinline__ void st_pair(double2* p, double v, double seq) {
-    asm volatile("st.global.v2.f64 [%0], {%1, %2};" ::"l"(p), "d"(v), "d"(seq) : "memory");
-}
-__device__ __forceinline__ void ld_pair_raw(const double2* p, double& x, double& y) {
-    asm volatile("ld.volatile.global.v2.f64 {%0, %1}, [%2];" : "=d"(x), "=d"(y) : "l"(p) : "memory");
-}
-
-// vals[0..31] per lane -> returns in every lane l the sum over the warp of vals[l] (butterfly
-// reduce-scatter: 31 shuffles instead of 160)
-__device__ __forceinline__ double warp_reduce_scatter32(double (&vals)[32], int lane) {
-#pragma unroll
-    for (int step = 16; step >= 1; step >>= 1) {
-        const bool hi = (lane & step) != 0;
-#pragma unroll
-        for (int i = 0; i < step; ++i) {
-            const double send = hi ? vals[i] : vals[i + step];
-            const double keep = hi ? vals[i + step] : vals[i];
-            vals[i] = keep + __shfl_xor_sync(0xffffffffu, send, step);
-        }
-    }
-    return vals[0];
-}
-
+// Geqr2Params, st_pair / ld_pair_raw and warp_reduce_scatter32 live in panel_qr.cuh (shared with the register-resident leaf)
 __device__ long long g_geqr2_prof[16];
 #ifdef NAB_GEQR2_PROF   // per-phase cycle counters of CTA 0 / thread 0 (tools/qr_timing.py), off in the product build
 #define QPROF(i) do { if (threadIdx.x == 0 && blockIdx.x == 0) { const long long t_ = clock64(); g_geqr2_prof[i] += t_ - qt_prev; qt_prev = t_; } } while (0)
@@ -278,7 +247,6 @@ __global__ void __launch_bounds__(256, 1) geqr2_coop_kernel(const Geqr2Params p)
         for (int r = tid; r < nrows; r += nt) p.a[(long long)(r_begin + r) + (long long)c * p.lda] = s[r + c * rp];
 }
 
-constexpr size_t kGeqr2MaxCtas = 160;
 size_t geqr2_workspace_bytes() { return (2 * kGeqr2MaxCtas * 32 + 2 * 32 + 2 * 32) * sizeof(double2); }
 
 // CTAs (and rows per CTA) the cooperative GEQR2 launch uses for an m x w panel; 0 if it does not fit.

@@ -154,3 +154,95 @@ impl QR {
     }
     pub fn is_invertible(&self) -> bool { self.diag.iter().all(|d| *d != 0.0) }
 }
+
+fn sequence(pairs: &[usize], len: usize, dim: usize) -> PermutationSequence<Dyn> {
+    let mut p = PermutationSequence::identity(dim);
+    for s in 0..len { p.append_permutation(pairs[2 * s], pairs[2 * s + 1]); }
+    p
+}
+
+/// `FullPivLU{lu, p, q}` (full_piv_lu.rs:56-91): P * matrix * Q = L U, pivot = `icamax_full` of the trailing matrix.
+/// The device applies the reference's arithmetic exactly, so `lu`, `p` and `q` are bit-identical to nalgebra's.
+pub struct FullPivLU { lu: DMatrix<f64>, p: PermutationSequence<Dyn>, q: PermutationSequence<Dyn> }
+
+impl FullPivLU {
+    pub fn new(mut m: DMatrix<f64>) -> Self {
+        let (nr, nc) = m.shape();
+        let mn = nr.min(nc);
+        let (mut ps, mut qs) = (vec![0usize; 2 * mn.max(1)], vec![0usize; 2 * mn.max(1)]);
+        let (mut np, mut nq) = (0usize, 0usize);
+        check(unsafe { sys::na_full_piv_lu_f64(nr, nc, m.as_mut_ptr(), nr.max(1), ps.as_mut_ptr(), &mut np, qs.as_mut_ptr(), &mut nq) });
+        Self { lu: m, p: sequence(&ps, np, mn), q: sequence(&qs, nq, mn) }
+    }
+    pub fn lu_internal(&self) -> &DMatrix<f64> { &self.lu }
+    pub fn p(&self) -> &PermutationSequence<Dyn> { &self.p }
+    pub fn q(&self) -> &PermutationSequence<Dyn> { &self.q }
+    pub fn u(&self) -> DMatrix<f64> { let mn = self.lu.nrows().min(self.lu.ncols()); self.lu.rows(0, mn).upper_triangle() }
+    pub fn l(&self) -> DMatrix<f64> {
+        let mn = self.lu.nrows().min(self.lu.ncols());
+        let mut l = self.lu.columns(0, mn).into_owned();
+        l.fill_upper_triangle(0.0, 1);
+        l.fill_diagonal(1.0);
+        l
+    }
+    pub fn is_invertible(&self) -> bool { let d = self.lu.nrows(); self.lu[(d - 1, d - 1)] != 0.0 }
+    /// `solve_mut` (full_piv_lu.rs:189-215).
+    pub fn solve_mut(&self, b: &mut DMatrix<f64>) -> bool {
+        let n = self.lu.nrows();
+        assert!(self.lu.is_square(), "FullPivLU solve: unable to solve a non-square system.");
+        assert_eq!(b.nrows(), n, "FullPivLU solve matrix dimension mismatch.");
+        if !self.is_invertible() { return false; }
+        self.p.permute_rows(b);
+        check(unsafe { sys::na_tri_solve_f64(1, 0, 1, n, self.lu.as_ptr(), n.max(1), b.as_mut_ptr(), n.max(1), b.ncols()) });
+        check(unsafe { sys::na_tri_solve_f64(0, 0, 0, n, self.lu.as_ptr(), n.max(1), b.as_mut_ptr(), n.max(1), b.ncols()) });
+        self.q.inv_permute_rows(b);
+        true
+    }
+    pub fn determinant(&self) -> f64 {
+        let d = self.lu.nrows();
+        let last = self.lu[(d - 1, d - 1)];
+        if last == 0.0 { return 0.0; }
+        (0..d - 1).fold(last, |acc, i| acc * self.lu[(i, i)]) * self.p.determinant::<f64>() * self.q.determinant::<f64>()
+    }
+}
+
+/// `ColPivQR{col_piv_qr, p, diag}` (col_piv_qr.rs:56-93): matrix * P = Q R, storage as `QR`.
+pub struct ColPivQR { col_piv_qr: DMatrix<f64>, p: PermutationSequence<Dyn>, diag: DVector<f64> }
+
+impl ColPivQR {
+    pub fn new(mut m: DMatrix<f64>) -> Self {
+        let (nr, nc) = m.shape();
+        let mn = nr.min(nc);
+        let mut diag = DVector::zeros(mn);
+        let mut ps = vec![0usize; 2 * mn.max(1)];
+        let mut np = 0usize;
+        check(unsafe { sys::na_col_piv_qr_f64(nr, nc, m.as_mut_ptr(), nr.max(1), diag.as_mut_ptr(), ps.as_mut_ptr(), &mut np) });
+        Self { col_piv_qr: m, p: sequence(&ps, np, mn), diag }
+    }
+    pub fn col_piv_qr_internal(&self) -> &DMatrix<f64> { &self.col_piv_qr }
+    pub fn p(&self) -> &PermutationSequence<Dyn> { &self.p }
+    pub fn r(&self) -> DMatrix<f64> {
+        let mn = self.diag.len();
+        let mut r = self.col_piv_qr.rows(0, mn).upper_triangle();
+        for i in 0..mn { r[(i, i)] = self.diag[i].abs(); }
+        r
+    }
+    /// `q()` (col_piv_qr.rs:129-150): the axes are stored like `QR`'s, so the same device routine forms Q.
+    pub fn q(&self) -> DMatrix<f64> {
+        let (nr, nc) = self.col_piv_qr.shape();
+        let mut q = DMatrix::zeros(nr, nr.min(nc));
+        check(unsafe { sys::na_qr_q_f64(nr, nc, self.col_piv_qr.as_ptr(), nr.max(1), self.diag.as_ptr(), q.as_mut_ptr(), nr.max(1)) });
+        q
+    }
+    /// `solve_mut` (col_piv_qr.rs:227-247).
+    pub fn solve_mut(&self, b: &mut DMatrix<f64>) -> bool {
+        let n = self.col_piv_qr.nrows();
+        assert!(self.col_piv_qr.is_square(), "ColPivQR solve: unable to solve a non-square system.");
+        assert_eq!(b.nrows(), n, "ColPivQR solve matrix dimension mismatch.");
+        let ok = check(unsafe { sys::na_qr_solve_f64(n, self.col_piv_qr.as_ptr(), n.max(1), self.diag.as_ptr(), b.as_mut_ptr(), n.max(1), b.ncols()) }) != sys::NA_SINGULAR;
+        self.p.inv_permute_rows(b);
+        ok
+    }
+    pub fn is_invertible(&self) -> bool { self.diag.iter().all(|d| *d != 0.0) }
+    pub fn determinant(&self) -> f64 { self.diag.iter().product::<f64>() * self.p.determinant::<f64>() }
+}
