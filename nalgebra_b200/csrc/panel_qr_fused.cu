@@ -20,6 +20,7 @@
 //      memory, the next 64 columns' loads in flight while the current ones are in the pipe).
 // All CTAs must be co-resident (the hand-offs spin): cooperative launch, grid <= the SMs the caller keeps free.
 #include <algorithm>
+#include <cstdlib>
 
 #include "common.cuh"
 #include "dmma_stream.cuh"
@@ -28,7 +29,8 @@
 namespace nab {
 
 namespace lf {
-constexpr int T = 256;            // threads: 8 warps, each owning a slice of the CTA's rows
+// threads: NW warps (template parameter of the kernel: 8 with explicit double buffering, or 16 with half the registers and
+// the warps covering each other's memory stalls), interleaved over the CTA's rows
 constexpr int W = 32;             // reflectors per leaf
 constexpr int NCX = 256;          // row stride of the [W | G] partials / totals in global memory: nc <= 224, + 32
 constexpr int NCXP = 260;         // row stride of X in shared memory: = 4 (mod 16) doubles, so the DMMA B fragments
@@ -66,17 +68,22 @@ __device__ long long g_larfb_prof[16];
 #define LF_T(i) do { } while (0)
 #endif
 
-__global__ void __launch_bounds__(lf::T, 1) larfb_leaf_fused_kernel(const LarfbParams p) {
+template <int NW>
+__global__ void __launch_bounds__(32 * NW, 1) larfb_leaf_fused_kernel(const LarfbParams p) {
     using namespace lf;
+    constexpr int T = 32 * NW;
+    constexpr int PB = NW == 8 ? 4 : 2;              // DMMA k-steps (4 rows each) per phase-1 batch
+    constexpr bool PREFETCH = NW == 8;               // explicit double buffering only where the registers allow it
+    constexpr int NSUB = T / 64;                     // partial sums per entry in the cross-CTA reduction
 #ifdef NAB_LARFB_PROF
     long long lf_t0 = clock64();
 #endif
     extern __shared__ __align__(16) double sm[];
-    double* red = sm;                                // phase 1: [8 warps][W][RLD] partial tiles
+    double* red = sm;                                // phase 1: [NW warps][W][RLD] partial tiles
     double* Ws = sm;                                 // later:   [W][NCXP] totals, then X
     double* Ss = sm + W * NCXP;                      //          [W][W + 1]: S(i, j), i <= j
     __shared__ double tau_s[W];
-    __shared__ double red4[4][64];
+    __shared__ double red4[NSUB][64];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int g8 = lane >> 2, q4 = lane & 3;         // DMMA fragment coordinates
     const int G = gridDim.x, cta = blockIdx.x;
@@ -103,12 +110,13 @@ __global__ void __launch_bounds__(lf::T, 1) larfb_leaf_fused_kernel(const LarfbP
         double* mypart = p.part + (size_t)cta * (W * NCX);
         const double* vq = vbase + r_cta + q4 + (long long)g8 * lda;
         const double* cq = cbase + r_cta + q4 + (long long)g8 * lda;
-        const int r_first = 16 * warp;
-        double cav[4][4], cbv[4][4], nav[4][4], nbv[4][4];
-        auto load_batch = [&](double (&av)[4][4], double (&bv)[4][4], int grp, int r0) {
+        constexpr int BR = 4 * PB;                   // rows per batch
+        const int r_first = BR * warp;
+        double cav[PB][4], cbv[PB][4], nav[PB][4], nbv[PB][4];
+        auto load_batch = [&](double (&av)[PB][4], double (&bv)[PB][4], int grp, int r0) {
             const bool vgrp = grp == n_cg;
 #pragma unroll
-            for (int s4 = 0; s4 < 4; ++s4) {
+            for (int s4 = 0; s4 < PB; ++s4) {
                 const int r = r0 + 4 * s4;
                 const bool rok = r + q4 < slab_n;
 #pragma unroll
@@ -118,7 +126,7 @@ __global__ void __launch_bounds__(lf::T, 1) larfb_leaf_fused_kernel(const LarfbP
                     bv[s4][nt] = (rok && !vgrp && 32 * grp + 8 * nt + g8 < nc) ? __ldcg(cq + r + (long long)(32 * grp + 8 * nt) * lda) : 0.0;
             }
         };
-        load_batch(cav, cbv, 0, r_first);
+        if constexpr (PREFETCH) load_batch(cav, cbv, 0, r_first);
         for (int grp = 0; grp <= n_cg; ++grp) {
             double acc[4][4][2];
 #pragma unroll
@@ -126,11 +134,15 @@ __global__ void __launch_bounds__(lf::T, 1) larfb_leaf_fused_kernel(const LarfbP
 #pragma unroll
                 for (int nt = 0; nt < 4; ++nt) acc[mt][nt][0] = acc[mt][nt][1] = 0.0;
             const bool vgrp = grp == n_cg;
-            for (int r0 = r_first; r0 < slab_n; r0 += 128) {
-                if (r0 + 128 < slab_n) load_batch(nav, nbv, grp, r0 + 128);
-                else if (!vgrp) load_batch(nav, nbv, grp + 1, r_first);
+            for (int r0 = r_first; r0 < slab_n; r0 += BR * NW) {
+                if constexpr (PREFETCH) {
+                    if (r0 + BR * NW < slab_n) load_batch(nav, nbv, grp, r0 + BR * NW);
+                    else if (!vgrp) load_batch(nav, nbv, grp + 1, r_first);
+                } else {
+                    load_batch(cav, cbv, grp, r0);
+                }
 #pragma unroll
-                for (int s4 = 0; s4 < 4; ++s4) {
+                for (int s4 = 0; s4 < PB; ++s4) {
                     if (top && r0 < W) {
                         const int row = r0 + 4 * s4 + q4;
 #pragma unroll
@@ -148,10 +160,12 @@ __global__ void __launch_bounds__(lf::T, 1) larfb_leaf_fused_kernel(const LarfbP
 #pragma unroll
                         for (int nt = 0; nt < 4; ++nt) ptx::dmma884(acc[mt][nt][0], acc[mt][nt][1], cav[s4][mt], cbv[s4][nt]);
                 }
+                if constexpr (PREFETCH) {
 #pragma unroll
-                for (int s4 = 0; s4 < 4; ++s4)
+                    for (int s4 = 0; s4 < PB; ++s4)
 #pragma unroll
-                    for (int t = 0; t < 4; ++t) { cav[s4][t] = nav[s4][t]; cbv[s4][t] = nbv[s4][t]; }
+                        for (int t = 0; t < 4; ++t) { cav[s4][t] = nav[s4][t]; cbv[s4][t] = nbv[s4][t]; }
+                }
             }
             // the eight warps' tiles are added in warp order
             double* mine = red + warp * (W * RLD);
@@ -163,11 +177,11 @@ __global__ void __launch_bounds__(lf::T, 1) larfb_leaf_fused_kernel(const LarfbP
             __syncthreads();
             const int cbeg = vgrp ? nc : 32 * grp;
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {
+            for (int u = 0; u < W * 32 / T; ++u) {
                 const int e = tid + u * T, i = e >> 5, c = e & 31;
                 double sum = 0.0;
 #pragma unroll
-                for (int wq = 0; wq < 8; ++wq) sum += red[wq * (W * RLD) + i * RLD + c];
+                for (int wq = 0; wq < NW; ++wq) sum += red[wq * (W * RLD) + i * RLD + c];
                 if (cbeg + c < (vgrp ? ncx : nc)) mypart[i * NCX + cbeg + c] = sum;
             }
             __syncthreads();
@@ -190,7 +204,7 @@ __global__ void __launch_bounds__(lf::T, 1) larfb_leaf_fused_kernel(const LarfbP
                 if (e < e1) {
                     const int i = e / ncx, c = e - i * ncx;
                     const double* src = p.part + i * NCX + c;
-                    const int ga = (G * sub) >> 2, gb = (G * (sub + 1)) >> 2;
+                    const int ga = G * sub / NSUB, gb = G * (sub + 1) / NSUB;
                     int g = ga;
                     for (; g + 10 <= gb; g += 10) {
                         double t[10];
@@ -205,7 +219,10 @@ __global__ void __launch_bounds__(lf::T, 1) larfb_leaf_fused_kernel(const LarfbP
                 __syncthreads();
                 if (tid < 64 && e < e1) {
                     const int i = e / ncx, c = e - i * ncx;
-                    p.total[i * NCX + c] = ((red4[0][tid] + red4[1][tid]) + red4[2][tid]) + red4[3][tid];
+                    double t = 0.0;
+#pragma unroll
+                    for (int q = 0; q < NSUB; ++q) t += red4[q][tid];
+                    p.total[i * NCX + c] = t;
                 }
                 __syncthreads();
             }
@@ -233,7 +250,8 @@ __global__ void __launch_bounds__(lf::T, 1) larfb_leaf_fused_kernel(const LarfbP
     }
     __syncthreads();
     if (tid < nc) {          // one thread per column of C: x_i = (w_i - sum_{j<i} S(j, i) x_j) / S(i, i)
-        double xv[W];
+        double xv[W];        // (with 16 warps this array spills to local memory: 400 bytes once per launch, cheaper than
+                             // walking the column in shared memory -- 10 000 vs 20 000 cycles)
 #pragma unroll
         for (int i = 0; i < W; ++i) xv[i] = Ws[i * NCXP + tid];
 #pragma unroll
@@ -268,7 +286,7 @@ __global__ void __launch_bounds__(lf::T, 1) larfb_leaf_fused_kernel(const LarfbP
                 }
             }
         };
-        dmma_stream_update<8, NCXP, true>(cbase + r_cta, lda, slab_n, nc, Ws, lane, warp, T / 32, load_a);
+        dmma_stream_update<8, NCXP, true, (NW == 8 ? 8 : 4)>(cbase + r_cta, lda, slab_n, nc, Ws, lane, warp, NW, load_a);
     }
     LF_T(4);
 }
@@ -291,10 +309,17 @@ int larfb_leaf_fused(cudaStream_t st, double* a_leaf, size_t lda, size_t ml, siz
     G = (int)std::min<size_t>((size_t)G, std::min<size_t>(kLarfbMaxCtas, ceil_div(ml, (size_t)64)));
     const size_t rows_cta = round_up(ceil_div(ml, (size_t)G), (size_t)64);
     G = (int)ceil_div(ml, rows_cta);
-    const size_t smem = std::max<size_t>(8 * (size_t)W * RLD, (size_t)W * NCXP + W * (W + 1)) * sizeof(double);
+    static const int nw = [] { const char* e = getenv("NAB_LARFB_WARPS"); return (e && atoi(e) == 8) ? 8 : 16; }();
+    const size_t smem = std::max<size_t>((size_t)nw * W * RLD, (size_t)W * NCXP + W * (W + 1)) * sizeof(double);
     static std::once_flag once;
     static cudaError_t attr_err = cudaSuccess;
-    std::call_once(once, [smem] { attr_err = cudaFuncSetAttribute(larfb_leaf_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); });
+    std::call_once(once, [] {
+        attr_err = cudaFuncSetAttribute(larfb_leaf_fused_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        (int)(std::max<size_t>(8 * (size_t)W * RLD, (size_t)W * NCXP + W * (W + 1)) * sizeof(double)));
+        if (attr_err == cudaSuccess)
+            attr_err = cudaFuncSetAttribute(larfb_leaf_fused_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                            (int)(std::max<size_t>(16 * (size_t)W * RLD, (size_t)W * NCXP + W * (W + 1)) * sizeof(double)));
+    });
     if (attr_err != cudaSuccess) return cuda_fail(attr_err, "cudaFuncSetAttribute(larfb_fused)", __FILE__, __LINE__);
     LarfbParams p;
     p.a = a_leaf; p.lda = (long long)lda; p.ml = (int)ml; p.w = (int)w; p.nc = (int)nc; p.rows_cta = (int)rows_cta; p.tau = tau;
@@ -303,7 +328,8 @@ int larfb_leaf_fused(cudaStream_t st, double* a_leaf, size_t lda, size_t ml, siz
     p.flags = reinterpret_cast<int*>(p.total + (size_t)W * NCX);
     p.seq = ++*seq;
     void* args[] = {(void*)&p};
-    NAB_CUDA(cudaLaunchCooperativeKernel((void*)larfb_leaf_fused_kernel, dim3((unsigned)G), dim3(T), args, smem, st));
+    if (nw == 8) NAB_CUDA(cudaLaunchCooperativeKernel((void*)larfb_leaf_fused_kernel<8>, dim3((unsigned)G), dim3(256), args, smem, st));
+    else NAB_CUDA(cudaLaunchCooperativeKernel((void*)larfb_leaf_fused_kernel<16>, dim3((unsigned)G), dim3(512), args, smem, st));
     count_launch();
     return NA_OK;
 }

@@ -29,8 +29,18 @@ constexpr int ROWS = T * RPT; // rows per CTA
 constexpr int W = 32;         // panel width the registers are laid out for
 }  // namespace qrr
 
+#ifdef NAB_GEQR2_PROF   // per-phase cycle counters of CTA 1 / thread 0 (tools/qr_timing.py), off in the product build
+__device__ long long g_geqr2r_prof[16];
+#define RPROF(i) do { if (threadIdx.x == 0 && blockIdx.x == 1) { const long long t_ = clock64(); g_geqr2r_prof[i] += t_ - rt_prev; rt_prev = t_; } } while (0)
+#else
+#define RPROF(i) do { } while (0)
+#endif
+
 __global__ void __launch_bounds__(qrr::T, 1) geqr2_reg_kernel(const Geqr2Params p) {
     using namespace qrr;
+#ifdef NAB_GEQR2_PROF
+    long long rt_prev = clock64();
+#endif
     __shared__ double wred[8 * 32];          // per-warp partial sums / reducer scratch
     __shared__ double tot[32];               // totals T_j of the column being received
     __shared__ double rowv[32];              // row c
@@ -152,21 +162,32 @@ __global__ void __launch_bounds__(qrr::T, 1) geqr2_reg_kernel(const Geqr2Params 
                     const double v = g == c ? 1.0 : ac * scale;     // v[c] = 1; the diagonal slot holds beta (set by the caller)
 #pragma unroll
                     for (int jj = 0; jj < 8; ++jj) if (J0 + jj == c && g != c) a[k][J0 + jj] = v;
+                    // dots[j] = 0 for j <= c and j >= w, so the finished columns of the group need no predicate -- unless v
+                    // is not finite (0 * inf): then only the columns right of c may change, as in the reference
+                    if (isfinite(v)) {
 #pragma unroll
-                    for (int j = J0; j < W; ++j) if (j >= cn) a[k][j] -= dots[j] * v;      // dots[j] = 0 for j >= w
+                        for (int j = J0; j < W; ++j) a[k][j] = fma(-dots[j], v, a[k][j]);
+                    } else {
+#pragma unroll
+                        for (int j = J0; j < W; ++j) if (j >= cn) a[k][j] = fma(-dots[j], v, a[k][j]);
+                    }
                 }
                 double xs = 0.0;
 #pragma unroll
                 for (int jj = 0; jj <= 8; ++jj) if (J0 + jj < W && J0 + jj == cn) xs = a[k][J0 + jj < W ? J0 + jj : 0];
                 const double x = g > cn ? xs : 0.0;
+                // sums of the finished columns (j < cn) are garbage that is never published
 #pragma unroll
-                for (int j = J0; j < W; ++j) if (j >= cn) vals[j] = fma(x, a[k][j], vals[j]);
+                for (int j = J0; j < W; ++j) vals[j] = fma(x, a[k][j], vals[j]);
             }
         }
+        RPROF(3);
         if (cn >= ncol) return;                              // nothing left to exchange (uniform)
         const double mine = warp_reduce_scatter32(vals, lane);
         wred[warp * 32 + lane] = mine;
+        RPROF(4);
         __syncthreads();
+        RPROF(5);
         const double seq = (double)(p.seq0 + cn + 1);
         const int par = cn & 1;
         if (tid < 32) {
@@ -191,7 +212,9 @@ __global__ void __launch_bounds__(qrr::T, 1) geqr2_reg_kernel(const Geqr2Params 
         constexpr int J0 = 8 * decltype(cg_tag)::value;
 #pragma unroll 1
         for (int c = J0; c < J0 + 8 && c < ncol; ++c) {
+            RPROF(0);
             receive(c);
+            RPROF(1);
             const double alpha = rowv[c], sigma = tot[c];
             const double nrm = sqrt(alpha * alpha + sigma);
             double beta = 0.0, tau = 0.0, scale = 0.0;
@@ -208,8 +231,11 @@ __global__ void __launch_bounds__(qrr::T, 1) geqr2_reg_kernel(const Geqr2Params 
                 for (int jj = 0; jj < 8; ++jj) if (J0 + jj == c) a[0][J0 + jj] = beta;
             }
             __syncthreads();
+            RPROF(2);
             pass(cg_tag, c, scale);
+            RPROF(6);
             __syncthreads();
+            RPROF(7);
         }
     };
     static_for<0, W / 8>(group);
@@ -249,3 +275,11 @@ int geqr2_panel_reg(cudaStream_t st, double* a_panel, size_t lda, size_t m, size
 }
 
 }  // namespace nab
+
+#if defined(NAB_GEQR2_PROF) && defined(NAB_DEBUG_HOOKS)   // debug build only (nalgebra_b200/build.py)
+extern "C" __attribute__((visibility("default"))) int na_debug_geqr2r_prof(long long* out, int reset) {
+    cudaMemcpyFromSymbol(out, nab::g_geqr2r_prof, sizeof(long long) * 16);
+    if (reset) { long long z[16] = {0}; cudaMemcpyToSymbol(nab::g_geqr2r_prof, z, sizeof(z)); }
+    return 0;
+}
+#endif

@@ -49,7 +49,7 @@ __global__ void __launch_bounds__(ru::T, 1) rank_update_kernel(double* __restric
 #pragma unroll
         for (int ks = 0; ks < KS; ++ks) na[ks] = rok ? -arow[r + (long long)(4 * ks) * lda] : 0.0;
     };
-    dmma_stream_update<KS, NP, false>(c + r_cta + (long long)col0 * ldc, ldc, nrows, ncb, bs, lane, warp, T / 32, load_a);
+    dmma_stream_update<KS, NP, false, 8>(c + r_cta + (long long)col0 * ldc, ldc, nrows, ncb, bs, lane, warp, T / 32, load_a);
 }
 
 // C (m x n, ldc) -= A (m x k, lda) * B (k x n, ldb), all column-major.  Returns NA_OK when it ran, 1 when the shape is
