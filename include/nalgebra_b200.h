@@ -228,7 +228,9 @@ NAB_API int na_tri_solve_f64_dev(int lower, int trans, int unit_diag, size_t n, 
 NAB_API int na_set_gemm_sm_limit(int max_ctas);
 
 /* Tuning / diagnostic switches, never needed for correctness.  Keys: "lu_lookahead" (0: factor with the plain
- * recursive driver instead of the two-stream look-ahead driver; the tests compare the two paths' pivots). */
+ * recursive driver instead of the two-stream look-ahead driver; the tests compare the two paths' pivots);
+ * "qr_reg_leaf" (0: shared-memory GEQR2 leaf + two-stream look-ahead driver instead of the register-resident leaf +
+ * plain outer loop); "qr_fused" (0: in-panel block reflectors as GEMM sequences instead of the fused kernel). */
 NAB_API int na_set_tuning(const char* key, long value);
 
 /* ---- building blocks of the multi-GPU (1D block-cyclic) factorizations, device pointers ------ */

@@ -91,16 +91,15 @@ struct QrWork {
 // 32-wide block reflector: one fused cooperative kernel (panel_qr_fused.cu) when the leaf is tall enough for its two
 // grid-wide hand-offs to pay, the GEMM sequence otherwise.  vleaf / sleaf / wkleaf: leaf-level workspaces of the
 // latter.  max_ctas: SMs the panel chain may occupy (0 = all).
-static bool qr_fused_enabled() {
-    static bool v = [] { const char* e = getenv("NAB_QR_FUSED"); return e ? atoi(e) != 0 : true; }();
-    return v;
-}
+static bool qr_fused_enabled();
 // NAB_QR_LEAF=smem keeps the shared-memory GEQR2 leaf everywhere (A/B timing); default: the register-resident leaf
 // (panel_qr_reg.cu) wherever its grid (512 rows per CTA) fits the SMs the panel may use.
-static bool qr_reg_leaf_enabled() {
-    static bool v = [] { const char* e = getenv("NAB_QR_LEAF"); return !(e && strcmp(e, "smem") == 0); }();
-    return v;
-}
+static long g_qr_reg_leaf = [] { const char* e = getenv("NAB_QR_LEAF"); return (long)!(e && strcmp(e, "smem") == 0); }();
+static long g_qr_fused = [] { const char* e = getenv("NAB_QR_FUSED"); return (long)(e ? atoi(e) != 0 : 1); }();
+// na_set_tuning("qr_reg_leaf" / "qr_fused", 0 | 1): the tests factor the same matrix along every path
+void qr_set_tuning(int which, long v) { (which == 0 ? g_qr_reg_leaf : g_qr_fused) = v; }
+static bool qr_reg_leaf_enabled() { return g_qr_reg_leaf != 0; }
+static bool qr_fused_enabled() { return g_qr_fused != 0; }
 static bool qr_use_reg_leaf(size_t ml, int max_ctas) {
     if (!qr_reg_leaf_enabled() || ml < 4096) return false;
     const int g = geqr2_reg_grid(ml);

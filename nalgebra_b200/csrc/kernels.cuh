@@ -100,6 +100,7 @@ int scale_signs(cudaStream_t st, double* b, size_t ldb, size_t rows, size_t cols
 int trsm_left(cudaStream_t s, bool eff_lower, bool unit, size_t n, const double* m, ptrdiff_t rsm, ptrdiff_t csm,
               const double* diag_abs, const double* inv_blocks, double* b, ptrdiff_t rsb, ptrdiff_t csb, size_t nrhs);
 void lu_set_lookahead(long v);
+void qr_set_tuning(int which, long v);      // 0: register-resident GEQR2 leaf, 1: fused in-panel block reflector
 int cholesky_device(cudaStream_t s, size_t n, double* a, size_t lda, int use_sub, double sub, size_t* fail_col);
 int cholesky_solve_device(cudaStream_t s, size_t n, const double* l, size_t lda, double* b, size_t ldb, size_t nrhs);
 int lu_device(cudaStream_t s, size_t M, size_t N, double* a, size_t lda, size_t* swaps, size_t* nswaps);

@@ -440,17 +440,67 @@ def test_qr_65536x4096_residual_and_orthogonality(L):
     assert (torch.linalg.norm(axes, dim=0) - 1.0).abs().max().item() <= 1e-12   # unit Householder axes
 
 
-def test_qr_lookahead_path_vs_oracle(nab, oracle):
-    """The two-stream look-ahead QR driver (m >= 8192, >= 4 outer panels) against the oracle's nalgebra restatement."""
+@pytest.mark.parametrize("reg_leaf,fused", [(1, 1), (0, 1), (0, 0)])
+def test_qr_tall_paths_vs_oracle(nab, oracle, L, reg_leaf, fused):
+    """Tall QR (m >= 8192, >= 4 outer panels) along every driver: register-resident leaf + plain loop (default),
+    shared-memory leaf + two-stream look-ahead, and the GEMM-sequence in-panel reflectors, against the oracle."""
+    from nalgebra_b200 import _capi
     m, n = 8200, 1030
     a = oracle.uniform(m, n, 8) - 0.4
-    qr = nab.QR.new(a)
+    _capi.check(L.na_set_tuning(b"qr_reg_leaf", reg_leaf)); _capi.check(L.na_set_tuning(b"qr_fused", fused))
+    try:
+        qr = nab.QR.new(a)
+    finally:
+        _capi.check(L.na_set_tuning(b"qr_reg_leaf", 1)); _capi.check(L.na_set_tuning(b"qr_fused", 1))
     qr_ref, diag_ref = oracle.qr(a)
     assert np.abs(qr.qr_internal() - qr_ref).max() < 1e-10
     assert np.abs(qr.diag_internal() - diag_ref).max() < 1e-10
     q, r = qr.q(), qr.r()
     assert np.linalg.norm(q @ r - a) / np.linalg.norm(a) <= 10 * m * EPS
     assert np.abs(q.T @ q - np.eye(n)).max() <= 10 * m * EPS
+
+
+@pytest.mark.parametrize("shape", [(2100, 70), (2500, 300), (3000, 333), (4100, 257), (5000, 40)])
+def test_qr_fused_reflector_ragged_shapes(nab, oracle, shape):
+    """The fused in-panel block reflector (leaves with >= 2048 rows) and the register-resident leaf (>= 4096 rows) on
+    widths that are not multiples of 32 or 8, with a zero column (tau = 0) inside a fused leaf."""
+    m, n = shape
+    a = oracle.uniform(m, n, 8) - 0.4
+    if n > 45: a[:, 40] = 0.0
+    qr = nab.QR.new(a)
+    qr_ref, diag_ref = oracle.qr(a)
+    assert np.abs(qr.qr_internal() - qr_ref).max() < 1e-10
+    assert np.abs(qr.diag_internal() - diag_ref).max() < 1e-10
+
+
+def test_host_pointer_calls_stream_and_match_the_device_calls(nab, L):
+    """na_cholesky_f64 (lower triangle only over PCIe, finished panels streamed back) and na_qr_f64 (panels converted and
+    streamed back behind the factorization) must give the bits of the device-resident calls; Cholesky must leave the
+    host's strict upper triangle alone and report the failing column as before."""
+    import ctypes as C
+    import torch
+    from nalgebra_b200 import _capi
+    dev = torch.device("cuda:0"); s = torch.cuda.current_stream().cuda_stream
+    n = 2304                                                   # > 2 * 512: the look-ahead / streaming path
+    a0 = torch.empty(n * n, dtype=torch.float64, device=dev)
+    _capi.check(L.na_fill_spd_block_dev(a0.data_ptr(), n, n, n, 5, 0, 0, n, s))
+    a = a0.clone(); fail = C.c_size_t(0)
+    assert _capi.check(L.na_cholesky_f64_dev(n, a.data_ptr(), n, 0, 0.0, C.addressof(fail), s)) == 0
+    h0 = a0.cpu(); h = h0.clone().pin_memory()
+    assert _capi.check(L.na_cholesky_f64(n, h.data_ptr(), n, 0, 0.0, C.addressof(fail))) == 0
+    g, hm = a.cpu().view(n, n).t(), h.view(n, n).t()
+    assert torch.equal(torch.tril(g), torch.tril(hm))
+    assert torch.equal(torch.triu(hm, 1), torch.triu(h0.view(n, n).t(), 1))
+    h.copy_(h0); h.view(n, n)[1500, 1500] = -1.0
+    assert L.na_cholesky_f64(n, h.data_ptr(), n, 0, 0.0, C.addressof(fail)) == 1 and fail.value == 1500
+    m, nq = 8300, 1100
+    a0 = torch.empty(m * nq, dtype=torch.float64, device=dev); d = torch.empty(nq, dtype=torch.float64, device=dev)
+    _capi.check(L.na_fill_uniform_dev(a0.data_ptr(), m, nq, m, 8, s))
+    a = a0.clone()
+    _capi.check(L.na_qr_f64_dev(m, nq, a.data_ptr(), m, d.data_ptr(), s)); torch.cuda.synchronize()
+    h = a0.cpu().pin_memory(); hd = torch.empty(nq, dtype=torch.float64)
+    _capi.check(L.na_qr_f64(m, nq, h.data_ptr(), m, hd.data_ptr()))
+    assert torch.equal(a.cpu(), h) and torch.equal(d.cpu(), hd)
 
 
 def test_concurrent_calls_from_two_host_threads(L):
