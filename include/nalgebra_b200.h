@@ -210,6 +210,25 @@ NAB_API int na_col_piv_qr_f64(size_t m, size_t n, double* a, size_t lda, double*
 /* a, diag: DEVICE; p_swaps / np: HOST; synchronises `stream` before returning. */
 NAB_API int na_col_piv_qr_f64_dev(size_t m, size_t n, double* a, size_t lda, double* diag, size_t* p_swaps, size_t* np, void* stream);
 
+/* ---- two-sided Householder reductions (src/linalg/householder.rs:61-127) ---------------------- */
+/* Hessenberg::new (src/linalg/hessenberg.rs:61-100): a (n x n) is overwritten with nalgebra's packed `hess`: H in the upper
+ * Hessenberg part except its first subdiagonal, the unit Householder axis of step i in column i, rows i + 1..; subdiag[i]
+ * (n - 1 entries) = the signed norm clear_column_unchecked returns (H[i + 1, i] = |subdiag[i]|, the sign feeds
+ * householder::assemble_q).  n == 0 -> NA_EINVAL (the reference panics). */
+NAB_API int na_hessenberg_f64(size_t n, double* a, size_t lda, double* subdiag);
+/* a, subdiag: DEVICE.  Asynchronous on `stream`. */
+NAB_API int na_hessenberg_f64_dev(size_t n, double* a, size_t lda, double* subdiag, void* stream);
+/* SymmetricTridiagonal::new (src/linalg/symmetric_tridiagonal.rs:54-95): only the lower triangle of a is read and written;
+ * on return its diagonal is the diagonal of T, column i rows i + 1.. the axis of step i, off_diagonal[i] (n - 1 entries) the
+ * signed norm (T[i + 1, i] = |off_diagonal[i]|). */
+NAB_API int na_symmetric_tridiagonal_f64(size_t n, double* a, size_t lda, double* off_diagonal);
+NAB_API int na_symmetric_tridiagonal_f64_dev(size_t n, double* a, size_t lda, double* off_diagonal, void* stream);
+/* Bidiagonal::new (src/linalg/bidiagonal.rs:74-150): a (m x n) is overwritten with nalgebra's packed `uv` (m >= n: column
+ * axes in column i rows i.., row axes in row i columns i + 1..; m < n: row axes in row i columns i.., column axes in column i
+ * rows i + 1..); diagonal: min(m, n) signed norms, off_diagonal: min(m, n) - 1.  upper_diagonal = (m >= n). */
+NAB_API int na_bidiagonal_f64(size_t m, size_t n, double* a, size_t lda, double* diagonal, double* off_diagonal);
+NAB_API int na_bidiagonal_f64_dev(size_t m, size_t n, double* a, size_t lda, double* diagonal, double* off_diagonal, void* stream);
+
 /* ---- triangular solves (src/linalg/solve.rs:55-182) ---------------------------------------- */
 /* op(T) x = b in place on b (n x nrhs).  lower: 1 = lower, 0 = upper triangle of `t` is used.
  * trans: 0 = T, 1 = T^T.  unit_diag: 1 = implicit unit diagonal (solve_lower_triangular_with_diag_mut

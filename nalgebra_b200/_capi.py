@@ -62,6 +62,12 @@ SIGNATURES = {
     "na_full_piv_lu_f64_dev": (_int, [_sz, _sz, _p, _sz, _p, _p, _p, _p, _p]),
     "na_col_piv_qr_f64": (_int, [_sz, _sz, _p, _sz, _p, _p, _p]),
     "na_col_piv_qr_f64_dev": (_int, [_sz, _sz, _p, _sz, _p, _p, _p, _p]),
+    "na_hessenberg_f64": (_int, [_sz, _p, _sz, _p]),
+    "na_hessenberg_f64_dev": (_int, [_sz, _p, _sz, _p, _p]),
+    "na_symmetric_tridiagonal_f64": (_int, [_sz, _p, _sz, _p]),
+    "na_symmetric_tridiagonal_f64_dev": (_int, [_sz, _p, _sz, _p, _p]),
+    "na_bidiagonal_f64": (_int, [_sz, _sz, _p, _sz, _p, _p]),
+    "na_bidiagonal_f64_dev": (_int, [_sz, _sz, _p, _sz, _p, _p, _p]),
     "na_set_gemm_sm_limit": (_int, [_int]),
     "na_trsm_f64_dev": (_int, [_int, _int, _int, _int, _sz, _sz, _p, _sz, _p, _sz, _p]),
     "na_permute_rows_f64_dev": (_int, [_sz, _p, _sz, _sz, _p, _sz, _int, _p]),

@@ -1,0 +1,621 @@
+// factor_twosided.cu -- nalgebra's two-sided Householder reductions: Hessenberg, SymmetricTridiagonal, Bidiagonal.
+//
+// Reference: Hessenberg::new_with_workspace (/root/reference/src/linalg/hessenberg.rs:61-100) ->
+// householder::clear_column_unchecked(.., shift = 1, bilateral) (src/linalg/householder.rs:61-85) ->
+// reflection_axis_mut (householder.rs:19-53), Reflection::reflect_rows_with_sign / reflect_with_sign
+// (src/geometry/reflection.rs:70-131); SymmetricTridiagonal::new (src/linalg/symmetric_tridiagonal.rs:54-95: hegemv,
+// dotc, three hegerc, src/base/blas.rs:359-420, 868-900); Bidiagonal::new (src/linalg/bidiagonal.rs:74-150:
+// clear_column_unchecked / clear_row_unchecked, householder.rs:92-127).
+//
+// The reference applies every reflector with Level-1 sweeps: a product pass and an update pass over the trailing
+// matrix per side (four to six trips through memory per step).  These reductions cannot be blocked without changing
+// which vectors get stored, so they stay one-reflector-per-step, memory-bound Level-2 work -- but one persistent
+// cooperative kernel per factorization does each step in the minimum number of passes over HBM:
+//   Hessenberg / SymmetricTridiagonal: ONE read pass that forms both products at once (w = A u along rows and
+//     z = A^T u along columns of the same tile), ONE read-modify-write pass that applies both sides at once
+//     (d_j = u . (s A + (-2 s u_j) w)_j is s z_j + (-2 s u_j)(u . w) by linearity, so no pass over the half-updated
+//     matrix is needed);
+//   Bidiagonal: read pass (column products), read pass (row products of the column-reflected matrix formed on the
+//     fly), one read-modify-write pass that applies both reflections.
+// The trailing matrix is cut into (row block) x (column chunk) tasks, one per CTA: a thread owns U rows (coalesced
+// along the column), walks the columns of its chunk, keeps its row products in registers and reduces column products
+// with warp shuffles.  Partial products go to small per-task arrays and are summed in a fixed order (run-to-run
+// deterministic, no atomics).  The last CTA is the "leader": while the others run the update pass it updates the next
+// pivot column alone and turns it into the next reflection axis, so axis construction is off the critical path; two
+// grid barriers per step (four for Bidiagonal).  Per-element update arithmetic is the reference's (unfused multiply,
+// then add, same operand order); only the order of summation inside the products differs (results to rounding).
+#include <cooperative_groups.h>
+
+#include <algorithm>
+
+#include "common.cuh"
+#include "kernels.cuh"
+
+namespace cg = cooperative_groups;
+
+namespace nab {
+
+namespace ts {
+constexpr int T = 256;            // threads per CTA
+constexpr int U = 4;              // rows per thread
+constexpr int RB = T * U;         // rows per row block
+constexpr int NCB_MAX = 64;       // column chunks per row block (= partial row products to sum)
+constexpr int CB = 256;           // columns whose per-column factors are staged in shared memory at a time
+constexpr int NW = T / 32;
+
+enum Mode { HESS = 0, SYM = 1, BD_Z = 2, BD_W = 3 };
+
+struct Params {
+    double* a; long long lda; int m, n;
+    double* d;        // Hessenberg: subdiag; SymmetricTridiagonal: off_diagonal; Bidiagonal: diagonal
+    double* e;        // Bidiagonal: off_diagonal
+    double* wpart;    // [NCB_MAX][m]   partial row products by column chunk
+    double* zpart;    // [ceil(m / RB)][n] partial column products by row block
+    double* gpart;    // [G] partial u . w by task
+    double* fvec;     // [n] Bidiagonal: column-reflection factors of the step
+    double* vvec;     // [n] Bidiagonal: the row axis, contiguous
+    double* hh;       // [2][4] (sign, reflected) of the column axis and of the row axis, by step parity
+};
+
+struct Smem {
+    double zs[2][32][NW];
+    double c1[CB], c2[CB];
+    double red[NW];
+    double bc[4];
+};
+
+// ---- tiling of rows [row0, row0 + nrows) x columns [col0, col0 + ncols); tri: only j - col0 <= r - row0 ------------
+struct Tiling {
+    int row0, nrows, col0, ncols, nrb, gt, total; bool tri;      // 32-bit: gt * width and the summed widths stay below 2^31 for any matrix that fits the HBM
+    __device__ int width(int rb) const { return tri ? min(ncols, min(nrows, (rb + 1) * RB)) : ncols; }
+    __device__ int ncb(int rb) const {
+        const int w = width(rb);
+        int c = (int)((unsigned)(gt * w) / (unsigned)total);
+        c = min(c, NCB_MAX);
+        c = min(c, (w + 63) / 64);
+        return max(c, 1);
+    }
+    __device__ void init(int gt_, int row0_, int nrows_, int col0_, int ncols_, bool tri_) {
+        gt = gt_; row0 = row0_; nrows = nrows_; col0 = col0_; ncols = ncols_; tri = tri_;
+        nrb = (nrows + RB - 1) / RB;
+        total = 0;
+        for (int rb = 0; rb < nrb; ++rb) total += width(rb);
+        if (total < 1) total = 1;
+    }
+    __device__ int ntasks() const { int t = 0; for (int rb = 0; rb < nrb; ++rb) t += ncb(rb); return t; }
+    __device__ int rb_of_row(int r) const { return (r - row0) / RB; }
+};
+struct Task { int rb, cb, ncb, r0, r1, j0, j1; };
+__device__ inline bool find_task(const Tiling& tl, int t, Task& tk) {
+    int acc = 0;
+    for (int rb = 0; rb < tl.nrb; ++rb) {
+        const int c = tl.ncb(rb);
+        if (t < acc + c) {
+            tk.rb = rb; tk.cb = t - acc; tk.ncb = c;
+            tk.r0 = tl.row0 + rb * RB; tk.r1 = min(tl.row0 + tl.nrows, tk.r0 + RB);
+            const int w = tl.width(rb);
+            int cw = (w + c - 1) / c; cw = (cw + 3) & ~3;
+            tk.j0 = tl.col0 + min(w, tk.cb * cw); tk.j1 = tl.col0 + min(w, (tk.cb + 1) * cw);
+            return true;
+        }
+        acc += c;
+    }
+    return false;
+}
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ double block_sum(double v, double* red) {
+    v = warp_sum(v);
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+    __syncthreads();
+    double t = 0.0;
+#pragma unroll
+    for (int w = 0; w < NW; ++w) t += red[w];
+    return t;
+}
+
+// householder::reflection_axis_mut on a contiguous vector, by one CTA.  Returns the value the reference returns
+// (-signed_norm when a reflection is needed, signed_norm otherwise); *reflected says which.
+__device__ double make_axis(double* x, int len, double* red, bool* reflected) {
+    const int tid = threadIdx.x;
+    double s = 0.0;
+    for (int r = tid; r < len; r += T) { const double v = x[r]; s = fma(v, v, s); }
+    const double sq = block_sum(s, red);
+    const double nrm = sqrt(sq);
+    const double x0 = x[0];
+    const double modulus = x0 >= 0.0 ? x0 : -x0, sign = x0 >= 0.0 ? 1.0 : -1.0;       // simba to_exp
+    const double signed_norm = sign * nrm;
+    const double factor = (sq + modulus * nrm) * 2.0;
+    __syncthreads();                                             // x[0] read by everyone before it changes
+    if (factor != 0.0) {
+        const double sf = sqrt(factor);
+        double s2 = 0.0;
+        for (int r = tid; r < len; r += T) { const double v = (r == 0 ? x0 + signed_norm : x[r]) / sf; s2 = fma(v, v, s2); }
+        const double nn = sqrt(block_sum(s2, red));              // the second normalisation (householder.rs:38-46)
+        for (int r = tid; r < len; r += T) { const double v = (r == 0 ? x0 + signed_norm : x[r]) / sf; x[r] = v / nn; }
+        *reflected = true;
+        return -signed_norm;
+    }
+    if (tid == 0) x[0] = x0 + signed_norm;
+    *reflected = false;
+    return signed_norm;
+}
+__device__ __forceinline__ double signum_of(double v) { return signbit(v) ? -1.0 : 1.0; }
+
+// sum of the row-product partials of row r (row block rb of tiling tl)
+__device__ __forceinline__ double sum_wpart(const Params& p, const Tiling& tl, int r) {
+    const int c = tl.ncb(tl.rb_of_row(r));
+    double w = 0.0;
+    for (int q = 0; q < c; ++q) w += __ldcg(p.wpart + (size_t)q * p.m + r);
+    return w;
+}
+// sum of the column-product partials of column j: row blocks b0 .. nrb - 1
+__device__ __forceinline__ double sum_zpart(const Params& p, const Tiling& tl, int j) {
+    const int b0 = tl.tri ? (j - tl.col0) / RB : 0;
+    double z = 0.0;
+    for (int b = b0; b < tl.nrb; ++b) z += __ldcg(p.zpart + (size_t)b * p.n + j);
+    return z;
+}
+__device__ __forceinline__ double sum_gpart(const Params& p, int ntasks, Smem& sm) {
+    double g = 0.0;
+    if (threadIdx.x < 32) {
+        for (int t = threadIdx.x; t < ntasks; t += 32) g += __ldcg(p.gpart + t);
+        g = warp_sum(g);
+        if (threadIdx.x == 0) sm.bc[0] = g;
+    }
+    __syncthreads();
+    g = sm.bc[0];
+    __syncthreads();
+    return g;
+}
+
+// ---- the read pass of one task: row products w_r = sum_j e(r, j) x_j (registers -> wpart) and column products
+// z_j = sum_r e(r, j) y_r (-> zpart), plus the task's share of y . w (-> gpart).
+//   HESS: e = a, x_j = u_j, y_r = u_r (0 above the axis);   SYM: lower triangle, w over j <= r, z over r > j;
+//   BD_Z: z only, y_r = u_r;   BD_W: w only, e = column-reflected element f_j u_r + s a formed on the fly, x_j = v_j.
+template <int MODE>
+__device__ void pass_reduce(const Params& p, const Tiling& tl, const Task& tk, int task_id, int k, double su, bool refl_u, Smem& sm) {
+    constexpr bool WANT_W = MODE != BD_Z, WANT_Z = MODE != BD_W, TRI = MODE == SYM;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const long long lda = p.lda;
+    const double* ucol = p.a + (long long)k * lda;               // the column axis lives in column k
+    int r[U]; bool ok[U]; double y[U], wacc[U];
+#pragma unroll
+    for (int i = 0; i < U; ++i) {
+        r[i] = tk.r0 + tid + T * i; ok[i] = r[i] < tk.r1;
+        y[i] = (ok[i] && (MODE != HESS || r[i] > k)) ? ucol[r[i]] : 0.0;
+        wacc[i] = 0.0;
+    }
+    double gacc = 0.0;
+    int it = 0;
+    for (int jb = tk.j0; jb < tk.j1; jb += 32, ++it) {
+        const int buf = it & 1;
+#pragma unroll 2
+        for (int jj = 0; jj < 32; jj += 4) {
+            double av[4][U], x[4], f[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const int j = jb + jj + q;
+                const bool jok = j < tk.j1;
+                x[q] = 0.0; f[q] = 0.0;
+                if (WANT_W && jok) x[q] = MODE == BD_W ? __ldcg(p.vvec + j) : ucol[j];
+                if (MODE == BD_W && jok) f[q] = __ldcg(p.fvec + j);
+#pragma unroll
+                for (int i = 0; i < U; ++i) av[q][i] = (ok[i] && jok && (!TRI || j <= r[i])) ? p.a[r[i] + (long long)j * lda] : 0.0;
+            }
+            double zl[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const int j = jb + jj + q;
+                zl[q] = 0.0;
+#pragma unroll
+                for (int i = 0; i < U; ++i) {
+                    double ev = av[q][i];
+                    if (MODE == BD_W && refl_u) ev = ok[i] ? __dadd_rn(__dmul_rn(f[q], y[i]), __dmul_rn(su, ev)) : 0.0;
+                    if (WANT_W) wacc[i] = fma(ev, x[q], wacc[i]);
+                    if (WANT_Z) zl[q] = (!TRI || r[i] > j) ? fma(ev, y[i], zl[q]) : zl[q];
+                }
+            }
+            if (WANT_Z) {
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) zl[q] += __shfl_xor_sync(0xffffffffu, zl[q], o);
+                }
+                if (lane == 0) {
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) sm.zs[buf][jj + q][warp] = zl[q];
+                }
+            }
+        }
+        if (WANT_Z) {
+            __syncthreads();
+            if (tid < 32 && jb + tid < tk.j1) {
+                double z = 0.0;
+#pragma unroll
+                for (int w = 0; w < NW; ++w) z += sm.zs[buf][tid][w];
+                p.zpart[(size_t)tk.rb * p.n + jb + tid] = z;
+                if (MODE == HESS || MODE == SYM) gacc = fma(ucol[jb + tid], z, gacc);
+            }
+        }
+    }
+    if (WANT_W) {
+#pragma unroll
+        for (int i = 0; i < U; ++i)
+            if (ok[i]) { p.wpart[(size_t)tk.cb * p.m + r[i]] = wacc[i]; if (MODE == SYM) gacc = fma(y[i], wacc[i], gacc); }
+    }
+    if (MODE == HESS || MODE == SYM) {
+        const double g = block_sum(gacc, sm.red);
+        if (tid == 0) p.gpart[task_id] = g;
+    }
+    __syncthreads();                                             // zs / red are free for the next task
+}
+
+// ---- the read-modify-write pass of one task -------------------------------------------------------------------------
+//   HESS: a1 = (m2s u_j) w_r + s a;  rows below the pivot row: a2 = F_j u_r + s a1, F_j = (s z_j + (m2s u_j) g) m2s
+//   SYM : a = (-u_j) p_r + a;  a = (-p_j) u_r + a;  a = ((dot 2) u_j) u_r + a          (rows >= columns only)
+//   BD  : a1 = f_j u_r + su a (if the column reflected);  a2 = (m2sv v_j) w_r + sv a1 (if the row reflected)
+// skip_col: the column the leader updates itself.
+template <int MODE>
+__device__ void pass_update(const Params& p, const Tiling& tl, const Task& tk, int k, int skip_col, double su, bool refl_u, double sv,
+                            bool refl_v, double g, Smem& sm) {
+    const int tid = threadIdx.x;
+    const long long lda = p.lda;
+    const double* ucol = p.a + (long long)k * lda;
+    const double m2su = su * -2.0, m2sv = sv * -2.0;
+    int r[U]; bool ok[U]; double ur[U], wr[U];
+#pragma unroll
+    for (int i = 0; i < U; ++i) {
+        r[i] = tk.r0 + tid + T * i; ok[i] = r[i] < tk.r1;
+        ur[i] = (ok[i] && (MODE != HESS || r[i] > k)) ? ucol[r[i]] : 0.0;
+        wr[i] = 0.0;
+        if (ok[i]) {
+            if (MODE == SYM) wr[i] = 2.0 * (sum_wpart(p, tl, r[i]) + sum_zpart(p, tl, r[i]));        // p_r
+            else if (MODE == HESS || refl_v) wr[i] = sum_wpart(p, tl, r[i]);
+        }
+    }
+    for (int jb = tk.j0; jb < tk.j1; jb += CB) {
+        const int nb = min(CB, tk.j1 - jb);
+        __syncthreads();
+        for (int c = tid; c < nb; c += T) {
+            const int j = jb + c;
+            if (MODE == HESS) {
+                const double c1 = m2su * ucol[j];
+                sm.c1[c] = c1;
+                sm.c2[c] = __dmul_rn(__dadd_rn(__dmul_rn(su, sum_zpart(p, tl, j)), __dmul_rn(c1, g)), m2su);
+            } else if (MODE == SYM) {
+                sm.c1[c] = ucol[j];
+                sm.c2[c] = 2.0 * (sum_wpart(p, tl, j) + sum_zpart(p, tl, j));                             // p_j
+            } else {
+                sm.c1[c] = refl_u ? __ldcg(p.fvec + j) : 0.0;
+                sm.c2[c] = refl_v ? m2sv * __ldcg(p.vvec + j) : 0.0;
+            }
+        }
+        __syncthreads();
+#pragma unroll 2
+        for (int c0 = 0; c0 < nb; c0 += 4) {
+            double av[4][U];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const int j = jb + c0 + q;
+#pragma unroll
+                for (int i = 0; i < U; ++i)
+                    av[q][i] = (ok[i] && c0 + q < nb && j != skip_col && (MODE != SYM || j <= r[i])) ? p.a[r[i] + (long long)j * lda] : 0.0;
+            }
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const int j = jb + c0 + q;
+                if (c0 + q >= nb || j == skip_col) continue;
+                const double c1 = sm.c1[c0 + q], c2 = sm.c2[c0 + q];
+#pragma unroll
+                for (int i = 0; i < U; ++i) {
+                    if (!ok[i] || (MODE == SYM && j > r[i])) continue;
+                    double v = av[q][i];
+                    if (MODE == HESS) {
+                        v = __dadd_rn(__dmul_rn(c1, wr[i]), __dmul_rn(su, v));
+                        if (r[i] > k) v = __dadd_rn(__dmul_rn(c2, ur[i]), __dmul_rn(su, v));
+                    } else if (MODE == SYM) {
+                        v = __dadd_rn(__dmul_rn(-c1, wr[i]), v);
+                        v = __dadd_rn(__dmul_rn(-c2, ur[i]), v);
+                        v = __dadd_rn(__dmul_rn(__dmul_rn(g, c1), ur[i]), v);           // g = dot * 2
+                    } else {
+                        if (refl_u) v = __dadd_rn(__dmul_rn(c1, ur[i]), __dmul_rn(su, v));
+                        if (refl_v) v = __dadd_rn(__dmul_rn(c2, wr[i]), __dmul_rn(sv, v));
+                    }
+                    p.a[r[i] + (long long)j * lda] = v;
+                }
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// Hessenberg (SYMM = false) and SymmetricTridiagonal (SYMM = true): axes in column k, rows k + 1..
+// ------------------------------------------------------------------------------------------------------------------
+template <bool SYMM>
+__global__ void __launch_bounds__(T, 1) two_sided_kernel(const Params p) {
+    constexpr int MODE = SYMM ? SYM : HESS;
+    cg::grid_group grid = cg::this_grid();
+    __shared__ Smem sm;
+    const int tid = threadIdx.x, cta = blockIdx.x, G = gridDim.x, Gt = G - 1;
+    const bool leader = cta == G - 1;
+    const int n = p.n;
+    const long long lda = p.lda;
+    if (leader) {
+        bool refl;
+        const double nr = make_axis(p.a + 1, n - 1, sm.red, &refl);
+        if (tid == 0) { p.d[0] = nr; p.hh[0] = signum_of(nr); p.hh[1] = refl ? 1.0 : 0.0; }
+    }
+    grid.sync();
+    for (int k = 0; k + 1 < n; ++k) {
+        const double* hh = p.hh + 4 * (k & 1);
+        double* hn = p.hh + 4 * ((k + 1) & 1);
+        const double su = __ldcg(hh + 0);
+        const bool refl = __ldcg(hh + 1) != 0.0;
+        const int c = k + 1;                                        // the leader's column
+        Tiling tl;
+        tl.init(Gt, SYMM ? k + 1 : 0, SYMM ? n - k - 1 : n, k + 1, n - k - 1, SYMM);
+        const int ntasks = tl.ntasks();
+        if (refl) {
+            if (!leader)
+                for (int t = cta; t < ntasks; t += Gt) { Task tk; if (find_task(tl, t, tk)) pass_reduce<MODE>(p, tl, tk, t, k, su, true, sm); }
+            grid.sync();
+            double g = sum_gpart(p, ntasks, sm);
+            if (SYMM) g = (2.0 * g) * 2.0;                           // dot = u . p = 2 u . (w + z); the reference uses dot * 2
+            if (!leader) {
+                for (int t = cta; t < ntasks; t += Gt) { Task tk; if (find_task(tl, t, tk)) pass_update<MODE>(p, tl, tk, k, c, su, true, 1.0, false, g, sm); }
+            } else {
+                // column c of the updated matrix, then the axis of step k + 1 out of its rows c + 1..
+                const double* ucol = p.a + (long long)k * lda;
+                double* col = p.a + (long long)c * lda;
+                const double m2s = su * -2.0, uc = ucol[c];
+                if (!SYMM) {
+                    const double c1 = m2s * uc;
+                    const double c2 = __dmul_rn(__dadd_rn(__dmul_rn(su, sum_zpart(p, tl, c)), __dmul_rn(c1, g)), m2s);
+                    for (int r = tid; r < n; r += T) {
+                        double v = __dadd_rn(__dmul_rn(c1, sum_wpart(p, tl, r)), __dmul_rn(su, col[r]));
+                        if (r > k) v = __dadd_rn(__dmul_rn(c2, ucol[r]), __dmul_rn(su, v));
+                        col[r] = v;
+                    }
+                } else {
+                    const double pc = 2.0 * (sum_wpart(p, tl, c) + sum_zpart(p, tl, c));
+                    for (int r = c + tid; r < n; r += T) {
+                        const double pr = 2.0 * (sum_wpart(p, tl, r) + sum_zpart(p, tl, r));
+                        double v = col[r];
+                        v = __dadd_rn(__dmul_rn(-uc, pr), v);
+                        v = __dadd_rn(__dmul_rn(-pc, ucol[r]), v);
+                        v = __dadd_rn(__dmul_rn(__dmul_rn(g, uc), ucol[r]), v);
+                        col[r] = v;
+                    }
+                }
+                __syncthreads();
+            }
+        }
+        if (leader && c + 1 < n) {
+            bool r2;
+            const double nr = make_axis(p.a + (long long)c * lda + c + 1, n - c - 1, sm.red, &r2);
+            if (tid == 0) { p.d[c] = nr; hn[0] = signum_of(nr); hn[1] = r2 ? 1.0 : 0.0; }
+        }
+        grid.sync();
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// Bidiagonal, m >= n (upper bidiagonal; the wide case runs on the transpose): column axes in column k rows k..,
+// row axes in row k columns k + 1..
+// ------------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(T, 1) bidiagonal_kernel(const Params p) {
+    cg::grid_group grid = cg::this_grid();
+    __shared__ Smem sm;
+    const int tid = threadIdx.x, cta = blockIdx.x, G = gridDim.x, Gt = G - 1;
+    const bool leader = cta == G - 1;
+    const int m = p.m, n = p.n;
+    const long long lda = p.lda;
+    if (leader) {
+        bool refl;
+        const double nr = make_axis(p.a, m, sm.red, &refl);
+        if (tid == 0) { p.d[0] = nr; p.hh[0] = signum_of(nr); p.hh[1] = refl ? 1.0 : 0.0; }
+    }
+    grid.sync();
+    for (int k = 0; k + 1 < n; ++k) {
+        double* hh = p.hh + 4 * (k & 1);
+        double* hn = p.hh + 4 * ((k + 1) & 1);
+        const double su = __ldcg(hh + 0);
+        const bool refl_u = __ldcg(hh + 1) != 0.0;
+        const double* ucol = p.a + (long long)k * lda;
+        const int c = k + 1;
+        Tiling tz, tw;
+        tz.init(Gt, k, m - k, k + 1, n - k - 1, false);             // column products: rows k.., columns k + 1..
+        tw.init(Gt, k + 1, m - k - 1, k + 1, n - k - 1, false);     // row products / update: rows k + 1..
+        // ---- pass 1: z_j = u . a_j
+        if (refl_u && !leader) {
+            const int nt = tz.ntasks();
+            for (int t = cta; t < nt; t += Gt) { Task tk; if (find_task(tz, t, tk)) pass_reduce<BD_Z>(p, tz, tk, t, k, su, true, sm); }
+        }
+        grid.sync();
+        // ---- leader: factors f_j, row k of the column-reflected matrix, the row axis v (stored in row k and in vvec)
+        if (leader) {
+            const double m2s = su * -2.0, u0 = ucol[k];
+            for (int j = c + tid; j < n; j += T) {
+                double v = p.a[k + (long long)j * lda];
+                if (refl_u) {
+                    const double f = sum_zpart(p, tz, j) * m2s;       // reflection.rs:79
+                    p.fvec[j] = f;
+                    v = __dadd_rn(__dmul_rn(f, u0), __dmul_rn(su, v));
+                }
+                p.vvec[j] = v;
+            }
+            __syncthreads();
+            bool rv;
+            const double nr = make_axis(p.vvec + c, n - c, sm.red, &rv);
+            __syncthreads();
+            for (int j = c + tid; j < n; j += T) p.a[k + (long long)j * lda] = p.vvec[j];
+            if (tid == 0) { p.e[k] = nr; hh[2] = signum_of(nr); hh[3] = rv ? 1.0 : 0.0; }
+        }
+        grid.sync();
+        const double sv = __ldcg(hh + 2);
+        const bool refl_v = __ldcg(hh + 3) != 0.0;
+        // ---- pass 2: w_r = (column-reflected row r) . v
+        if (refl_v && !leader) {
+            const int nt = tw.ntasks();
+            for (int t = cta; t < nt; t += Gt) { Task tk; if (find_task(tw, t, tk)) pass_reduce<BD_W>(p, tw, tk, t, k, su, refl_u, sm); }
+        }
+        grid.sync();
+        // ---- pass 3: both reflections applied; the leader does column c and the next column axis
+        if (refl_u || refl_v) {
+            if (!leader) {
+                const int nt = tw.ntasks();
+                for (int t = cta; t < nt; t += Gt) { Task tk; if (find_task(tw, t, tk)) pass_update<BD_W>(p, tw, tk, k, c, su, refl_u, sv, refl_v, 0.0, sm); }
+            } else {
+                double* col = p.a + (long long)c * lda;
+                const double fc = refl_u ? __ldcg(p.fvec + c) : 0.0;
+                const double c2 = refl_v ? (sv * -2.0) * __ldcg(p.vvec + c) : 0.0;
+                for (int r = c + tid; r < m; r += T) {
+                    double v = col[r];
+                    if (refl_u) v = __dadd_rn(__dmul_rn(fc, ucol[r]), __dmul_rn(su, v));
+                    if (refl_v) v = __dadd_rn(__dmul_rn(c2, sum_wpart(p, tw, r)), __dmul_rn(sv, v));
+                    col[r] = v;
+                }
+                __syncthreads();
+            }
+        }
+        if (leader) {
+            bool r2;
+            const double nr = make_axis(p.a + (long long)c * lda + c, m - c, sm.red, &r2);
+            if (tid == 0) { p.d[c] = nr; hn[0] = signum_of(nr); hn[1] = r2 ? 1.0 : 0.0; }
+        }
+        grid.sync();
+    }
+}
+
+static int two_sided_grid(size_t m, size_t n) {
+    // one task per CTA plus the leader; small problems take fewer CTAs (cheaper grid barriers)
+    const size_t tasks = ceil_div(m, (size_t)RB) * std::max<size_t>(1, std::min<size_t>(NCB_MAX, n / 64));
+    return (int)std::min<size_t>((size_t)ctx().sm_count, std::max<size_t>(2, tasks + 1));
+}
+
+static int launch(const void* kernel, cudaStream_t s, size_t m, size_t n, double* a, size_t lda, double* d, double* e) {
+    const int G = two_sided_grid(m, n);
+    const size_t nrb = ceil_div(m, (size_t)RB);
+    Scratch ws;
+    const size_t ng = (size_t)G + nrb;                            // tasks: at most one per CTA plus one per row block
+    const size_t words = (size_t)NCB_MAX * m + nrb * n + ng + 2 * n + 8;
+    NAB_TRY(ws.alloc(words * sizeof(double), s));
+    NAB_CUDA(cudaMemsetAsync(ws.p, 0, words * sizeof(double), s));
+    double* w = ws.as<double>();
+    double* zp = w + (size_t)NCB_MAX * m; double* gp = zp + nrb * n; double* fv = gp + ng;
+    Params p{a, (long long)lda, (int)m, (int)n, d, e, w, zp, gp, fv, fv + n, fv + 2 * n};
+    void* args[] = {(void*)&p};
+    NAB_CUDA(cudaLaunchCooperativeKernel(kernel, dim3((unsigned)G), dim3(T), args, 0, s));
+    count_launch();
+    return NA_OK;
+}
+}  // namespace ts
+
+// subdiag: DEVICE, n - 1 signed norms (nalgebra's Hessenberg::subdiag)
+int hessenberg_device(cudaStream_t s, size_t n, double* a, size_t lda, double* subdiag) {
+    if (n < 2) return NA_OK;
+    if (lda < n) { set_error("hessenberg: lda < n"); return NA_EINVAL; }
+    if (n > 0x7fffffull) { set_error("hessenberg: dimension exceeds 2^23"); return NA_EINVAL; }
+    return ts::launch((const void*)ts::two_sided_kernel<false>, s, n, n, a, lda, subdiag, nullptr);
+}
+// off_diagonal: DEVICE, n - 1 signed norms; only the lower triangle of a is read / written
+int symmetric_tridiagonal_device(cudaStream_t s, size_t n, double* a, size_t lda, double* off_diagonal) {
+    if (n < 2) return NA_OK;
+    if (lda < n) { set_error("symmetric_tridiagonal: lda < n"); return NA_EINVAL; }
+    if (n > 0x7fffffull) { set_error("symmetric_tridiagonal: dimension exceeds 2^23"); return NA_EINVAL; }
+    return ts::launch((const void*)ts::two_sided_kernel<true>, s, n, n, a, lda, off_diagonal, nullptr);
+}
+// diagonal (min(m, n)) / off_diagonal (min(m, n) - 1): DEVICE.  m < n runs on the transpose (the row step of the wide
+// case is the column step of the tall one, householder.rs:92-127 against :61-85).
+int bidiagonal_device(cudaStream_t s, size_t m, size_t n, double* a, size_t lda, double* diagonal, double* off_diagonal) {
+    if (std::min(m, n) == 0) return NA_OK;
+    if (lda < m) { set_error("bidiagonal: lda < m"); return NA_EINVAL; }
+    if (m > 0x7fffffull || n > 0x7fffffull) { set_error("bidiagonal: dimension exceeds 2^23"); return NA_EINVAL; }
+    if (m >= n) return ts::launch((const void*)ts::bidiagonal_kernel, s, m, n, a, lda, diagonal, off_diagonal);
+    Scratch t;
+    NAB_TRY(t.alloc(m * n * sizeof(double), s));
+    NAB_TRY(copy_strided(s, t.as<double>(), 1, (ptrdiff_t)n, a, (ptrdiff_t)lda, 1, n, m));           // t (n x m) = a^T
+    NAB_TRY(ts::launch((const void*)ts::bidiagonal_kernel, s, n, m, t.as<double>(), n, diagonal, off_diagonal));
+    NAB_TRY(copy_strided(s, a, 1, (ptrdiff_t)lda, t.as<double>(), (ptrdiff_t)n, 1, m, n));
+    return NA_OK;
+}
+
+}  // namespace nab
+
+using namespace nab;
+
+extern "C" {
+
+int na_hessenberg_f64_dev(size_t n, double* a, size_t lda, double* subdiag, void* stream) {
+    NAB_TRY(ensure_init());
+    if (n == 0) { set_error("Cannot compute the hessenberg decomposition of an empty matrix."); return NA_EINVAL; }
+    if (!a || (n > 1 && !subdiag)) { set_error("hessenberg: null argument"); return NA_EINVAL; }
+    return hessenberg_device(static_cast<cudaStream_t>(stream), n, a, lda, subdiag);
+}
+
+int na_symmetric_tridiagonal_f64_dev(size_t n, double* a, size_t lda, double* off_diagonal, void* stream) {
+    NAB_TRY(ensure_init());
+    if (n == 0) { set_error("Unable to compute the symmetric tridiagonal decomposition of an empty matrix."); return NA_EINVAL; }
+    if (!a || (n > 1 && !off_diagonal)) { set_error("symmetric_tridiagonal: null argument"); return NA_EINVAL; }
+    return symmetric_tridiagonal_device(static_cast<cudaStream_t>(stream), n, a, lda, off_diagonal);
+}
+
+int na_bidiagonal_f64_dev(size_t m, size_t n, double* a, size_t lda, double* diagonal, double* off_diagonal, void* stream) {
+    NAB_TRY(ensure_init());
+    const size_t mn = std::min(m, n);
+    if (mn == 0) { set_error("Cannot compute the bidiagonalization of an empty matrix."); return NA_EINVAL; }
+    if (!a || !diagonal || (mn > 1 && !off_diagonal)) { set_error("bidiagonal: null argument"); return NA_EINVAL; }
+    return bidiagonal_device(static_cast<cudaStream_t>(stream), m, n, a, lda, diagonal, off_diagonal);
+}
+
+// host-pointer twins: upload, reduce, download (the first step touches the whole matrix and every step rewrites the
+// trailing block, so nothing can stream)
+static int two_sided_host(int which, size_t m, size_t n, double* a, size_t lda, double* d, double* e) {
+    const size_t mn = std::min(m, n);
+    if (!a || lda < m) { set_error("two-sided reduction: bad arguments"); return NA_EINVAL; }
+    std::lock_guard<std::mutex> lock(host_api_mutex());
+    cudaStream_t s = ctx().stream;
+    Scratch da, dd; size_t ldd;
+    NAB_TRY(upload_matrix(s, da, ldd, a, lda, m, n));
+    NAB_TRY(dd.alloc(2 * std::max<size_t>(mn, 1) * sizeof(double), s));
+    double* d_dev = dd.as<double>(); double* e_dev = d_dev + std::max<size_t>(mn, 1);
+    size_t nd = 0, ne = 0;
+    if (which == 0) { NAB_TRY(na_hessenberg_f64_dev(n, da.as<double>(), ldd, d_dev, s)); nd = n - 1; }
+    else if (which == 1) { NAB_TRY(na_symmetric_tridiagonal_f64_dev(n, da.as<double>(), ldd, d_dev, s)); nd = n - 1; }
+    else { NAB_TRY(na_bidiagonal_f64_dev(m, n, da.as<double>(), ldd, d_dev, e_dev, s)); nd = mn; ne = mn - 1; }
+    NAB_TRY(download_matrix(s, a, lda, da.as<double>(), ldd, m, n));
+    if (nd) NAB_CUDA(cudaMemcpyAsync(d, d_dev, nd * sizeof(double), cudaMemcpyDeviceToHost, s));
+    if (ne) NAB_CUDA(cudaMemcpyAsync(e, e_dev, ne * sizeof(double), cudaMemcpyDeviceToHost, s));
+    NAB_CUDA(cudaStreamSynchronize(s));
+    return NA_OK;
+}
+
+int na_hessenberg_f64(size_t n, double* a, size_t lda, double* subdiag) {
+    NAB_TRY(ensure_init());
+    if (n == 0) { set_error("Cannot compute the hessenberg decomposition of an empty matrix."); return NA_EINVAL; }
+    if (n > 1 && !subdiag) { set_error("hessenberg: null argument"); return NA_EINVAL; }
+    return two_sided_host(0, n, n, a, lda, subdiag, nullptr);
+}
+
+int na_symmetric_tridiagonal_f64(size_t n, double* a, size_t lda, double* off_diagonal) {
+    NAB_TRY(ensure_init());
+    if (n == 0) { set_error("Unable to compute the symmetric tridiagonal decomposition of an empty matrix."); return NA_EINVAL; }
+    if (n > 1 && !off_diagonal) { set_error("symmetric_tridiagonal: null argument"); return NA_EINVAL; }
+    return two_sided_host(1, n, n, a, lda, off_diagonal, nullptr);
+}
+
+int na_bidiagonal_f64(size_t m, size_t n, double* a, size_t lda, double* diagonal, double* off_diagonal) {
+    NAB_TRY(ensure_init());
+    const size_t mn = std::min(m, n);
+    if (mn == 0) { set_error("Cannot compute the bidiagonalization of an empty matrix."); return NA_EINVAL; }
+    if (!diagonal || (mn > 1 && !off_diagonal)) { set_error("bidiagonal: null argument"); return NA_EINVAL; }
+    return two_sided_host(2, m, n, a, lda, diagonal, off_diagonal);
+}
+
+}  // extern "C"

@@ -110,6 +110,10 @@ struct QrHostSink { double* h; size_t ldh; };
 int qr_device(cudaStream_t s, size_t m, size_t n, double* a, size_t lda, double* diag, double* tau_out, const QrHostSink* sink = nullptr);
 int apply_q_blocks(cudaStream_t s, size_t m, size_t k, const double* qr, size_t lda, const double* diag,
                    double* b, size_t ldb, size_t nb, bool forward, bool triangular_q, const double* lapack_tau);
+// factor_twosided.cu: d / e DEVICE vectors of signed norms
+int hessenberg_device(cudaStream_t s, size_t n, double* a, size_t lda, double* subdiag);
+int symmetric_tridiagonal_device(cudaStream_t s, size_t n, double* a, size_t lda, double* off_diagonal);
+int bidiagonal_device(cudaStream_t s, size_t m, size_t n, double* a, size_t lda, double* diagonal, double* off_diagonal);
 int upload_matrix(cudaStream_t s, Scratch& buf, size_t& ldd, const double* h, size_t ldh, size_t rows, size_t cols);
 int download_matrix(cudaStream_t s, double* h, size_t ldh, const double* d, size_t ldd, size_t rows, size_t cols);
 

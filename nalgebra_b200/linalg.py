@@ -657,6 +657,189 @@ class ColPivQR:
 
 
 # ---------------------------------------------------------------------------------------------
+# two-sided Householder reductions  (src/linalg/hessenberg.rs, symmetric_tridiagonal.rs, bidiagonal.rs)
+# ---------------------------------------------------------------------------------------------
+def _assemble_q(m: np.ndarray, signs: np.ndarray) -> np.ndarray:
+    """``householder::assemble_q`` (householder.rs:132-152): the axes sit in column i, rows i + 1.. of ``m``.  The product
+    of the reflectors is 1 (+) the ``QR::q`` of the storage one row down, so the blocked reflector application of the QR
+    path builds it (one device call)."""
+    n = m.shape[0]
+    q = np.zeros((n, n), order="F")
+    q[0, 0] = 1.0
+    if n > 1:
+        m = np.asfortranarray(m)
+        it = m.itemsize
+        sg = np.ascontiguousarray(signs, dtype=np.float64)
+        check(_capi.lib().na_qr_q_f64(n - 1, n - 1, m.ctypes.data + it, n, sg.ctypes.data, q.ctypes.data + (1 + n) * it, n))
+    return q
+
+
+class Hessenberg:
+    """``Hessenberg{hess, subdiag}``: matrix = Q H Q^T; ``hess`` holds H above the first subdiagonal and the unit
+    Householder axes below it, ``subdiag`` the signed norms."""
+
+    def __init__(self, hess: np.ndarray, subdiag: np.ndarray):
+        self.hess, self.subdiag = hess, subdiag
+
+    @classmethod
+    def new(cls, hess) -> "Hessenberg":                               # :48-100
+        m = _owned(hess)
+        if m.shape[0] != m.shape[1]:
+            raise ValueError("Cannot compute the hessenberg decomposition of a non-square matrix.")
+        n = m.shape[0]
+        if n == 0:
+            raise ValueError("Cannot compute the hessenberg decomposition of an empty matrix.")
+        sub = np.zeros(max(n - 1, 1))
+        check(_capi.lib().na_hessenberg_f64(n, m.ctypes.data, n, sub.ctypes.data))
+        return cls(m, sub[: n - 1].copy())
+
+    def hess_internal(self) -> np.ndarray:                            # :152
+        return self.hess
+
+    def h(self) -> np.ndarray:                                        # :128-140
+        n = self.hess.shape[0]
+        res = np.triu(self.hess, -1)
+        if n > 1:
+            res[np.arange(1, n), np.arange(n - 1)] = np.abs(self.subdiag)
+        return np.asfortranarray(res)
+
+    unpack_h = h                                                       # :111-123
+
+    def q(self) -> np.ndarray:                                        # :144-146
+        return _assemble_q(self.hess, self.subdiag)
+
+    def unpack(self):                                                 # :104-108
+        return self.q(), self.h()
+
+
+class SymmetricTridiagonal:
+    """``SymmetricTridiagonal{tri, off_diagonal}``: matrix = Q T Q^T for a symmetric matrix (only its lower triangle is
+    read); ``tri`` keeps T's diagonal and the Householder axes below the first subdiagonal."""
+
+    def __init__(self, tri: np.ndarray, off_diagonal: np.ndarray):
+        self.tri, self._off = tri, off_diagonal
+
+    @classmethod
+    def new(cls, m) -> "SymmetricTridiagonal":                        # :54-95
+        a = _owned(m)
+        if a.shape[0] != a.shape[1]:
+            raise ValueError("Unable to compute the symmetric tridiagonal decomposition of a non-square matrix.")
+        n = a.shape[0]
+        if n == 0:
+            raise ValueError("Unable to compute the symmetric tridiagonal decomposition of an empty matrix.")
+        off = np.zeros(max(n - 1, 1))
+        check(_capi.lib().na_symmetric_tridiagonal_f64(n, a.ctypes.data, n, off.ctypes.data))
+        return cls(a, off[: n - 1].copy())
+
+    def internal_tri(self) -> np.ndarray:                             # :99
+        return self.tri
+
+    def diagonal(self) -> np.ndarray:                                 # :135-140
+        return np.diagonal(self.tri).copy()
+
+    def off_diagonal(self) -> np.ndarray:                             # :144-149
+        return np.abs(self._off)
+
+    def q(self) -> np.ndarray:                                        # :153-155
+        return _assemble_q(self.tri, self._off)
+
+    def unpack(self):                                                 # :105-119
+        return self.q(), self.diagonal(), self.off_diagonal()
+
+    def unpack_tridiagonal(self):                                     # :122-131
+        return self.diagonal(), self.off_diagonal()
+
+    def recompose(self) -> np.ndarray:                                # :158-171
+        q = self.q()
+        n = self.tri.shape[0]
+        t = np.zeros((n, n), order="F")
+        t[np.arange(n), np.arange(n)] = np.diagonal(self.tri)
+        if n > 1:
+            idx = np.arange(n - 1)
+            t[idx + 1, idx] = np.abs(self._off); t[idx, idx + 1] = np.abs(self._off)
+        return mul(mul(q, t), np.asfortranarray(q.T))
+
+
+class Bidiagonal:
+    """``Bidiagonal{uv, diagonal, off_diagonal, upper_diagonal}``: matrix = U D V^T with D bidiagonal (upper when
+    nrows >= ncols, lower otherwise)."""
+
+    def __init__(self, uv: np.ndarray, diagonal: np.ndarray, off_diagonal: np.ndarray, upper_diagonal: bool):
+        self.uv, self._diag, self._off, self.upper_diagonal = uv, diagonal, off_diagonal, upper_diagonal
+
+    @classmethod
+    def new(cls, matrix) -> "Bidiagonal":                             # :74-150
+        m = _owned(matrix)
+        nrows, ncols = m.shape
+        mn = min(nrows, ncols)
+        if mn == 0:
+            raise ValueError("Cannot compute the bidiagonalization of an empty matrix.")
+        d = np.zeros(mn); e = np.zeros(max(mn - 1, 1))
+        check(_capi.lib().na_bidiagonal_f64(nrows, ncols, m.ctypes.data, nrows, d.ctypes.data, e.ctypes.data))
+        return cls(m, d, e[: mn - 1].copy(), nrows >= ncols)
+
+    def is_upper_diagonal(self) -> bool:                              # :154-156
+        return self.upper_diagonal
+
+    def uv_internal(self) -> np.ndarray:                              # :306
+        return self.uv
+
+    def diagonal(self) -> np.ndarray:                                 # :287-292
+        return np.abs(self._diag)
+
+    def off_diagonal(self) -> np.ndarray:                             # :296-301
+        return np.abs(self._off)
+
+    def d(self) -> np.ndarray:                                        # :185-200
+        mn = len(self._diag)
+        res = np.zeros((mn, mn), order="F")
+        res[np.arange(mn), np.arange(mn)] = np.abs(self._diag)
+        if mn > 1:
+            idx = np.arange(mn - 1)
+            if self.upper_diagonal:
+                res[idx, idx + 1] = np.abs(self._off)
+            else:
+                res[idx + 1, idx] = np.abs(self._off)
+        return res
+
+    @staticmethod
+    def _q_of(storage: np.ndarray, signs: np.ndarray, shift: int) -> np.ndarray:
+        """Product of the reflectors whose axes sit in column i, rows i + shift.. of ``storage`` (rows x cols): the first
+        min(rows, cols) columns of it, as a rows x min(rows, cols) matrix."""
+        storage = np.asfortranarray(storage)
+        rows, cols = storage.shape
+        k = min(rows, cols)
+        q = np.zeros((rows, k), order="F")
+        it = storage.itemsize
+        sg = np.ascontiguousarray(signs, dtype=np.float64)
+        if shift == 0:
+            check(_capi.lib().na_qr_q_f64(rows, cols, storage.ctypes.data, rows, sg.ctypes.data, q.ctypes.data, rows))
+        else:
+            q[0, 0] = 1.0
+            if rows > 1 and k > 1:
+                check(_capi.lib().na_qr_q_f64(rows - 1, k - 1, storage.ctypes.data + it, rows, sg.ctypes.data,
+                                              q.ctypes.data + (1 + rows) * it, rows))
+        return q
+
+    def u(self) -> np.ndarray:                                        # :205-240
+        if self.upper_diagonal:
+            return self._q_of(self.uv, self._diag, 0)
+        return self._q_of(self.uv, self._off, 1)
+
+    def v_t(self) -> np.ndarray:                                      # :244-283
+        # the row axes are the column axes of the transposed storage; V = (v_t)^T is their reflector product
+        st = np.asfortranarray(self.uv.T)
+        if self.upper_diagonal:
+            v = self._q_of(st, self._off, 1)
+        else:
+            v = self._q_of(st, self._diag, 0)
+        return np.asfortranarray(v.T)
+
+    def unpack(self):                                                 # :163-181
+        return self.u(), self.d(), self.v_t()
+
+
+# ---------------------------------------------------------------------------------------------
 # triangular solves  (src/linalg/solve.rs)
 # ---------------------------------------------------------------------------------------------
 def _tri_solve(t, b, lower: bool, trans: bool, unit: bool):

@@ -89,6 +89,17 @@ def lib() -> C.CDLL:
             getattr(_lib, name).restype = _int
         _lib.na_oracle_solve_lower_with_diag_f64.argtypes = [_sz, _p, _sz, _dbl, _p, _sz, _sz]
         _lib.na_oracle_solve_lower_with_diag_f64.restype = _int
+        _lib.na_oracle_hessenberg_f64.argtypes = [_sz, _p, _sz, _p]
+        _lib.na_oracle_hessenberg_f64.restype = None
+        _lib.na_oracle_assemble_q_f64.argtypes = [_sz, _p, _sz, _p, _p, _sz]
+        _lib.na_oracle_assemble_q_f64.restype = None
+        _lib.na_oracle_symmetric_tridiagonal_f64.argtypes = [_sz, _p, _sz, _p]
+        _lib.na_oracle_symmetric_tridiagonal_f64.restype = None
+        _lib.na_oracle_bidiagonal_f64.argtypes = [_sz, _sz, _p, _sz, _p, _p]
+        _lib.na_oracle_bidiagonal_f64.restype = _int
+        for name in ("na_oracle_bidiagonal_u_f64", "na_oracle_bidiagonal_v_t_f64"):
+            getattr(_lib, name).argtypes = [_sz, _sz, _p, _sz, _p, _p, _p, _sz]
+            getattr(_lib, name).restype = None
     return _lib
 
 
@@ -323,3 +334,89 @@ def solve_upper(a, b):
     b2 = b.reshape(n, -1, order="F") if b.ndim == 1 else b
     ok = lib().na_oracle_solve_upper_f64(n, _ptr(a), max(n, 1), _ptr(b2), max(n, 1), b2.shape[1])
     return b if ok else None
+
+
+# ---------------------------------------------------------------------------------------------
+# two-sided Householder reductions
+# ---------------------------------------------------------------------------------------------
+def hessenberg(a):
+    """``Hessenberg::new``: returns (packed hess, subdiag)."""
+    a = _f(a)
+    n = a.shape[0]
+    assert a.shape == (n, n) and n > 0
+    sub = np.zeros(max(n - 1, 1))
+    lib().na_oracle_hessenberg_f64(n, _ptr(a), n, _ptr(sub))
+    return a, sub[: n - 1]
+
+
+def assemble_q(m, signs):
+    """``householder::assemble_q`` (Hessenberg::q, SymmetricTridiagonal::q)."""
+    m = _f(m)
+    n = m.shape[0]
+    q = np.zeros((n, n), order="F")
+    s = np.ascontiguousarray(np.append(np.asarray(signs, dtype=np.float64), 0.0))
+    lib().na_oracle_assemble_q_f64(n, _ptr(m), n, _ptr(s), _ptr(q), n)
+    return q
+
+
+def hessenberg_h(hess, subdiag):
+    """``Hessenberg::h``: upper Hessenberg part with |subdiag| on the first subdiagonal."""
+    n = hess.shape[0]
+    h = np.triu(hess, -1)
+    if n > 1:
+        h[np.arange(1, n), np.arange(n - 1)] = np.abs(subdiag)
+    return np.asfortranarray(h)
+
+
+def symmetric_tridiagonal(a):
+    """``SymmetricTridiagonal::new``: returns (packed tri, off_diagonal); only the lower triangle is read / written."""
+    a = _f(a)
+    n = a.shape[0]
+    assert a.shape == (n, n) and n > 0
+    off = np.zeros(max(n - 1, 1))
+    lib().na_oracle_symmetric_tridiagonal_f64(n, _ptr(a), n, _ptr(off))
+    return a, off[: n - 1]
+
+
+def bidiagonal(a):
+    """``Bidiagonal::new``: returns (packed uv, diagonal, off_diagonal, upper_diagonal)."""
+    a = _f(a)
+    m, n = a.shape
+    mn = min(m, n)
+    assert mn > 0
+    d = np.zeros(mn); e = np.zeros(max(mn - 1, 1))
+    upper = lib().na_oracle_bidiagonal_f64(m, n, _ptr(a), m, _ptr(d), _ptr(e))
+    return a, d, e[: mn - 1], bool(upper)
+
+
+def bidiagonal_u(uv, d, e):
+    m, n = uv.shape
+    mn = min(m, n)
+    uv = _f(uv)
+    u = np.zeros((m, mn), order="F")
+    e1 = np.ascontiguousarray(np.append(np.asarray(e, dtype=np.float64), 0.0))
+    lib().na_oracle_bidiagonal_u_f64(m, n, _ptr(uv), m, _ptr(np.ascontiguousarray(d)), _ptr(e1), _ptr(u), m)
+    return u
+
+
+def bidiagonal_v_t(uv, d, e):
+    m, n = uv.shape
+    mn = min(m, n)
+    uv = _f(uv)
+    vt = np.zeros((mn, n), order="F")
+    e1 = np.ascontiguousarray(np.append(np.asarray(e, dtype=np.float64), 0.0))
+    lib().na_oracle_bidiagonal_v_t_f64(m, n, _ptr(uv), m, _ptr(np.ascontiguousarray(d)), _ptr(e1), _ptr(vt), mn)
+    return vt
+
+
+def bidiagonal_d(d, e, upper):
+    """``Bidiagonal::d``."""
+    mn = len(d)
+    res = np.diag(np.abs(d))
+    if mn > 1:
+        idx = np.arange(mn - 1)
+        if upper:
+            res[idx, idx + 1] = np.abs(e)
+        else:
+            res[idx + 1, idx] = np.abs(e)
+    return np.asfortranarray(res)

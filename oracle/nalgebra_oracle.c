@@ -635,3 +635,161 @@ void na_oracle_col_piv_qr_f64(size_t m, size_t n, double* a, size_t lda, double*
     }
     *np = lp;
 }
+
+/* ------------------------------------------------------------------------------------------ */
+/* Two-sided Householder reductions: Hessenberg, SymmetricTridiagonal, Bidiagonal               */
+/* ------------------------------------------------------------------------------------------ */
+
+/* src/geometry/reflection.rs:112-131 (reflect_rows_with_sign, bias = 0): work = lhs * axis through mul_to -> gemm ->
+ * gemm_uninit, whose result has one column (ncols1 = 1 <= SMALL_DIM, blas_uninit.rs:237-243), i.e. the gemv_uninit
+ * column loop; then lhs.gerc(-2 sign, work, axis, sign) = per column j: col_j = (alpha * axis[j]) * work + sign * col_j
+ * (blas.rs:615-643). */
+static void reflect_rows_with_sign(size_t nrows, size_t ncols, double* lhs, size_t ld, const double* axis, double* work, double sign) {
+    if (nrows == 0) return;
+    na_oracle_gemm_fallback_f64(nrows, ncols, 1, 1.0, lhs, 1, (ptrdiff_t)ld, axis, 1, (ptrdiff_t)ncols, 0.0, work, 1, (ptrdiff_t)nrows);
+    double m_two = sign * -2.0;
+    for (size_t j = 0; j < ncols; ++j) axpy(nrows, lhs + j * ld, 1, m_two * axis[j], work, 1, sign);
+}
+
+/* src/linalg/householder.rs:61-85 (clear_column_unchecked).  work != NULL: bilateral. */
+static double clear_column_unchecked(size_t m, size_t n, double* a, size_t lda, size_t icol, size_t shift, double* work) {
+    double* axis = &A_(a, lda, icol + shift, icol);
+    size_t len = m - icol - shift;
+    int not_zero;
+    double refl_norm = reflection_axis_mut(len, axis, &not_zero);
+    if (not_zero && icol + 1 < n) {
+        double sign = signum(refl_norm);
+        double* right = &A_(a, lda, 0, icol + 1);
+        if (work) reflect_rows_with_sign(m, n - icol - 1, right, lda, axis, work, sign);
+        reflect_with_sign(len, axis, right + icol + shift, lda, n - icol - 1, sign);
+    }
+    return refl_norm;
+}
+
+/* src/linalg/householder.rs:92-127 (clear_row_unchecked).  axis_packed: n entries, work: m entries. */
+static double clear_row_unchecked(size_t m, size_t n, double* a, size_t lda, double* axis_packed, double* work, size_t irow, size_t shift) {
+    size_t len = n - irow - shift;
+    double* axis = axis_packed + irow + shift;
+    for (size_t j = 0; j < len; ++j) axis[j] = A_(a, lda, irow, irow + shift + j);
+    int not_zero;
+    double refl_norm = reflection_axis_mut(len, axis, &not_zero);
+    if (not_zero && irow + 1 < m)
+        reflect_rows_with_sign(m - irow - 1, len, &A_(a, lda, irow + 1, irow + shift), lda, axis, work + irow + 1, signum(refl_norm));
+    for (size_t j = 0; j < len; ++j) A_(a, lda, irow, irow + shift + j) = axis[j];
+    return refl_norm;
+}
+
+/* src/linalg/hessenberg.rs:61-100: subdiag has n - 1 entries. */
+void na_oracle_hessenberg_f64(size_t n, double* a, size_t lda, double* subdiag) {
+    if (n < 2) return;
+    double* work = (double*)calloc(n, sizeof(double));
+    for (size_t ite = 0; ite + 1 < n; ++ite) subdiag[ite] = clear_column_unchecked(n, n, a, lda, ite, 1, work);
+    free(work);
+}
+
+/* src/linalg/householder.rs:132-152 (assemble_q): axes in column i, rows i + 1.. */
+void na_oracle_assemble_q_f64(size_t n, const double* m, size_t lda, const double* signs, double* q, size_t ldq) {
+    for (size_t j = 0; j < n; ++j) for (size_t i = 0; i < n; ++i) A_(q, ldq, i, j) = i == j ? 1.0 : 0.0;
+    if (n < 2) return;
+    for (size_t i = n - 1; i-- > 0;)
+        reflect_with_sign(n - i - 1, &A_(m, lda, i + 1, i), &A_(q, ldq, i + 1, i), ldq, n - i, signum(signs[i]));
+}
+
+/* src/base/blas.rs:359-420 (xxgemv with dotc): self = alpha * a * x + beta * self, lower triangle of a only. */
+static void hegemv(size_t dim, double* y, double alpha, const double* a, size_t lda, const double* x, double beta) {
+    if (dim == 0) return;
+    axpy(dim, y, 1, alpha * x[0], a, 1, beta);
+    y[0] += alpha * na_oracle_dot_f64(dim - 1, a + 1, 1, x + 1, 1);
+    for (size_t j = 1; j < dim; ++j) {
+        const double* col = a + j * lda;
+        double d = na_oracle_dot_f64(dim - j, col + j, 1, x + j, 1);
+        y[j] += alpha * d;
+        axpy(dim - j - 1, y + j + 1, 1, alpha * x[j], col + j + 1, 1, 1.0);
+    }
+}
+/* src/base/blas.rs:868-900 (xxgerx): lower triangle only, per column j: self[j.., j] = (alpha * y[j]) * x[j..] + beta * self[j.., j]. */
+static void hegerc(size_t dim, double* a, size_t lda, double alpha, const double* x, const double* y, double beta) {
+    for (size_t j = 0; j < dim; ++j) axpy(dim - j, a + j + j * lda, 1, alpha * y[j], x + j, 1, beta);
+}
+
+/* src/linalg/symmetric_tridiagonal.rs:54-95: reads / writes the lower triangle only; off_diagonal has n - 1 entries. */
+void na_oracle_symmetric_tridiagonal_f64(size_t n, double* a, size_t lda, double* off_diagonal) {
+    if (n < 2) return;
+    double* p = (double*)calloc(n - 1, sizeof(double));
+    for (size_t i = 0; i + 1 < n; ++i) {
+        size_t dim = n - i - 1;
+        double* axis = &A_(a, lda, i + 1, i);
+        double* m = &A_(a, lda, i + 1, i + 1);
+        int not_zero;
+        off_diagonal[i] = reflection_axis_mut(dim, axis, &not_zero);
+        if (not_zero) {
+            double* pp = p + i;
+            hegemv(dim, pp, 2.0, m, lda, axis, 0.0);
+            double dot = na_oracle_dot_f64(dim, axis, 1, pp, 1);
+            hegerc(dim, m, lda, -1.0, pp, axis, 1.0);
+            hegerc(dim, m, lda, -1.0, axis, pp, 1.0);
+            hegerc(dim, m, lda, dot * 2.0, axis, axis, 1.0);
+        }
+    }
+    free(p);
+}
+
+/* src/linalg/bidiagonal.rs:74-150.  diagonal: min(m, n) entries, off_diagonal: min(m, n) - 1.  Returns upper_diagonal. */
+int na_oracle_bidiagonal_f64(size_t m, size_t n, double* a, size_t lda, double* diagonal, double* off_diagonal) {
+    size_t dim = m < n ? m : n;
+    int upper = m >= n;
+    if (dim == 0) return upper;
+    double* axis_packed = (double*)calloc(n, sizeof(double));
+    double* work = (double*)calloc(m, sizeof(double));
+    if (upper) {
+        for (size_t ite = 0; ite + 1 < dim; ++ite) {
+            diagonal[ite] = clear_column_unchecked(m, n, a, lda, ite, 0, NULL);
+            off_diagonal[ite] = clear_row_unchecked(m, n, a, lda, axis_packed, work, ite, 1);
+        }
+        diagonal[dim - 1] = clear_column_unchecked(m, n, a, lda, dim - 1, 0, NULL);
+    } else {
+        for (size_t ite = 0; ite + 1 < dim; ++ite) {
+            diagonal[ite] = clear_row_unchecked(m, n, a, lda, axis_packed, work, ite, 0);
+            off_diagonal[ite] = clear_column_unchecked(m, n, a, lda, ite, 1, NULL);
+        }
+        diagonal[dim - 1] = clear_row_unchecked(m, n, a, lda, axis_packed, work, dim - 1, 0);
+    }
+    free(axis_packed); free(work);
+    return upper;
+}
+
+/* src/linalg/bidiagonal.rs:205-240 (u): m x min(m, n). */
+void na_oracle_bidiagonal_u_f64(size_t m, size_t n, const double* uv, size_t lda, const double* diagonal, const double* off_diagonal,
+                                double* u, size_t ldu) {
+    size_t dim = m < n ? m : n;
+    int upper = m >= n;
+    size_t shift = upper ? 0 : 1;
+    for (size_t j = 0; j < dim; ++j) for (size_t i = 0; i < m; ++i) A_(u, ldu, i, j) = i == j ? 1.0 : 0.0;
+    for (size_t i = dim - shift; i-- > 0;) {
+        const double* axis = &A_(uv, lda, i + shift, i);
+        size_t len = m - i - shift;
+        if (na_oracle_dot_f64(len, axis, 1, axis, 1) == 0.0) continue;
+        double sign = upper ? signum(diagonal[i]) : signum(off_diagonal[i]);
+        reflect_with_sign(len, axis, &A_(u, ldu, i + shift, i), ldu, dim - i, sign);
+    }
+}
+
+/* src/linalg/bidiagonal.rs:244-283 (v_t): min(m, n) x n. */
+void na_oracle_bidiagonal_v_t_f64(size_t m, size_t n, const double* uv, size_t lda, const double* diagonal, const double* off_diagonal,
+                                  double* vt, size_t ldvt) {
+    size_t dim = m < n ? m : n;
+    int upper = m >= n;
+    size_t shift = upper ? 1 : 0;
+    for (size_t j = 0; j < n; ++j) for (size_t i = 0; i < dim; ++i) A_(vt, ldvt, i, j) = i == j ? 1.0 : 0.0;
+    double* work = (double*)calloc(dim ? dim : 1, sizeof(double));
+    double* axis_packed = (double*)calloc(n ? n : 1, sizeof(double));
+    for (size_t i = dim - shift; i-- > 0;) {
+        size_t len = n - i - shift;
+        double* axis = axis_packed + i + shift;
+        for (size_t j = 0; j < len; ++j) axis[j] = A_(uv, lda, i, i + shift + j);
+        if (na_oracle_dot_f64(len, axis, 1, axis, 1) == 0.0) continue;
+        double sign = upper ? signum(off_diagonal[i]) : signum(diagonal[i]);
+        reflect_rows_with_sign(dim - i, len, &A_(vt, ldvt, i, i + shift), ldvt, axis, work + i, sign);
+    }
+    free(work); free(axis_packed);
+}

@@ -101,6 +101,21 @@ void na_oracle_full_piv_lu_f64(size_t m, size_t n, double* a, size_t lda, size_t
 /* src/linalg/col_piv_qr.rs:56-93.  Storage as na_oracle_qr_f64. */
 void na_oracle_col_piv_qr_f64(size_t m, size_t n, double* a, size_t lda, double* diag, size_t* p_swaps, size_t* np);
 
+/* ---- two-sided Householder reductions (householder.rs:61-127, reflection.rs:70-131) ---- */
+/* src/linalg/hessenberg.rs:61-100: axes in column i rows i + 1.., H in the upper Hessenberg part, subdiag: n - 1 signed norms. */
+void na_oracle_hessenberg_f64(size_t n, double* a, size_t lda, double* subdiag);
+/* src/linalg/householder.rs:132-152 (assemble_q), used by Hessenberg::q and SymmetricTridiagonal::q. */
+void na_oracle_assemble_q_f64(size_t n, const double* m, size_t lda, const double* signs, double* q, size_t ldq);
+/* src/linalg/symmetric_tridiagonal.rs:54-95 (lower triangle only; blas.rs:359-420 xxgemv, 868-900 xxgerx). */
+void na_oracle_symmetric_tridiagonal_f64(size_t n, double* a, size_t lda, double* off_diagonal);
+/* src/linalg/bidiagonal.rs:74-150; returns upper_diagonal (m >= n). */
+int na_oracle_bidiagonal_f64(size_t m, size_t n, double* a, size_t lda, double* diagonal, double* off_diagonal);
+/* src/linalg/bidiagonal.rs:205-240 and 244-283. */
+void na_oracle_bidiagonal_u_f64(size_t m, size_t n, const double* uv, size_t lda, const double* diagonal, const double* off_diagonal,
+                                double* u, size_t ldu);
+void na_oracle_bidiagonal_v_t_f64(size_t m, size_t n, const double* uv, size_t lda, const double* diagonal, const double* off_diagonal,
+                                  double* vt, size_t ldvt);
+
 #ifdef __cplusplus
 }
 #endif
