@@ -36,12 +36,31 @@ namespace cg = cooperative_groups;
 namespace nab {
 
 namespace ts {
+// -DNAB_TS_PROF: nanoseconds (globaltimer) spent by CTA 0 / the leader in each phase, summed over the steps
+#ifdef NAB_TS_PROF
+__device__ unsigned long long g_ts_prof[16];
+__device__ __forceinline__ unsigned long long gtime() { unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return t; }
+#define TS_MARK(slot)                                                                  \
+    do {                                                                               \
+        if (threadIdx.x == 0 && (blockIdx.x == 0 || blockIdx.x == gridDim.x - 1)) {    \
+            const unsigned long long now__ = gtime();                                  \
+            g_ts_prof[(blockIdx.x == 0 ? 0 : 8) + (slot)] += now__ - ts_t0;            \
+            ts_t0 = now__;                                                             \
+        }                                                                              \
+    } while (0)
+#define TS_START() unsigned long long ts_t0 = gtime()
+#else
+#define TS_MARK(slot) do {} while (0)
+#define TS_START() do {} while (0)
+#endif
 constexpr int T = 256;            // threads per CTA
 constexpr int U = 4;              // rows per thread
 constexpr int RB = T * U;         // rows per row block
 constexpr int NCB_MAX = 64;       // column chunks per row block (= partial row products to sum)
 constexpr int CB = 256;           // columns whose per-column factors are staged in shared memory at a time
 constexpr int NW = T / 32;
+constexpr int CG = 8;              // columns a thread has in flight (x U rows)
+constexpr int ZB = 64;             // columns between two CTA-wide reductions of the column products
 
 enum Mode { HESS = 0, SYM = 1, BD_Z = 2, BD_W = 3 };
 
@@ -50,6 +69,8 @@ struct Params {
     double* d;        // Hessenberg: subdiag; SymmetricTridiagonal: off_diagonal; Bidiagonal: diagonal
     double* e;        // Bidiagonal: off_diagonal
     double* wpart;    // [NCB_MAX][m]   partial row products by column chunk
+    double* wfull;    // [m]            their sums, written by the last task of a row block to finish the read pass
+    unsigned* cnt;    // [ceil(m / RB)] tasks of a row block that have delivered their partials (back to 0 after each pass)
     double* zpart;    // [ceil(m / RB)][n] partial column products by row block
     double* gpart;    // [G] partial u . w by task
     double* fvec;     // [n] Bidiagonal: column-reflection factors of the step
@@ -58,10 +79,11 @@ struct Params {
 };
 
 struct Smem {
-    double zs[2][32][NW];
+    double zs[2][ZB][NW];
     double c1[CB], c2[CB];
     double red[NW];
     double bc[4];
+    int last;
 };
 
 // ---- tiling of rows [row0, row0 + nrows) x columns [col0, col0 + ncols); tri: only j - col0 <= r - row0 ------------
@@ -94,7 +116,7 @@ __device__ inline bool find_task(const Tiling& tl, int t, Task& tk) {
             tk.rb = rb; tk.cb = t - acc; tk.ncb = c;
             tk.r0 = tl.row0 + rb * RB; tk.r1 = min(tl.row0 + tl.nrows, tk.r0 + RB);
             const int w = tl.width(rb);
-            int cw = (w + c - 1) / c; cw = (cw + 3) & ~3;
+            int cw = (w + c - 1) / c; cw = (cw + CG - 1) & ~(CG - 1);
             tk.j0 = tl.col0 + min(w, tk.cb * cw); tk.j1 = tl.col0 + min(w, (tk.cb + 1) * cw);
             return true;
         }
@@ -123,8 +145,18 @@ __device__ __forceinline__ double block_sum(double v, double* red) {
 // (-signed_norm when a reflection is needed, signed_norm otherwise); *reflected says which.
 __device__ double make_axis(double* x, int len, double* red, bool* reflected) {
     const int tid = threadIdx.x;
+    constexpr int R = 16;                                        // up to R entries per thread stay in registers: one trip through memory
+    const bool in_regs = len <= R * T;
+    double xr[R];
     double s = 0.0;
-    for (int r = tid; r < len; r += T) { const double v = x[r]; s = fma(v, v, s); }
+    if (in_regs) {
+#pragma unroll
+        for (int u = 0; u < R; ++u) { const int r = tid + u * T; xr[u] = r < len ? x[r] : 0.0; }
+#pragma unroll
+        for (int u = 0; u < R; ++u) s = fma(xr[u], xr[u], s);
+    } else {
+        for (int r = tid; r < len; r += T) { const double v = x[r]; s = fma(v, v, s); }
+    }
     const double sq = block_sum(s, red);
     const double nrm = sqrt(sq);
     const double x0 = x[0];
@@ -135,9 +167,20 @@ __device__ double make_axis(double* x, int len, double* red, bool* reflected) {
     if (factor != 0.0) {
         const double sf = sqrt(factor);
         double s2 = 0.0;
-        for (int r = tid; r < len; r += T) { const double v = (r == 0 ? x0 + signed_norm : x[r]) / sf; s2 = fma(v, v, s2); }
+        if (in_regs) {
+            if (tid == 0) xr[0] = x0 + signed_norm;
+#pragma unroll
+            for (int u = 0; u < R; ++u) { xr[u] = xr[u] / sf; s2 = fma(xr[u], xr[u], s2); }      // unscale_mut
+        } else {
+            for (int r = tid; r < len; r += T) { const double v = (r == 0 ? x0 + signed_norm : x[r]) / sf; s2 = fma(v, v, s2); }
+        }
         const double nn = sqrt(block_sum(s2, red));              // the second normalisation (householder.rs:38-46)
-        for (int r = tid; r < len; r += T) { const double v = (r == 0 ? x0 + signed_norm : x[r]) / sf; x[r] = v / nn; }
+        if (in_regs) {
+#pragma unroll
+            for (int u = 0; u < R; ++u) { const int r = tid + u * T; if (r < len) x[r] = xr[u] / nn; }
+        } else {
+            for (int r = tid; r < len; r += T) { const double v = (r == 0 ? x0 + signed_norm : x[r]) / sf; x[r] = v / nn; }
+        }
         *reflected = true;
         return -signed_norm;
     }
@@ -147,19 +190,22 @@ __device__ double make_axis(double* x, int len, double* red, bool* reflected) {
 }
 __device__ __forceinline__ double signum_of(double v) { return signbit(v) ? -1.0 : 1.0; }
 
-// sum of the row-product partials of row r (row block rb of tiling tl)
-__device__ __forceinline__ double sum_wpart(const Params& p, const Tiling& tl, int r) {
-    const int c = tl.ncb(tl.rb_of_row(r));
-    double w = 0.0;
-    for (int q = 0; q < c; ++q) w += __ldcg(p.wpart + (size_t)q * p.m + r);
-    return w;
+// Partial sums are fetched eight at a time (independent L2 loads in flight) and added in index order.
+__device__ __forceinline__ double sum_strided(const double* base, size_t stride, int count) {
+    double acc = 0.0;
+    for (int q0 = 0; q0 < count; q0 += 8) {
+        double v[8];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) v[q] = q0 + q < count ? __ldcg(base + (size_t)(q0 + q) * stride) : 0.0;
+#pragma unroll
+        for (int q = 0; q < 8; ++q) acc += v[q];
+    }
+    return acc;
 }
 // sum of the column-product partials of column j: row blocks b0 .. nrb - 1
 __device__ __forceinline__ double sum_zpart(const Params& p, const Tiling& tl, int j) {
     const int b0 = tl.tri ? (j - tl.col0) / RB : 0;
-    double z = 0.0;
-    for (int b = b0; b < tl.nrb; ++b) z += __ldcg(p.zpart + (size_t)b * p.n + j);
-    return z;
+    return sum_strided(p.zpart + (size_t)b0 * p.n + j, (size_t)p.n, tl.nrb - b0);
 }
 __device__ __forceinline__ double sum_gpart(const Params& p, int ntasks, Smem& sm) {
     double g = 0.0;
@@ -193,13 +239,13 @@ __device__ void pass_reduce(const Params& p, const Tiling& tl, const Task& tk, i
     }
     double gacc = 0.0;
     int it = 0;
-    for (int jb = tk.j0; jb < tk.j1; jb += 32, ++it) {
+    for (int jb = tk.j0; jb < tk.j1; jb += ZB, ++it) {
         const int buf = it & 1;
-#pragma unroll 2
-        for (int jj = 0; jj < 32; jj += 4) {
-            double av[4][U], x[4], f[4];
+        for (int jj = 0; jj < ZB && jb + jj < tk.j1; jj += CG) {
+            // CG columns x U rows per thread in flight
+            double av[CG][U], x[CG], f[CG];
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {
+            for (int q = 0; q < CG; ++q) {
                 const int j = jb + jj + q;
                 const bool jok = j < tk.j1;
                 x[q] = 0.0; f[q] = 0.0;
@@ -208,9 +254,9 @@ __device__ void pass_reduce(const Params& p, const Tiling& tl, const Task& tk, i
 #pragma unroll
                 for (int i = 0; i < U; ++i) av[q][i] = (ok[i] && jok && (!TRI || j <= r[i])) ? p.a[r[i] + (long long)j * lda] : 0.0;
             }
-            double zl[4];
+            double zl[CG];
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {
+            for (int q = 0; q < CG; ++q) {
                 const int j = jb + jj + q;
                 zl[q] = 0.0;
 #pragma unroll
@@ -222,20 +268,33 @@ __device__ void pass_reduce(const Params& p, const Tiling& tl, const Task& tk, i
                 }
             }
             if (WANT_Z) {
+                // eight column sums across the warp in 4 + 2 + 1 + 1 + 1 exchanges: each round a lane keeps half of its
+                // values and hands the other half to its partner (fixed tree: deterministic)
+                static_assert(CG == 8, "the exchange pattern below is written for eight columns");
+                double h4[4], h2[2], h1;
+                const bool b16 = lane & 16, b8 = lane & 8, b4 = lane & 4;
 #pragma unroll
-                for (int o = 16; o > 0; o >>= 1) {
-#pragma unroll
-                    for (int q = 0; q < 4; ++q) zl[q] += __shfl_xor_sync(0xffffffffu, zl[q], o);
+                for (int q = 0; q < 4; ++q) {
+                    const double send = b16 ? zl[q] : zl[q + 4], keep = b16 ? zl[q + 4] : zl[q];
+                    h4[q] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
                 }
-                if (lane == 0) {
 #pragma unroll
-                    for (int q = 0; q < 4; ++q) sm.zs[buf][jj + q][warp] = zl[q];
+                for (int q = 0; q < 2; ++q) {
+                    const double send = b8 ? h4[q] : h4[q + 2], keep = b8 ? h4[q + 2] : h4[q];
+                    h2[q] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
                 }
+                {
+                    const double send = b4 ? h2[0] : h2[1], keep = b4 ? h2[1] : h2[0];
+                    h1 = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+                }
+                h1 += __shfl_xor_sync(0xffffffffu, h1, 2);
+                h1 += __shfl_xor_sync(0xffffffffu, h1, 1);
+                if ((lane & 3) == 0) sm.zs[buf][jj + (b16 ? 4 : 0) + (b8 ? 2 : 0) + (b4 ? 1 : 0)][warp] = h1;
             }
         }
         if (WANT_Z) {
             __syncthreads();
-            if (tid < 32 && jb + tid < tk.j1) {
+            if (tid < ZB && jb + tid < tk.j1) {
                 double z = 0.0;
 #pragma unroll
                 for (int w = 0; w < NW; ++w) z += sm.zs[buf][tid][w];
@@ -248,6 +307,21 @@ __device__ void pass_reduce(const Params& p, const Tiling& tl, const Task& tk, i
 #pragma unroll
         for (int i = 0; i < U; ++i)
             if (ok[i]) { p.wpart[(size_t)tk.cb * p.m + r[i]] = wacc[i]; if (MODE == SYM) gacc = fma(y[i], wacc[i], gacc); }
+        // the last task of this row block to get here sums the partials (in chunk order, whoever does it) into wfull
+        __threadfence();
+        __syncthreads();
+        if (tid == 0) {
+            const unsigned done = atomicAdd(p.cnt + tk.rb, 1u);
+            sm.last = done + 1 == (unsigned)tk.ncb;
+            if (sm.last) p.cnt[tk.rb] = 0;
+            __threadfence();
+        }
+        __syncthreads();
+        if (sm.last) {
+#pragma unroll
+            for (int i = 0; i < U; ++i)
+                if (ok[i]) p.wfull[r[i]] = sum_strided(p.wpart + r[i], (size_t)p.m, tk.ncb);
+        }
     }
     if (MODE == HESS || MODE == SYM) {
         const double g = block_sum(gacc, sm.red);
@@ -275,8 +349,8 @@ __device__ void pass_update(const Params& p, const Tiling& tl, const Task& tk, i
         ur[i] = (ok[i] && (MODE != HESS || r[i] > k)) ? ucol[r[i]] : 0.0;
         wr[i] = 0.0;
         if (ok[i]) {
-            if (MODE == SYM) wr[i] = 2.0 * (sum_wpart(p, tl, r[i]) + sum_zpart(p, tl, r[i]));        // p_r
-            else if (MODE == HESS || refl_v) wr[i] = sum_wpart(p, tl, r[i]);
+            if (MODE == SYM) wr[i] = 2.0 * (__ldcg(p.wfull + r[i]) + sum_zpart(p, tl, r[i]));        // p_r
+            else if (MODE == HESS || refl_v) wr[i] = __ldcg(p.wfull + r[i]);
         }
     }
     for (int jb = tk.j0; jb < tk.j1; jb += CB) {
@@ -290,25 +364,24 @@ __device__ void pass_update(const Params& p, const Tiling& tl, const Task& tk, i
                 sm.c2[c] = __dmul_rn(__dadd_rn(__dmul_rn(su, sum_zpart(p, tl, j)), __dmul_rn(c1, g)), m2su);
             } else if (MODE == SYM) {
                 sm.c1[c] = ucol[j];
-                sm.c2[c] = 2.0 * (sum_wpart(p, tl, j) + sum_zpart(p, tl, j));                             // p_j
+                sm.c2[c] = 2.0 * (__ldcg(p.wfull + j) + sum_zpart(p, tl, j));                             // p_j
             } else {
                 sm.c1[c] = refl_u ? __ldcg(p.fvec + j) : 0.0;
                 sm.c2[c] = refl_v ? m2sv * __ldcg(p.vvec + j) : 0.0;
             }
         }
         __syncthreads();
-#pragma unroll 2
-        for (int c0 = 0; c0 < nb; c0 += 4) {
-            double av[4][U];
+        for (int c0 = 0; c0 < nb; c0 += CG) {
+            double av[CG][U];
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {
+            for (int q = 0; q < CG; ++q) {
                 const int j = jb + c0 + q;
 #pragma unroll
                 for (int i = 0; i < U; ++i)
                     av[q][i] = (ok[i] && c0 + q < nb && j != skip_col && (MODE != SYM || j <= r[i])) ? p.a[r[i] + (long long)j * lda] : 0.0;
             }
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {
+            for (int q = 0; q < CG; ++q) {
                 const int j = jb + c0 + q;
                 if (c0 + q >= nb || j == skip_col) continue;
                 const double c1 = sm.c1[c0 + q], c2 = sm.c2[c0 + q];
@@ -352,6 +425,7 @@ __global__ void __launch_bounds__(T, 1) two_sided_kernel(const Params p) {
         if (tid == 0) { p.d[0] = nr; p.hh[0] = signum_of(nr); p.hh[1] = refl ? 1.0 : 0.0; }
     }
     grid.sync();
+    TS_START();
     for (int k = 0; k + 1 < n; ++k) {
         const double* hh = p.hh + 4 * (k & 1);
         double* hn = p.hh + 4 * ((k + 1) & 1);
@@ -361,10 +435,13 @@ __global__ void __launch_bounds__(T, 1) two_sided_kernel(const Params p) {
         Tiling tl;
         tl.init(Gt, SYMM ? k + 1 : 0, SYMM ? n - k - 1 : n, k + 1, n - k - 1, SYMM);
         const int ntasks = tl.ntasks();
+        TS_MARK(0);
         if (refl) {
             if (!leader)
                 for (int t = cta; t < ntasks; t += Gt) { Task tk; if (find_task(tl, t, tk)) pass_reduce<MODE>(p, tl, tk, t, k, su, true, sm); }
+            TS_MARK(1);
             grid.sync();
+            TS_MARK(2);
             double g = sum_gpart(p, ntasks, sm);
             if (SYMM) g = (2.0 * g) * 2.0;                           // dot = u . p = 2 u . (w + z); the reference uses dot * 2
             if (!leader) {
@@ -378,14 +455,14 @@ __global__ void __launch_bounds__(T, 1) two_sided_kernel(const Params p) {
                     const double c1 = m2s * uc;
                     const double c2 = __dmul_rn(__dadd_rn(__dmul_rn(su, sum_zpart(p, tl, c)), __dmul_rn(c1, g)), m2s);
                     for (int r = tid; r < n; r += T) {
-                        double v = __dadd_rn(__dmul_rn(c1, sum_wpart(p, tl, r)), __dmul_rn(su, col[r]));
+                        double v = __dadd_rn(__dmul_rn(c1, __ldcg(p.wfull + r)), __dmul_rn(su, col[r]));
                         if (r > k) v = __dadd_rn(__dmul_rn(c2, ucol[r]), __dmul_rn(su, v));
                         col[r] = v;
                     }
                 } else {
-                    const double pc = 2.0 * (sum_wpart(p, tl, c) + sum_zpart(p, tl, c));
+                    const double pc = 2.0 * (__ldcg(p.wfull + c) + sum_zpart(p, tl, c));
                     for (int r = c + tid; r < n; r += T) {
-                        const double pr = 2.0 * (sum_wpart(p, tl, r) + sum_zpart(p, tl, r));
+                        const double pr = 2.0 * (__ldcg(p.wfull + r) + sum_zpart(p, tl, r));
                         double v = col[r];
                         v = __dadd_rn(__dmul_rn(-uc, pr), v);
                         v = __dadd_rn(__dmul_rn(-pc, ucol[r]), v);
@@ -395,13 +472,16 @@ __global__ void __launch_bounds__(T, 1) two_sided_kernel(const Params p) {
                 }
                 __syncthreads();
             }
+            TS_MARK(3);
         }
         if (leader && c + 1 < n) {
             bool r2;
             const double nr = make_axis(p.a + (long long)c * lda + c + 1, n - c - 1, sm.red, &r2);
             if (tid == 0) { p.d[c] = nr; hn[0] = signum_of(nr); hn[1] = r2 ? 1.0 : 0.0; }
         }
+        TS_MARK(4);
         grid.sync();
+        TS_MARK(5);
     }
 }
 
@@ -478,7 +558,7 @@ __global__ void __launch_bounds__(T, 1) bidiagonal_kernel(const Params p) {
                 for (int r = c + tid; r < m; r += T) {
                     double v = col[r];
                     if (refl_u) v = __dadd_rn(__dmul_rn(fc, ucol[r]), __dmul_rn(su, v));
-                    if (refl_v) v = __dadd_rn(__dmul_rn(c2, sum_wpart(p, tw, r)), __dmul_rn(sv, v));
+                    if (refl_v) v = __dadd_rn(__dmul_rn(c2, __ldcg(p.wfull + r)), __dmul_rn(sv, v));
                     col[r] = v;
                 }
                 __syncthreads();
@@ -504,12 +584,12 @@ static int launch(const void* kernel, cudaStream_t s, size_t m, size_t n, double
     const size_t nrb = ceil_div(m, (size_t)RB);
     Scratch ws;
     const size_t ng = (size_t)G + nrb;                            // tasks: at most one per CTA plus one per row block
-    const size_t words = (size_t)NCB_MAX * m + nrb * n + ng + 2 * n + 8;
+    const size_t words = (size_t)NCB_MAX * m + m + nrb * n + ng + 2 * n + 8 + nrb;
     NAB_TRY(ws.alloc(words * sizeof(double), s));
     NAB_CUDA(cudaMemsetAsync(ws.p, 0, words * sizeof(double), s));
     double* w = ws.as<double>();
-    double* zp = w + (size_t)NCB_MAX * m; double* gp = zp + nrb * n; double* fv = gp + ng;
-    Params p{a, (long long)lda, (int)m, (int)n, d, e, w, zp, gp, fv, fv + n, fv + 2 * n};
+    double* wf = w + (size_t)NCB_MAX * m; double* zp = wf + m; double* gp = zp + nrb * n; double* fv = gp + ng;
+    Params p{a, (long long)lda, (int)m, (int)n, d, e, w, wf, reinterpret_cast<unsigned*>(fv + 2 * n + 8), zp, gp, fv, fv + n, fv + 2 * n};
     void* args[] = {(void*)&p};
     NAB_CUDA(cudaLaunchCooperativeKernel(kernel, dim3((unsigned)G), dim3(T), args, 0, s));
     count_launch();
@@ -617,5 +697,16 @@ int na_bidiagonal_f64(size_t m, size_t n, double* a, size_t lda, double* diagona
     if (!diagonal || (mn > 1 && !off_diagonal)) { set_error("bidiagonal: null argument"); return NA_EINVAL; }
     return two_sided_host(2, m, n, a, lda, diagonal, off_diagonal);
 }
+
+#ifdef NAB_TS_PROF
+// debug build only: out[16] = nanoseconds per phase (CTA 0: slots 0..7, leader: 8..15) since the last call; resets them
+NAB_API int na_debug_ts_prof(unsigned long long* out) {
+    NAB_CUDA(cudaDeviceSynchronize());
+    NAB_CUDA(cudaMemcpyFromSymbol(out, ts::g_ts_prof, 16 * sizeof(unsigned long long)));
+    unsigned long long zero[16] = {0};
+    NAB_CUDA(cudaMemcpyToSymbol(ts::g_ts_prof, zero, sizeof(zero)));
+    return NA_OK;
+}
+#endif
 
 }  // extern "C"
