@@ -182,6 +182,15 @@ def oracle_factor_baselines(which):
             elif name == "lu":
                 a = O.uniform(n, n, 6); fl = 2.0 * n ** 3 / 3.0
                 t0 = time.perf_counter(); O.lu(a); dt = time.perf_counter() - t0
+            elif name == "hessenberg":
+                a = O.uniform(n, n, 6); fl = 10.0 * n ** 3 / 3.0
+                t0 = time.perf_counter(); O.hessenberg(a); dt = time.perf_counter() - t0
+            elif name == "symmetric_tridiagonal":
+                a = O.spd_wellcond(n, 5); fl = 4.0 * n ** 3 / 3.0
+                t0 = time.perf_counter(); O.symmetric_tridiagonal(a); dt = time.perf_counter() - t0
+            elif name == "bidiagonal":
+                a = O.uniform(n, n, 6); fl = 8.0 * n ** 3 / 3.0
+                t0 = time.perf_counter(); O.bidiagonal(a); dt = time.perf_counter() - t0
             else:
                 a = O.uniform(n, n, 8); fl = 4.0 * n ** 3 / 3.0
                 t0 = time.perf_counter(); O.qr(a); dt = time.perf_counter() - t0
@@ -483,7 +492,8 @@ def factorization_extras(L, _capi, torch, dev, stream, N, cpu=True, e2e=True):
     C ABI with pinned buffers, and next to the oracle's CPU time (n^3-extrapolated)."""
     import ctypes as C
     out = {}
-    base = oracle_factor_baselines({"cholesky": [1024, 2048, 4096], "lu": [1024, 2048, 4096], "qr": [1024, 2048]}) if cpu else {}
+    base = oracle_factor_baselines({"cholesky": [1024, 2048, 4096], "lu": [1024, 2048, 4096], "qr": [1024, 2048],
+                                    "hessenberg": [512, 1024], "symmetric_tridiagonal": [512, 1024], "bidiagonal": [512, 1024]}) if cpu else {}
 
     def dev_time(fn, reps):
         best = None
@@ -661,6 +671,37 @@ def factorization_extras(L, _capi, torch, dev, stream, N, cpu=True, e2e=True):
                                  "algorithmic_bytes_per_launch": alg_bytes,
                                  "note": "16 n^3 / 3 bytes: one read + one write of the trailing matrix per elimination step; "
                                          "two grid barriers per step bound the small-n end"}}
+    del A, A0
+
+    # ---- Hessenberg / SymmetricTridiagonal / Bidiagonal -- one fused product pass + one update pass over the
+    # trailing block per step (Bidiagonal: two product passes); n = 8192 so that the matrix (537 MB) does not sit in the L2
+    n8 = 8192
+    A0 = torch.empty(n8 * n8, dtype=torch.float64, device=dev); A = torch.empty_like(A0)
+    dg = torch.empty(n8, dtype=torch.float64, device=dev); eg = torch.empty(n8, dtype=torch.float64, device=dev)
+    _capi.check(L.na_fill_uniform_dev(A0.data_ptr(), n8, n8, n8, 6, stream))
+    def hess():
+        A.copy_(A0)
+        _capi.check(L.na_hessenberg_f64_dev(n8, A.data_ptr(), n8, dg.data_ptr(), stream))
+    def symtri():
+        A.copy_(A0)
+        _capi.check(L.na_symmetric_tridiagonal_f64_dev(n8, A.data_ptr(), n8, dg.data_ptr(), stream))
+    def bidiag():
+        A.copy_(A0)
+        _capi.check(L.na_bidiagonal_f64_dev(n8, n8, A.data_ptr(), n8, dg.data_ptr(), eg.data_ptr(), stream))
+    for key, fn, what, alg_bytes, flops, note in (
+            ("hessenberg_n8192", hess, "two_sided_kernel<false>", 12.0 * n8 ** 3, 10.0 * n8 ** 3 / 3.0,
+             "12 n^3 bytes: per step one read (w = A u and z = A^T u from the same tile) + one read-modify-write of the n x (n - k) block"),
+            ("symmetric_tridiagonal_n8192", symtri, "two_sided_kernel<true>", 4.0 * n8 ** 3, 4.0 * n8 ** 3 / 3.0,
+             "4 n^3 bytes: per step one read + one read-modify-write of the lower triangle of the (n - k)^2 block"),
+            ("bidiagonal_n8192", bidiag, "bidiagonal_kernel", 32.0 * n8 ** 3 / 3.0, 8.0 * n8 ** 3 / 3.0,
+             "32 n^3 / 3 bytes: per step two reads (column products, row products of the column-reflected block) + one read-modify-write")):
+        ms, _ = dev_time(fn, 2)
+        gbs = alg_bytes / ms / 1e6
+        out[key] = {"ms": ms, "us_per_step": ms * 1e3 / n8, "gflops": flops / ms / 1e6,
+                    "roofline": {"bound": "hbm", "achieved": gbs, "peak": hbm_peak, "unit": "GB/s", "frac": gbs / hbm_peak, "traffic": None,
+                                 "kernel": what, "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_bytes, "note": note}}
+        if key.rsplit("_", 1)[0] in base:
+            out[key]["cpu_baseline"] = base[key.rsplit("_", 1)[0]]
     return out
 
 

@@ -4,6 +4,7 @@ The product is ``libnalgebra_b200.so`` (C ABI: ``include/nalgebra_b200.h``); thi
 host-side mirror of nalgebra's interface over that ABI (see ``linalg.py``).  No CPU fallback.
 """
 from . import _capi  # noqa: F401
+from . import wire  # noqa: F401
 from .linalg import (  # noqa: F401
     LU, QR, Bidiagonal, Cholesky, ColPivQR, FullPivLU, Hessenberg, PermutationSequence, SymmetricTridiagonal, ad_mul, ad_mul_to, gemm, gemm_ad, gemm_f32, gemm_tr, gemv, gemv_ad, gemv_tr,
     kernel_launches, mul, mul_to, solve_lower_triangular, solve_lower_triangular_with_diag, solve_upper_triangular,

@@ -43,6 +43,9 @@ extern "C" {
     pub fn na_full_piv_lu_f64(m: usize, n: usize, a: *mut f64, lda: usize, p_swaps: *mut usize, np: *mut usize,
                               q_swaps: *mut usize, nq: *mut usize) -> c_int;
     pub fn na_col_piv_qr_f64(m: usize, n: usize, a: *mut f64, lda: usize, diag: *mut f64, p_swaps: *mut usize, np: *mut usize) -> c_int;
+    pub fn na_hessenberg_f64(n: usize, a: *mut f64, lda: usize, subdiag: *mut f64) -> c_int;
+    pub fn na_symmetric_tridiagonal_f64(n: usize, a: *mut f64, lda: usize, off_diagonal: *mut f64) -> c_int;
+    pub fn na_bidiagonal_f64(m: usize, n: usize, a: *mut f64, lda: usize, diagonal: *mut f64, off_diagonal: *mut f64) -> c_int;
     pub fn na_tri_solve_f64(lower: c_int, trans: c_int, unit_diag: c_int, n: usize, t: *const f64, ldt: usize,
                             b: *mut f64, ldb: usize, nrhs: usize) -> c_int;
 

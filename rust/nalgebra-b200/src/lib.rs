@@ -246,3 +246,117 @@ impl ColPivQR {
     pub fn is_invertible(&self) -> bool { self.diag.iter().all(|d| *d != 0.0) }
     pub fn determinant(&self) -> f64 { self.diag.iter().product::<f64>() * self.p.determinant::<f64>() }
 }
+
+/// `householder::assemble_q` (householder.rs:132-152): axes in column i, rows i + 1.. of `m`.  The reflector product is
+/// 1 (+) the `QR::q` of the storage one row down, so the device routine of the QR path forms it.
+fn assemble_q(m: &DMatrix<f64>, signs: &DVector<f64>) -> DMatrix<f64> {
+    let n = m.nrows();
+    let mut q = DMatrix::zeros(n, n);
+    q[(0, 0)] = 1.0;
+    if n > 1 {
+        check(unsafe { sys::na_qr_q_f64(n - 1, n - 1, m.as_ptr().add(1), n, signs.as_ptr(), q.as_mut_ptr().add(1 + n), n) });
+    }
+    q
+}
+
+/// `Hessenberg{hess, subdiag}` (hessenberg.rs:61-100): matrix = Q H Q^T.
+pub struct Hessenberg { hess: DMatrix<f64>, subdiag: DVector<f64> }
+
+impl Hessenberg {
+    pub fn new(mut hess: DMatrix<f64>) -> Self {
+        assert!(hess.is_square(), "Cannot compute the hessenberg decomposition of a non-square matrix.");
+        let n = hess.nrows();
+        assert!(n != 0, "Cannot compute the hessenberg decomposition of an empty matrix.");
+        let mut subdiag = DVector::zeros(n - 1);
+        check(unsafe { sys::na_hessenberg_f64(n, hess.as_mut_ptr(), n, subdiag.as_mut_ptr()) });
+        Self { hess, subdiag }
+    }
+    pub fn hess_internal(&self) -> &DMatrix<f64> { &self.hess }
+    /// `h()` (hessenberg.rs:128-140).
+    pub fn h(&self) -> DMatrix<f64> {
+        let n = self.hess.nrows();
+        let mut res = self.hess.clone();
+        res.fill_lower_triangle(0.0, 2);
+        for i in 0..n - 1 { res[(i + 1, i)] = self.subdiag[i].abs(); }
+        res
+    }
+    pub fn q(&self) -> DMatrix<f64> { assemble_q(&self.hess, &self.subdiag) }
+    pub fn unpack(self) -> (DMatrix<f64>, DMatrix<f64>) { (self.q(), self.h()) }
+}
+
+/// `SymmetricTridiagonal{tri, off_diagonal}` (symmetric_tridiagonal.rs:54-95); only the lower triangle is read.
+pub struct SymmetricTridiagonal { tri: DMatrix<f64>, off_diagonal: DVector<f64> }
+
+impl SymmetricTridiagonal {
+    pub fn new(mut m: DMatrix<f64>) -> Self {
+        assert!(m.is_square(), "Unable to compute the symmetric tridiagonal decomposition of a non-square matrix.");
+        let n = m.nrows();
+        assert!(n != 0, "Unable to compute the symmetric tridiagonal decomposition of an empty matrix.");
+        let mut off_diagonal = DVector::zeros(n - 1);
+        check(unsafe { sys::na_symmetric_tridiagonal_f64(n, m.as_mut_ptr(), n, off_diagonal.as_mut_ptr()) });
+        Self { tri: m, off_diagonal }
+    }
+    pub fn internal_tri(&self) -> &DMatrix<f64> { &self.tri }
+    pub fn diagonal(&self) -> DVector<f64> { self.tri.diagonal() }
+    pub fn off_diagonal(&self) -> DVector<f64> { self.off_diagonal.map(|e| e.abs()) }
+    pub fn q(&self) -> DMatrix<f64> { assemble_q(&self.tri, &self.off_diagonal) }
+    pub fn unpack(self) -> (DMatrix<f64>, DVector<f64>, DVector<f64>) { (self.q(), self.diagonal(), self.off_diagonal()) }
+    pub fn unpack_tridiagonal(self) -> (DVector<f64>, DVector<f64>) { (self.diagonal(), self.off_diagonal()) }
+}
+
+/// `Bidiagonal{uv, diagonal, off_diagonal, upper_diagonal}` (bidiagonal.rs:74-150): matrix = U D V^T.
+pub struct Bidiagonal { uv: DMatrix<f64>, diagonal: DVector<f64>, off_diagonal: DVector<f64>, upper_diagonal: bool }
+
+impl Bidiagonal {
+    pub fn new(mut matrix: DMatrix<f64>) -> Self {
+        let (nr, nc) = matrix.shape();
+        let mn = nr.min(nc);
+        assert!(mn != 0, "Cannot compute the bidiagonalization of an empty matrix.");
+        let mut diagonal = DVector::zeros(mn);
+        let mut off_diagonal = DVector::zeros(mn - 1);
+        let mut dummy = 0.0f64;
+        let off_ptr = if mn > 1 { off_diagonal.as_mut_ptr() } else { &mut dummy as *mut f64 };
+        check(unsafe { sys::na_bidiagonal_f64(nr, nc, matrix.as_mut_ptr(), nr, diagonal.as_mut_ptr(), off_ptr) });
+        Self { uv: matrix, diagonal, off_diagonal, upper_diagonal: nr >= nc }
+    }
+    pub fn is_upper_diagonal(&self) -> bool { self.upper_diagonal }
+    pub fn uv_internal(&self) -> &DMatrix<f64> { &self.uv }
+    pub fn diagonal(&self) -> DVector<f64> { self.diagonal.map(|e| e.abs()) }
+    pub fn off_diagonal(&self) -> DVector<f64> { self.off_diagonal.map(|e| e.abs()) }
+    /// `d()` (bidiagonal.rs:185-200).
+    pub fn d(&self) -> DMatrix<f64> {
+        let mn = self.diagonal.len();
+        let mut res = DMatrix::zeros(mn, mn);
+        for i in 0..mn { res[(i, i)] = self.diagonal[i].abs(); }
+        for i in 0..mn.saturating_sub(1) {
+            if self.upper_diagonal { res[(i, i + 1)] = self.off_diagonal[i].abs(); } else { res[(i + 1, i)] = self.off_diagonal[i].abs(); }
+        }
+        res
+    }
+    /// reflector product of the axes in column i, rows i + shift.. of `st` (rows x min(rows, cols))
+    fn q_of(st: &DMatrix<f64>, signs: &DVector<f64>, shift: usize) -> DMatrix<f64> {
+        let (rows, cols) = st.shape();
+        let k = rows.min(cols);
+        let mut q = DMatrix::zeros(rows, k);
+        if shift == 0 {
+            check(unsafe { sys::na_qr_q_f64(rows, cols, st.as_ptr(), rows, signs.as_ptr(), q.as_mut_ptr(), rows) });
+        } else {
+            q[(0, 0)] = 1.0;
+            if rows > 1 && k > 1 {
+                check(unsafe { sys::na_qr_q_f64(rows - 1, k - 1, st.as_ptr().add(1), rows, signs.as_ptr(), q.as_mut_ptr().add(1 + rows), rows) });
+            }
+        }
+        q
+    }
+    /// `u()` (bidiagonal.rs:205-240).
+    pub fn u(&self) -> DMatrix<f64> {
+        if self.upper_diagonal { Self::q_of(&self.uv, &self.diagonal, 0) } else { Self::q_of(&self.uv, &self.off_diagonal, 1) }
+    }
+    /// `v_t()` (bidiagonal.rs:244-283): the row axes are the column axes of the transposed storage.
+    pub fn v_t(&self) -> DMatrix<f64> {
+        let st = self.uv.transpose();
+        let v = if self.upper_diagonal { Self::q_of(&st, &self.off_diagonal, 1) } else { Self::q_of(&st, &self.diagonal, 0) };
+        v.transpose()
+    }
+    pub fn unpack(self) -> (DMatrix<f64>, DMatrix<f64>, DMatrix<f64>) { (self.u(), self.d(), self.v_t()) }
+}
