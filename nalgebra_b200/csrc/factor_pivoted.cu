@@ -26,7 +26,11 @@ namespace cg = cooperative_groups;
 namespace nab {
 
 namespace pv {
-constexpr int T = 256;
+#ifndef NAB_PV_T
+#define NAB_PV_T 512
+#endif
+constexpr int RU = 12;             // rows per lane in flight in the column sweeps
+constexpr int T = NAB_PV_T;      // warps own columns: the loads a CTA keeps in flight scale with its warp count
 
 struct Cand { double key; long long pos; double val; };   // key: |value| (-1: can never win); pos = row + col * m (column-major order); val: the entry itself
 
@@ -155,19 +159,21 @@ __global__ void __launch_bounds__(pv::T, 1) full_piv_lu_kernel(const PivotedPara
             for (long long r = i + 1 + gtid; r < m; r += nthreads)
                 if (r != pr) a[r + (i - 1) * lda] = __dmul_rn(a[r + (i - 1) * lda], inv_prev);
         grid.sync();
-        // ---- phase U: eight rows per lane in flight
+        // ---- phase U: RU rows per lane in flight
         const double inv_diag = 1.0 / diag;                         // lu.rs:345
         const double* ci = a + i * lda;                             // column i: unscaled until the next phase S
         double bk = -2.0, bv = 0.0; long long bp = 0x7fffffffffffffffll;
         for (int j = i + 1 + gwarp; j < n; j += nwarps) {
             double* cj = a + j * lda;
             const double npiv = -cj[i];                             // -pivot_row[k]   (lu.rs:353-356)
-            for (int r0 = i + 1 + lane; r0 < m; r0 += 256) {
-                double x[8], y[8];
+            for (int r0 = i + 1 + lane; r0 < m; r0 += 32 * RU) {
+                double x[RU], y[RU];
 #pragma unroll
-                for (int u = 0; u < 8; ++u) { const int r = r0 + 32 * u; x[u] = r < m ? ci[r] : 0.0; y[u] = r < m ? cj[r] : 0.0; }
+                for (int u = 0; u < RU; ++u) { const int r = r0 + 32 * u; y[u] = r < m ? cj[r] : 0.0; }
 #pragma unroll
-                for (int u = 0; u < 8; ++u) {
+                for (int u = 0; u < RU; ++u) { const int r = r0 + 32 * u; x[u] = r < m ? ci[r] : 0.0; }      // the pivot column: L1 hits after the first warp
+#pragma unroll
+                for (int u = 0; u < RU; ++u) {
                     const int r = r0 + 32 * u;
                     if (r < m) {
                         const double coeff = __dmul_rn(x[u], inv_diag);                  // coeffs *= inv_diag (the value the reference stores)
@@ -245,12 +251,12 @@ __global__ void __launch_bounds__(pv::T, 1) col_piv_qr_kernel(const PivotedParam
         // ---- phase H
         if (cta == 0) {
             // column pc, rows i.. -> unit axis (householder.rs:19-53) stored in column i; old column i -> column pc.
-            // Up to 16 entries per thread live in registers (one round of loads for the three passes); longer columns
+            // Up to 4096 / T entries per thread live in registers (one round of loads for the three passes); longer columns
             // are re-read.
             double* ci = a + i + i * lda;
             double* cp = a + i + pc * lda;
             const int len = m - i;
-            constexpr int R = 16;
+            constexpr int R = 4096 / T;                             // columns of up to 4096 entries stay in registers
             const bool in_regs = len <= R * T;
             double xr[R], oi[R];
 #pragma unroll
@@ -333,18 +339,25 @@ __global__ void __launch_bounds__(pv::T, 1) col_piv_qr_kernel(const PivotedParam
             double factor = 0.0;
             if (reflected) {
                 double d = 0.0;
-#pragma unroll 8
-                for (int r = lane; r < len; r += 32) d = fma(axis[r], cj[r], d);
+                for (int r0 = lane; r0 < len; r0 += 32 * RU) {
+                    double y[RU];
+#pragma unroll
+                    for (int u = 0; u < RU; ++u) { const int r = r0 + 32 * u; y[u] = r < len ? cj[r] : 0.0; }
+#pragma unroll
+                    for (int u = 0; u < RU; ++u) { const int r = r0 + 32 * u; if (r < len) d = fma(axis[r], y[u], d); }
+                }
 #pragma unroll
                 for (int o = 16; o > 0; o >>= 1) d += __shfl_xor_sync(0xffffffffu, d, o);
                 factor = d * (sign * -2.0);                          // reflection.rs:76-79, bias = 0
             }
-            for (int r0 = lane; r0 < len; r0 += 256) {
-                double x[8], y[8];
+            for (int r0 = lane; r0 < len; r0 += 32 * RU) {
+                double x[RU], y[RU];
 #pragma unroll
-                for (int u = 0; u < 8; ++u) { const int r = r0 + 32 * u; x[u] = r < len ? axis[r] : 0.0; y[u] = r < len ? cj[r] : 0.0; }
+                for (int u = 0; u < RU; ++u) { const int r = r0 + 32 * u; y[u] = r < len ? cj[r] : 0.0; }
 #pragma unroll
-                for (int u = 0; u < 8; ++u) {
+                for (int u = 0; u < RU; ++u) { const int r = r0 + 32 * u; x[u] = r < len ? axis[r] : 0.0; }
+#pragma unroll
+                for (int u = 0; u < RU; ++u) {
                     const int r = r0 + 32 * u;
                     if (r < len) {
                         double v = y[u];
