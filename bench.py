@@ -703,6 +703,15 @@ def factorization_extras(L, _capi, torch, dev, stream, N, cpu=True, e2e=True):
                                  "kernel": what, "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_bytes, "note": note}}
         if key.rsplit("_", 1)[0] in base:
             out[key]["cpu_baseline"] = base[key.rsplit("_", 1)[0]]
+    try:   # DRAM bytes of the Hessenberg launch from the committed ncu capture, valid for the kernel source it was taken with
+        import hashlib
+        with open(os.path.join(ROOT, "profiles", "twosided_traffic.json")) as f:
+            tj = json.load(f)
+        with open(os.path.join(ROOT, "nalgebra_b200", "csrc", "factor_twosided.cu"), "rb") as f:
+            if hashlib.sha256(f.read()).hexdigest() == tj.get("kernel_source_sha256"):
+                out["hessenberg_n8192"]["roofline"]["traffic"] = tj["traffic_bytes_per_launch"]
+    except Exception:
+        pass
     return out
 
 

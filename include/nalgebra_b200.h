@@ -137,7 +137,10 @@ NAB_API int na_daxcpy_dev(size_t n, double a, const double* x, ptrdiff_t incx, d
 /* Cholesky::new / new_with_substitute (src/linalg/cholesky.rs:196-272).  On NA_OK the lower
  * triangle (incl. diagonal) of `a` holds L; the strict upper triangle is never read or written
  * (tests/linalg/cholesky.rs:3-12).  NA_NOT_PD == `None`; *fail_col (may be NULL) receives the
- * first column whose pivot was <= 0 or NaN.  use_sub/sub = new_with_substitute's `substitute`. */
+ * first column whose pivot was <= 0 or NaN.  use_sub/sub = new_with_substitute's `substitute`.
+ * One deliberate deviation from the reference's arithmetic: a column is scaled by the reciprocal of
+ * sqrt(pivot) where cholesky.rs:261-262 divides (<= 1 ulp per entry; eight serial FP64 divisions per
+ * thread and column would lengthen the latency-bound 128-column leaf by a quarter). */
 NAB_API int na_cholesky_f64(size_t n, double* a, size_t lda, int use_sub, double sub, size_t* fail_col);
 /* Synchronises `stream` before returning (the status is a value). */
 NAB_API int na_cholesky_f64_dev(size_t n, double* a, size_t lda, int use_sub, double sub, size_t* fail_col, void* stream);
