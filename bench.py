@@ -215,6 +215,10 @@ def run_gpu(args):
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        # NCCL here carries only the panel broadcasts of the block-cyclic factorizations (the GEMM exchange goes through the
+        # copy engines): 8 channels = 8 resident CTAs, for which nalgebra_b200.distributed keeps 8 SMs free of the persistent
+        # GEMM CTAs (8-GPU Cholesky N = 65536: 542 -> 492 ms, profiles/r02_bc_chol_8gpu.txt)
+        os.environ.setdefault("NCCL_MAX_NCHANNELS", "8")
         dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local_rank}"))
     if world != args.gpus and rank == 0 and world > 1:
         print(f"warning: --gpus {args.gpus} but WORLD_SIZE={world}", file=sys.stderr)

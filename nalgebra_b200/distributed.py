@@ -25,6 +25,8 @@ from __future__ import annotations
 
 import ctypes as C
 
+import os
+
 import torch
 import torch.distributed as dist
 
@@ -404,6 +406,22 @@ class _PanelPipe:
             torch.cuda.current_stream(self.A.data.device).wait_stream(self.side)
 
 
+def _nccl_sm_reserve(A: "ColumnBlockCyclic") -> int:
+    """SMs kept free of the persistent GEMM CTAs while a block-cyclic factorization runs on several GPUs.  The trailing
+    updates are back-to-back 148-CTA launches with a static tile schedule; NCCL's broadcast of the NEXT panel (one CTA per
+    channel, resident for the whole transfer) otherwise takes SMs from them and every GEMM launched meanwhile waits for its
+    displaced CTAs.  Measured on 8 B200s, Cholesky N = 65536 (`profiles/r02_bc_chol_8gpu.txt`): NCCL default channels / no
+    reservation 542 ms; 2 channels / 2 SMs 601; 4 / 4 519; 8 / 8 492; 12 / 12 489; 16 / 16 510.  So: as many SMs as NCCL has
+    channels when the caller capped them (NCCL_MAX_NCHANNELS -- bench.py sets 8), nothing otherwise (with NCCL's default
+    channel count the reservation costs more than the stalls).  NAB_BC_RESERVE overrides."""
+    if A.world == 1 or not A.data.is_cuda:
+        return 0
+    if "NAB_BC_RESERVE" in os.environ:
+        return int(os.environ["NAB_BC_RESERVE"])
+    ch = int(os.environ.get("NCCL_MAX_NCHANNELS", "0") or 0)
+    return ch if 0 < ch <= 16 else 0
+
+
 def cholesky_block_cyclic(A: ColumnBlockCyclic, group=None, lookahead: bool = True) -> int:
     """In-place lower Cholesky of the distributed SPD matrix.  Returns 0 (NA_OK) or 1 (NA_NOT_PD) on every rank;
     ``A.fail_col`` then holds the first failing global column (the reference returns None there,
@@ -417,6 +435,9 @@ def cholesky_block_cyclic(A: ColumnBlockCyclic, group=None, lookahead: bool = Tr
     n, nb, rank, world, ops = A.n, A.nb, A.rank, A.world, A.ops
     pipe = _PanelPipe(A, group, lookahead)
     fail = ops.status_word()
+    reserve = _nccl_sm_reserve(A)
+    if reserve:
+        ops.reserve_sms(reserve)
 
     def factor_and_pack(k: int, bi: int) -> None:
         r0, w = k * nb, A.width(k)
@@ -451,6 +472,8 @@ def cholesky_block_cyclic(A: ColumnBlockCyclic, group=None, lookahead: bool = Tr
         for b in mine:
             update_block(b, k, buf)
         pipe.join()
+    if reserve:
+        ops.reserve_sms(0)
     # the word is an unsigned "first failing column" (all ones = none): combine across ranks on the host, once
     local = int(fail.cpu().item()) & U64_MAX
     if world > 1:
@@ -476,6 +499,9 @@ def lu_block_cyclic(A: ColumnBlockCyclic, group=None, lookahead: bool = True):
     n, nb, rank, world, ops = A.n, A.nb, A.rank, A.world, A.ops
     pipe = _PanelPipe(A, group, lookahead)
     ipiv = ops.ipiv(n)                                   # panel-relative 0-based pivot rows of all columns
+    reserve = _nccl_sm_reserve(A)
+    if reserve:
+        ops.reserve_sms(reserve)
 
     def piv_slice(k: int) -> torch.Tensor:
         r0 = k * nb
@@ -524,6 +550,8 @@ def lu_block_cyclic(A: ColumnBlockCyclic, group=None, lookahead: bool = True):
     if A.data.is_cuda:
         torch.cuda.synchronize(A.data.device)
     A.ipiv = ipiv
+    if reserve:
+        ops.reserve_sms(0)
     return pivot_pairs(ipiv.cpu().tolist(), n, nb)
 
 
