@@ -378,7 +378,9 @@ def run_gpu(args):
             from nalgebra_b200.distributed import (ColumnBlockCyclic, cholesky_block_cyclic, cholesky_residual_block_cyclic,
                                                    lu_block_cyclic, lu_residual_block_cyclic)
             n_bc = {2: 32768, 4: 49152, 8: 65536}.get(ngpus, 16384)
-            nb_bc = 1024
+            # block width: 1024 on 2 GPUs; on more ranks 512 (shorter owner chain per step, finer balance): 8 GPUs N = 65536
+            # 492 ms at 512, 519 at 768, 537 at 1024 (profiles/r02_bc_chol_8gpu.txt)
+            nb_bc = 1024 if ngpus <= 2 else 512
 
             def timed(fn):
                 barrier()
