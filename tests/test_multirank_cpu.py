@@ -259,3 +259,24 @@ def test_gemm2d_product_logic(tmp_path, oracle):
         mp.spawn(_gemm2d_worker, args=(world, port, n, str(tmp_path)), nprocs=world, join=True)
         full = np.load(tmp_path / f"g2d_{world}.npy")
         assert np.abs(full - ref).max() <= 4 * n * np.finfo(np.float64).eps * np.linalg.norm(a) * np.linalg.norm(b)
+
+
+def test_nccl_sm_reservation_rule(monkeypatch):
+    """distributed._nccl_sm_reserve: as many SMs as NCCL has channels when the caller capped them, nothing otherwise."""
+    import torch
+    from nalgebra_b200 import distributed as D
+
+    class Fake:
+        def __init__(self, world, cuda):
+            self.world = world
+            self.data = type("T", (), {"is_cuda": cuda})()
+    for k in ("NAB_BC_RESERVE", "NCCL_MAX_NCHANNELS"):
+        monkeypatch.delenv(k, raising=False)
+    assert D._nccl_sm_reserve(Fake(8, True)) == 0                  # NCCL's default channel count: no reservation
+    monkeypatch.setenv("NCCL_MAX_NCHANNELS", "8")
+    assert D._nccl_sm_reserve(Fake(8, True)) == 8
+    assert D._nccl_sm_reserve(Fake(1, True)) == 0 and D._nccl_sm_reserve(Fake(8, False)) == 0
+    monkeypatch.setenv("NCCL_MAX_NCHANNELS", "32")
+    assert D._nccl_sm_reserve(Fake(8, True)) == 0                  # too many to give away
+    monkeypatch.setenv("NAB_BC_RESERVE", "12")
+    assert D._nccl_sm_reserve(Fake(8, True)) == 12

@@ -216,3 +216,39 @@ def test_two_sided_is_deterministic(nab, oracle):
     assert np.array_equal(h1.hess_internal(), h2.hess_internal()) and np.array_equal(h1.subdiag, h2.subdiag)
     b1, b2 = nab.Bidiagonal.new(a), nab.Bidiagonal.new(a)
     assert np.array_equal(b1.uv_internal(), b2.uv_internal())
+
+
+@pytest.mark.gpu
+def test_two_sided_4096_properties(nab, oracle):
+    """Beyond the oracle's reach in test time: reconstruction and orthogonality at n = 4096 with the products on the GPU
+    (north-star gates 10 n eps), plus the trace / Frobenius invariants of a similarity / orthogonal equivalence."""
+    n = 4096
+    a = oracle.uniform(n, n, 31) - 0.5
+    h = nab.Hessenberg.new(a)
+    q, hm = h.unpack()
+    rec = nab.mul(nab.mul(q, hm), np.asfortranarray(q.T))
+    assert np.linalg.norm(rec - a) <= 10 * n * EPS * np.linalg.norm(a)
+    assert np.linalg.norm(nab.tr_mul(q, q) - np.eye(n)) <= 10 * n * EPS
+    assert abs(np.trace(hm) - np.trace(a)) <= 10 * n * EPS * np.linalg.norm(a)
+    s = np.asfortranarray((a + a.T) / 2.0)
+    t = nab.SymmetricTridiagonal.new(s)
+    rec = t.recompose()
+    assert np.linalg.norm(np.tril(rec) - np.tril(s)) <= 10 * n * EPS * np.linalg.norm(s)
+    b = nab.Bidiagonal.new(a)
+    u, d, vt = b.unpack()
+    rec = nab.mul(nab.mul(u, d), vt)
+    assert np.linalg.norm(rec - a) <= 10 * n * EPS * np.linalg.norm(a)
+    assert abs(np.linalg.norm(d) - np.linalg.norm(a)) <= 10 * n * EPS * np.linalg.norm(a)
+
+
+@pytest.mark.gpu
+def test_wire_round_trip_of_gpu_factors(nab, oracle):
+    """A factor object computed on the GPU survives nalgebra's serde wire format bit for bit and still solves."""
+    a = oracle.uniform(300, 300, 32) - 0.5; b = oracle.uniform(300, 2, 33)
+    lu = nab.LU.new(a)
+    back = nab.wire.loads(nab.wire.dumps(lu), "LU")
+    assert np.array_equal(back.lu, lu.lu) and np.array_equal(back.p().ipiv, lu.p().ipiv)
+    assert np.array_equal(back.solve(b), lu.solve(b))
+    hs = nab.Hessenberg.new(a)
+    back = nab.wire.loads(nab.wire.dumps(hs), "Hessenberg")
+    assert np.array_equal(back.q(), hs.q()) and np.array_equal(back.h(), hs.h())
