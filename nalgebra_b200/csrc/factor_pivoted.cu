@@ -224,6 +224,9 @@ __global__ void __launch_bounds__(pv::T, 1) col_piv_qr_kernel(const PivotedParam
     __shared__ long long s_pos;
     __shared__ double s_val;
     __shared__ double sred[T / 32];
+    __shared__ double s_dot[2][T / 32];
+    constexpr int CR = 8192 / T;                                    // entries of a column a thread keeps (CTA-per-column sweep)
+    constexpr int kColCtaMin = 2048;                                // shorter columns: warp per column (thresholds 512 .. 2048 measure the same)
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int G = gridDim.x, cta = blockIdx.x;
     const int m = p.m, n = p.n, mn = min(m, n);
@@ -334,6 +337,56 @@ __global__ void __launch_bounds__(pv::T, 1) col_piv_qr_kernel(const PivotedParam
         const double* axis = a + i + i * lda;
         const int len = m - i;
         double bk = -2.0, bv = 0.0; long long bp = 0x7fffffffffffffffll;
+        if (reflected && len > kColCtaMin && len <= CR * T) {
+            // Long columns: a warp would read its column twice (dot product, then reflection) and the second read misses
+            // the L1.  Here a CTA owns a column, every thread keeps CR entries of it in registers between the dot product
+            // (one CTA-wide sum: warp shuffles + one barrier, double-buffered slots) and the reflection, and the next
+            // column's loads are issued before the current one is reduced: one read + one write per element.
+            double y[2][CR];
+            int j = i + 1 + cta;
+            if (j < n) {
+#pragma unroll
+                for (int u = 0; u < CR; ++u) { const int r = tid + u * T; y[0][u] = r < len ? a[i + r + (long long)j * lda] : 0.0; }
+            }
+            int par = 0;
+            auto step = [&](double (&yc)[CR], double (&yn)[CR], int jc) {
+                const int jn = jc + G;
+                if (jn < n) {
+#pragma unroll
+                    for (int u = 0; u < CR; ++u) { const int r = tid + u * T; yn[u] = r < len ? a[i + r + (long long)jn * lda] : 0.0; }
+                }
+                double d = 0.0;
+#pragma unroll
+                for (int u = 0; u < CR; ++u) { const int r = tid + u * T; if (r < len) d = fma(axis[r], yc[u], d); }
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) d += __shfl_xor_sync(0xffffffffu, d, o);
+                if (lane == 0) s_dot[par][warp] = d;
+                __syncthreads();
+                double tot = 0.0;
+#pragma unroll
+                for (int w = 0; w < T / 32; ++w) tot += s_dot[par][w];
+                par ^= 1;
+                const double factor = tot * (sign * -2.0);           // reflection.rs:76-79, bias = 0
+                double* cj = a + i + (long long)jc * lda;
+#pragma unroll
+                for (int u = 0; u < CR; ++u) {
+                    const int r = tid + u * T;
+                    if (r < len) {
+                        const double v = __dadd_rn(__dmul_rn(factor, axis[r]), __dmul_rn(sign, yc[u]));   // axpy(factor, axis, sign)
+                        cj[r] = v;
+                        if (r >= 1) {
+                            const double k = cand_key(v, r == 1 && jc == i + 1);
+                            const long long pos2 = (i + r) + (long long)jc * m;
+                            if (cand_better(k, pos2, bk, bp)) { bk = k; bp = pos2; bv = v; }
+                        }
+                    }
+                }
+            };
+            for (; j < n; j += 2 * G) {
+                step(y[0], y[1], j);
+                if (j + G < n) step(y[1], y[0], j + G);
+            }
+        } else
         for (int j = i + 1 + gwarp; j < n; j += nwarps) {
             double* cj = a + i + j * lda;
             double factor = 0.0;

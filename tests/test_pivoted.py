@@ -121,7 +121,7 @@ def test_col_piv_qr_kat(nab):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("shape", SHAPES + [(257, 300), (700, 512), (1000, 600)])
+@pytest.mark.parametrize("shape", SHAPES + [(257, 300), (700, 512), (1000, 600), (2600, 200), (4200, 70), (8192, 40), (9000, 33)])   # > 2048 rows: CTA-per-column sweep
 def test_col_piv_qr_vs_oracle(nab, oracle, shape):
     m, n = shape
     a = oracle.uniform(m, n, 13) - 0.4
