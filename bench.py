@@ -696,8 +696,10 @@ def factorization_extras(L, _capi, torch, dev, stream, N, cpu=True, e2e=True):
         A.copy_(A0)
         _capi.check(L.na_bidiagonal_f64_dev(n8, n8, A.data_ptr(), n8, dg.data_ptr(), eg.data_ptr(), stream))
     for key, fn, what, alg_bytes, flops, note in (
-            ("hessenberg_n8192", hess, "two_sided_kernel<false>", 12.0 * n8 ** 3, 10.0 * n8 ** 3 / 3.0,
-             "12 n^3 bytes: per step one read (w = A u and z = A^T u from the same tile) + one read-modify-write of the n x (n - k) block"),
+            ("hessenberg_n8192", hess, "two_sided_fused_kernel<false>", 8.0 * n8 ** 3, 10.0 * n8 ** 3 / 3.0,
+             "8 n^3 bytes: per step ONE read + ONE write of the n x (n - k) block (the update of step s - 1 and the products of "
+             "step s, w = A u and z = A^T u, in the same pass; n >= 6144).  Against the 12 n^3 of the two-pass kernel the same "
+             "time reads as 1.5x this bandwidth"),
             ("symmetric_tridiagonal_n8192", symtri, "two_sided_kernel<true>", 4.0 * n8 ** 3, 4.0 * n8 ** 3 / 3.0,
              "4 n^3 bytes: per step one read + one read-modify-write of the lower triangle of the (n - k)^2 block"),
             ("bidiagonal_n8192", bidiag, "bidiagonal_kernel", 32.0 * n8 ** 3 / 3.0, 8.0 * n8 ** 3 / 3.0,

@@ -252,7 +252,8 @@ NAB_API int na_set_gemm_sm_limit(int max_ctas);
 /* Tuning / diagnostic switches, never needed for correctness.  Keys: "lu_lookahead" (0: factor with the plain
  * recursive driver instead of the two-stream look-ahead driver; the tests compare the two paths' pivots);
  * "qr_reg_leaf" (0: shared-memory GEQR2 leaf + two-stream look-ahead driver instead of the register-resident leaf +
- * plain outer loop); "qr_fused" (0: in-panel block reflectors as GEMM sequences instead of the fused kernel). */
+ * plain outer loop); "qr_fused" (0: in-panel block reflectors as GEMM sequences instead of the fused kernel); "ts_fused" (Hessenberg /
+ * SymmetricTridiagonal: 1 = one fused pass per step, 0 = product pass + update pass, -1 = by size, the default). */
 NAB_API int na_set_tuning(const char* key, long value);
 
 /* ---- building blocks of the multi-GPU (1D block-cyclic) factorizations, device pointers ------ */

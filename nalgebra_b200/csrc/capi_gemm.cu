@@ -306,6 +306,7 @@ int na_set_tuning(const char* key, long value) {
     if (strcmp(key, "lu_lookahead") == 0) { lu_set_lookahead(value); return NA_OK; }
     if (strcmp(key, "qr_reg_leaf") == 0) { qr_set_tuning(0, value); return NA_OK; }
     if (strcmp(key, "qr_fused") == 0) { qr_set_tuning(1, value); return NA_OK; }
+    if (strcmp(key, "ts_fused") == 0) { ts_set_fused(value); return NA_OK; }
     set_error("na_set_tuning: unknown key '%s'", key);
     return NA_EINVAL;
 }

@@ -76,7 +76,15 @@ struct Params {
     double* fvec;     // [n] Bidiagonal: column-reflection factors of the step
     double* vvec;     // [n] Bidiagonal: the row axis, contiguous
     double* hh;       // [2][4] (sign, reflected) of the column axis and of the row axis, by step parity
+    long long set2;   // fused kernel: offset (in doubles) of the second copy of wpart / wfull / zpart / gpart (step parity)
 };
+// the partial-product arrays of step parity q
+__device__ __forceinline__ Params with_parity(const Params& p, int q) {
+    Params r = p;
+    const long long o = q ? p.set2 : 0;
+    r.wpart += o; r.wfull += o; r.zpart += o; r.gpart += o;
+    return r;
+}
 
 struct Smem {
     double zs[2][ZB][NW];
@@ -143,9 +151,9 @@ __device__ __forceinline__ double block_sum(double v, double* red) {
 
 // householder::reflection_axis_mut on a contiguous vector, by one CTA.  Returns the value the reference returns
 // (-signed_norm when a reflection is needed, signed_norm otherwise); *reflected says which.
+template <int R = 16>                                            // up to R entries per thread stay in registers: one trip through memory
 __device__ double make_axis(double* x, int len, double* red, bool* reflected) {
     const int tid = threadIdx.x;
-    constexpr int R = 16;                                        // up to R entries per thread stay in registers: one trip through memory
     const bool in_regs = len <= R * T;
     double xr[R];
     double s = 0.0;
@@ -486,6 +494,270 @@ __global__ void __launch_bounds__(T, 1) two_sided_kernel(const Params p) {
 }
 
 // ------------------------------------------------------------------------------------------------------------------
+// Fused variant (the default): ONE pass per step.  The update of step s - 1 is applied to an element while it sits in a
+// register and the products with the axis of step s are accumulated from the updated value before it is stored: one
+// read + one write of the trailing block per step (16 n (n - k) / 8 (n - k)^2 bytes) instead of two reads + one write.
+// The axis of step s must exist before the pass, so the leader's work (update of the next pivot column with the products
+// of the pass that just ended, axis construction) sits between the two grid barriers of a step while the other CTAs wait
+// (~8 us), which is cheaper than a second trip through memory from n ~ 2000 on.  Partial products are double-buffered by
+// step parity: the pass of step s reads the sums of step s - 1 while it writes those of step s.
+//   pend: an update (step s - 1; axis up = column s - 1, sign sup, scalar gp) is outstanding; prod: step s reflects.
+// ------------------------------------------------------------------------------------------------------------------
+template <int MODE>
+__device__ void pass_fused(const Params& pr, const Params& pw, const Tiling& tlp, const Tiling& tl, const Task& tk, int task_id, int s,
+                           bool pend, double sup, double gp, bool prod, Smem& sm, double* sx) {
+    constexpr bool TRI = MODE == SYM;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const long long lda = pr.lda;
+    double* a = pr.a;
+    const double* up = a + (long long)(s - 1) * lda;             // axis of the outstanding update (valid when pend)
+    const double* un = a + (long long)s * lda;                   // axis of this step
+    const double m2sp = sup * -2.0;
+    int r[U]; bool ok[U]; double wr[U], ur[U], y[U], wacc[U];
+#pragma unroll
+    for (int i = 0; i < U; ++i) {
+        r[i] = tk.r0 + tid + T * i; ok[i] = r[i] < tk.r1;
+        wr[i] = 0.0; ur[i] = 0.0; wacc[i] = 0.0;
+        if (ok[i] && pend) {
+            if (MODE == SYM) wr[i] = 2.0 * (__ldcg(pr.wfull + r[i]) + sum_zpart(pr, tlp, r[i]));      // p_r of step s - 1
+            else wr[i] = __ldcg(pr.wfull + r[i]);
+            if (MODE != HESS || r[i] > s - 1) ur[i] = up[r[i]];
+        }
+        y[i] = (ok[i] && prod && (MODE != HESS || r[i] > s)) ? un[r[i]] : 0.0;
+    }
+    double gacc = 0.0;
+    int it = 0;
+    for (int jb = tk.j0; jb < tk.j1; jb += CB) {
+        const int nb = min(CB, tk.j1 - jb);
+        __syncthreads();
+        for (int c = tid; c < nb; c += T) {
+            const int j = jb + c;
+            double c1 = 0.0, c2 = 0.0;
+            if (pend) {
+                if (MODE == HESS) {
+                    c1 = m2sp * up[j];
+                    c2 = __dmul_rn(__dadd_rn(__dmul_rn(sup, sum_zpart(pr, tlp, j)), __dmul_rn(c1, gp)), m2sp);
+                } else {
+                    c1 = up[j];
+                    c2 = 2.0 * (__ldcg(pr.wfull + j) + sum_zpart(pr, tlp, j));                           // p_j
+                }
+            }
+            sm.c1[c] = c1; sm.c2[c] = c2;
+            sx[c] = prod ? un[j] : 0.0;
+        }
+        __syncthreads();
+        for (int z0 = 0; z0 < nb; z0 += ZB, ++it) {
+            const int buf = it & 1;
+            for (int jj = 0; jj < ZB && z0 + jj < nb; jj += CG) {
+                double av[CG][U];
+#pragma unroll
+                for (int q = 0; q < CG; ++q) {
+                    const int c = z0 + jj + q, j = jb + c;
+#pragma unroll
+                    for (int i = 0; i < U; ++i) av[q][i] = (ok[i] && c < nb && (!TRI || j <= r[i])) ? a[r[i] + (long long)j * lda] : 0.0;
+                }
+                double zl[CG];
+#pragma unroll
+                for (int q = 0; q < CG; ++q) {
+                    const int c = z0 + jj + q, j = jb + c;
+                    zl[q] = 0.0;
+                    if (c >= nb) continue;
+                    const double c1 = sm.c1[c], c2 = sm.c2[c], x = sx[c];
+#pragma unroll
+                    for (int i = 0; i < U; ++i) {
+                        if (!ok[i] || (TRI && j > r[i])) continue;
+                        double v = av[q][i];
+                        if (pend) {
+                            if (MODE == HESS) {
+                                v = __dadd_rn(__dmul_rn(c1, wr[i]), __dmul_rn(sup, v));
+                                if (r[i] > s - 1) v = __dadd_rn(__dmul_rn(c2, ur[i]), __dmul_rn(sup, v));
+                            } else {
+                                v = __dadd_rn(__dmul_rn(-c1, wr[i]), v);
+                                v = __dadd_rn(__dmul_rn(-c2, ur[i]), v);
+                                v = __dadd_rn(__dmul_rn(__dmul_rn(gp, c1), ur[i]), v);
+                            }
+                            a[r[i] + (long long)j * lda] = v;
+                        }
+                        wacc[i] = fma(v, x, wacc[i]);
+                        if (!TRI || r[i] > j) zl[q] = fma(v, y[i], zl[q]);
+                    }
+                }
+                if (prod) {
+                    static_assert(CG == 8, "the exchange pattern below is written for eight columns");
+                    double h4[4], h2[2], h1;
+                    const bool b16 = lane & 16, b8 = lane & 8, b4 = lane & 4;
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        const double send = b16 ? zl[q] : zl[q + 4], keep = b16 ? zl[q + 4] : zl[q];
+                        h4[q] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+                    }
+#pragma unroll
+                    for (int q = 0; q < 2; ++q) {
+                        const double send = b8 ? h4[q] : h4[q + 2], keep = b8 ? h4[q + 2] : h4[q];
+                        h2[q] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+                    }
+                    {
+                        const double send = b4 ? h2[0] : h2[1], keep = b4 ? h2[1] : h2[0];
+                        h1 = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+                    }
+                    h1 += __shfl_xor_sync(0xffffffffu, h1, 2);
+                    h1 += __shfl_xor_sync(0xffffffffu, h1, 1);
+                    if ((lane & 3) == 0) sm.zs[buf][jj + (b16 ? 4 : 0) + (b8 ? 2 : 0) + (b4 ? 1 : 0)][warp] = h1;
+                }
+            }
+            if (prod) {
+                __syncthreads();
+                if (tid < ZB && z0 + tid < nb) {
+                    double z = 0.0;
+#pragma unroll
+                    for (int w = 0; w < NW; ++w) z += sm.zs[buf][tid][w];
+                    pw.zpart[(size_t)tk.rb * pw.n + jb + z0 + tid] = z;
+                    gacc = fma(sx[z0 + tid], z, gacc);
+                }
+            }
+        }
+    }
+    if (prod) {
+#pragma unroll
+        for (int i = 0; i < U; ++i)
+            if (ok[i]) { pw.wpart[(size_t)tk.cb * pw.m + r[i]] = wacc[i]; if (MODE == SYM) gacc = fma(y[i], wacc[i], gacc); }
+        __threadfence();
+        __syncthreads();
+        if (tid == 0) {
+            const unsigned done = atomicAdd(pw.cnt + tk.rb, 1u);
+            sm.last = done + 1 == (unsigned)tk.ncb;
+            if (sm.last) pw.cnt[tk.rb] = 0;
+            __threadfence();
+        }
+        __syncthreads();
+        if (sm.last) {
+#pragma unroll
+            for (int i = 0; i < U; ++i)
+                if (ok[i]) pw.wfull[r[i]] = sum_strided(pw.wpart + r[i], (size_t)pw.m, tk.ncb);
+        }
+        const double g = block_sum(gacc, sm.red);
+        if (tid == 0) pw.gpart[task_id] = g;
+    }
+    __syncthreads();
+}
+
+template <bool SYMM>
+__global__ void __launch_bounds__(T, 1) two_sided_fused_kernel(const Params p) {
+    constexpr int MODE = SYMM ? SYM : HESS;
+    cg::grid_group grid = cg::this_grid();
+    __shared__ Smem sm;
+    __shared__ double sx[CB];
+    const int tid = threadIdx.x, cta = blockIdx.x, G = gridDim.x, Gt = G - 1;
+    const bool leader = cta == G - 1;
+    const int n = p.n;
+    const long long lda = p.lda;
+    if (leader) {
+        bool refl;
+        const double nr = make_axis<32>(p.a + 1, n - 1, sm.red, &refl);
+        if (tid == 0) { p.d[0] = nr; p.hh[0] = signum_of(nr); p.hh[1] = refl ? 1.0 : 0.0; }
+    }
+    grid.sync();
+    TS_START();
+    bool pend = false;
+    double sup = 1.0, gp = 0.0;
+    Tiling tlp;
+    tlp.init(Gt, SYMM ? 1 : 0, SYMM ? n - 1 : n, 1, n - 1, SYMM);
+    for (int s = 0; s + 1 < n; ++s) {
+        const double* hh = p.hh + 4 * (s & 1);
+        double* hn = p.hh + 4 * ((s + 1) & 1);
+        const double su = __ldcg(hh + 0);
+        const bool prod = __ldcg(hh + 1) != 0.0;
+        const int c = s + 1;                                        // the leader's column
+        Tiling tl;
+        tl.init(Gt, SYMM ? s + 1 : 0, SYMM ? n - s - 1 : n, s + 1, n - s - 1, SYMM);
+        const int ntasks = tl.ntasks();
+        const Params pr = with_parity(p, (s + 1) & 1), pw = with_parity(p, s & 1);      // sums of step s - 1 / of step s
+        TS_MARK(0);
+        if ((pend || prod) && !leader)
+            for (int t = cta; t < ntasks; t += Gt) { Task tk; if (find_task(tl, t, tk)) pass_fused<MODE>(pr, pw, tlp, tl, tk, t, s, pend, sup, gp, prod, sm, sx); }
+        TS_MARK(1);
+        grid.sync();
+        TS_MARK(2);
+        double g = 0.0;
+        if (prod) {
+            g = sum_gpart(pw, ntasks, sm);
+            if (SYMM) g = (2.0 * g) * 2.0;                           // dot = u . p = 2 u . (w + z); the reference uses dot * 2
+        }
+        if (leader) {
+            // column c carries every update up to step s - 1 (the pass just applied the last one): apply step s, then
+            // turn its rows c + 1.. into the axis of step s + 1
+            if (prod) {
+                const double* ucol = p.a + (long long)s * lda;
+                double* col = p.a + (long long)c * lda;
+                const double m2s = su * -2.0, uc = ucol[c];
+                // eight rows per thread at a time, every load of the batch issued before the first use (the leader sits
+                // between the two barriers of the step: its latency is everybody's)
+                constexpr int LB = 8;
+                if (!SYMM) {
+                    const double c1 = m2s * uc;
+                    const double c2 = __dmul_rn(__dadd_rn(__dmul_rn(su, sum_zpart(pw, tl, c)), __dmul_rn(c1, g)), m2s);
+                    for (int r0 = tid; r0 < n; r0 += LB * T) {
+                        double wv[LB], cv[LB], uv[LB];
+#pragma unroll
+                        for (int q = 0; q < LB; ++q) {
+                            const int r = r0 + q * T;
+                            wv[q] = r < n ? __ldcg(pw.wfull + r) : 0.0; cv[q] = r < n ? col[r] : 0.0; uv[q] = (r < n && r > s) ? ucol[r] : 0.0;
+                        }
+#pragma unroll
+                        for (int q = 0; q < LB; ++q) {
+                            const int r = r0 + q * T;
+                            if (r >= n) continue;
+                            double v = __dadd_rn(__dmul_rn(c1, wv[q]), __dmul_rn(su, cv[q]));
+                            if (r > s) v = __dadd_rn(__dmul_rn(c2, uv[q]), __dmul_rn(su, v));
+                            col[r] = v;
+                        }
+                    }
+                } else {
+                    const double pc = 2.0 * (__ldcg(pw.wfull + c) + sum_zpart(pw, tl, c));
+                    for (int r0 = c + tid; r0 < n; r0 += LB * T) {
+                        double wv[LB], cv[LB], uv[LB], zv[LB];
+#pragma unroll
+                        for (int q = 0; q < LB; ++q) {
+                            const int r = r0 + q * T;
+                            wv[q] = r < n ? __ldcg(pw.wfull + r) : 0.0; cv[q] = r < n ? col[r] : 0.0; uv[q] = r < n ? ucol[r] : 0.0; zv[q] = 0.0;
+                        }
+                        for (int b = 0; b < tl.nrb; ++b) {              // column products of row r: row blocks (r - col0) / RB ..
+#pragma unroll
+                            for (int q = 0; q < LB; ++q) {
+                                const int r = r0 + q * T;
+                                if (r < n && b >= (r - tl.col0) / RB) zv[q] += __ldcg(pw.zpart + (size_t)b * pw.n + r);
+                            }
+                        }
+#pragma unroll
+                        for (int q = 0; q < LB; ++q) {
+                            const int r = r0 + q * T;
+                            if (r >= n) continue;
+                            const double prr = 2.0 * (wv[q] + zv[q]);
+                            double v = cv[q];
+                            v = __dadd_rn(__dmul_rn(-uc, prr), v);
+                            v = __dadd_rn(__dmul_rn(-pc, uv[q]), v);
+                            v = __dadd_rn(__dmul_rn(__dmul_rn(g, uc), uv[q]), v);
+                            col[r] = v;
+                        }
+                    }
+                }
+                __syncthreads();
+            }
+            TS_MARK(3);
+            if (c + 1 < n) {
+                bool r2;
+                const double nr = make_axis<32>(p.a + (long long)c * lda + c + 1, n - c - 1, sm.red, &r2);
+                if (tid == 0) { p.d[c] = nr; hn[0] = signum_of(nr); hn[1] = r2 ? 1.0 : 0.0; }
+            }
+        }
+        TS_MARK(4);
+        grid.sync();
+        TS_MARK(5);
+        pend = prod; sup = su; gp = g; tlp = tl;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
 // Bidiagonal, m >= n (upper bidiagonal; the wide case runs on the transpose): column axes in column k rows k..,
 // row axes in row k columns k + 1..
 // ------------------------------------------------------------------------------------------------------------------
@@ -584,32 +856,45 @@ static int launch(const void* kernel, cudaStream_t s, size_t m, size_t n, double
     const size_t nrb = ceil_div(m, (size_t)RB);
     Scratch ws;
     const size_t ng = (size_t)G + nrb;                            // tasks: at most one per CTA plus one per row block
-    const size_t words = (size_t)NCB_MAX * m + m + nrb * n + ng + 2 * n + 8 + nrb;
+    const size_t set = (size_t)NCB_MAX * m + m + nrb * n + ng;     // wpart | wfull | zpart | gpart, two copies (step parity)
+    const size_t words = 2 * set + 2 * n + 8 + nrb;
     NAB_TRY(ws.alloc(words * sizeof(double), s));
     NAB_CUDA(cudaMemsetAsync(ws.p, 0, words * sizeof(double), s));
     double* w = ws.as<double>();
-    double* wf = w + (size_t)NCB_MAX * m; double* zp = wf + m; double* gp = zp + nrb * n; double* fv = gp + ng;
-    Params p{a, (long long)lda, (int)m, (int)n, d, e, w, wf, reinterpret_cast<unsigned*>(fv + 2 * n + 8), zp, gp, fv, fv + n, fv + 2 * n};
+    double* wf = w + (size_t)NCB_MAX * m; double* zp = wf + m; double* gp = zp + nrb * n; double* fv = w + 2 * set;
+    Params p{a, (long long)lda, (int)m, (int)n, d, e, w, wf, reinterpret_cast<unsigned*>(fv + 2 * n + 8), zp, gp, fv, fv + n, fv + 2 * n,
+             (long long)set};
     void* args[] = {(void*)&p};
     NAB_CUDA(cudaLaunchCooperativeKernel(kernel, dim3((unsigned)G), dim3(T), args, 0, s));
     count_launch();
     return NA_OK;
 }
+// One fused pass per step (two trips through memory per element instead of three, but the leader's ~15 us between the two
+// barriers of a step are exposed) pays once the trailing block is well beyond the L2: measured (profiles/r02_twosided_timing.txt)
+// Hessenberg 6144 568 / 575 ms, 8192 1154 / 1271, 12288 3463 / 4019, 16384 7839 / 9337 (fused / two-pass);
+// SymmetricTridiagonal 8192 699 / 644, 12288 1971 / 1971, 16384 4241 / 4334.  na_set_tuning("ts_fused", 0 | 1) forces
+// one of them (tests), -1 restores the size rule; NAB_TS_FUSED=0|1 does the same from the environment.
+static long g_ts_fused = [] { const char* e = getenv("NAB_TS_FUSED"); return e ? (long)(atoi(e) != 0) : -1L; }();
+static bool ts_fused(size_t n, bool symmetric) {
+    if (g_ts_fused >= 0) return g_ts_fused != 0;
+    return n >= (symmetric ? (size_t)16384 : (size_t)6144);
+}
 }  // namespace ts
+void ts_set_fused(long v) { ts::g_ts_fused = v < 0 ? -1 : (v != 0); }
 
 // subdiag: DEVICE, n - 1 signed norms (nalgebra's Hessenberg::subdiag)
 int hessenberg_device(cudaStream_t s, size_t n, double* a, size_t lda, double* subdiag) {
     if (n < 2) return NA_OK;
     if (lda < n) { set_error("hessenberg: lda < n"); return NA_EINVAL; }
     if (n > 0x7fffffull) { set_error("hessenberg: dimension exceeds 2^23"); return NA_EINVAL; }
-    return ts::launch((const void*)ts::two_sided_kernel<false>, s, n, n, a, lda, subdiag, nullptr);
+    return ts::launch(ts::ts_fused(n, false) ? (const void*)ts::two_sided_fused_kernel<false> : (const void*)ts::two_sided_kernel<false>, s, n, n, a, lda, subdiag, nullptr);
 }
 // off_diagonal: DEVICE, n - 1 signed norms; only the lower triangle of a is read / written
 int symmetric_tridiagonal_device(cudaStream_t s, size_t n, double* a, size_t lda, double* off_diagonal) {
     if (n < 2) return NA_OK;
     if (lda < n) { set_error("symmetric_tridiagonal: lda < n"); return NA_EINVAL; }
     if (n > 0x7fffffull) { set_error("symmetric_tridiagonal: dimension exceeds 2^23"); return NA_EINVAL; }
-    return ts::launch((const void*)ts::two_sided_kernel<true>, s, n, n, a, lda, off_diagonal, nullptr);
+    return ts::launch(ts::ts_fused(n, true) ? (const void*)ts::two_sided_fused_kernel<true> : (const void*)ts::two_sided_kernel<true>, s, n, n, a, lda, off_diagonal, nullptr);
 }
 // diagonal (min(m, n)) / off_diagonal (min(m, n) - 1): DEVICE.  m < n runs on the transpose (the row step of the wide
 // case is the column step of the tall one, householder.rs:92-127 against :61-85).

@@ -111,6 +111,7 @@ int qr_device(cudaStream_t s, size_t m, size_t n, double* a, size_t lda, double*
 int apply_q_blocks(cudaStream_t s, size_t m, size_t k, const double* qr, size_t lda, const double* diag,
                    double* b, size_t ldb, size_t nb, bool forward, bool triangular_q, const double* lapack_tau);
 // factor_twosided.cu: d / e DEVICE vectors of signed norms
+void ts_set_fused(long v);           // -1: size rule, 0: two-pass kernels, 1: fused one-pass kernels
 int hessenberg_device(cudaStream_t s, size_t n, double* a, size_t lda, double* subdiag);
 int symmetric_tridiagonal_device(cudaStream_t s, size_t n, double* a, size_t lda, double* off_diagonal);
 int bidiagonal_device(cudaStream_t s, size_t m, size_t n, double* a, size_t lda, double* diagonal, double* off_diagonal);

@@ -253,3 +253,33 @@ def test_wire_round_trip_of_gpu_factors(nab, oracle):
     hs = nab.Hessenberg.new(a)
     back = nab.wire.loads(nab.wire.dumps(hs), "Hessenberg")
     assert np.array_equal(back.q(), hs.q()) and np.array_equal(back.h(), hs.h())
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("n", [2, 3, 7, 64, 130, 600, 1100, 2100])
+def test_fused_and_two_pass_kernels_agree(nab, oracle, n):
+    """Hessenberg / SymmetricTridiagonal have two kernels (one fused pass per step from n = 6144 / 16384, two passes
+    below): both against the oracle at oracle sizes, and against each other."""
+    from nalgebra_b200 import _capi
+    L = _capi.lib()
+    a = oracle.uniform(n, n, 34) - 0.4
+    sy = np.asfortranarray((a + a.T) / 2.0)
+    res = {}
+    try:
+        for mode in (0, 1):
+            _capi.check(L.na_set_tuning(b"ts_fused", mode))
+            res[mode] = (nab.Hessenberg.new(a), nab.SymmetricTridiagonal.new(sy))
+    finally:
+        _capi.check(L.na_set_tuning(b"ts_fused", -1))
+    tol = _storage_tol(n)
+    assert np.abs(res[0][0].hess_internal() - res[1][0].hess_internal()).max() <= tol
+    assert np.abs(np.tril(res[0][1].internal_tri()) - np.tril(res[1][1].internal_tri())).max() <= tol
+    if n <= 1100:
+        hess_ref, sub_ref = oracle.hessenberg(a)
+        tri_ref, off_ref = oracle.symmetric_tridiagonal(sy)
+        assert np.abs(res[1][0].hess_internal() - hess_ref).max() <= tol and np.abs(res[1][0].subdiag - sub_ref).max() <= tol
+        assert np.abs(np.tril(res[1][1].internal_tri()) - np.tril(tri_ref)).max() <= tol and np.abs(res[1][1]._off - off_ref).max() <= tol
+    q, h = res[1][0].unpack()
+    assert np.linalg.norm(q @ h @ q.T - a) <= 10 * n * EPS * np.linalg.norm(a)
+    rec = res[1][1].recompose()
+    assert np.linalg.norm(np.tril(rec) - np.tril(sy)) <= 10 * n * EPS * np.linalg.norm(sy)
