@@ -53,8 +53,8 @@ __device__ __forceinline__ unsigned long long gtime() { unsigned long long t; as
 #define TS_MARK(slot) do {} while (0)
 #define TS_START() do {} while (0)
 #endif
-constexpr int T = 256;            // threads per CTA
-constexpr int U = 4;              // rows per thread
+constexpr int T = 512;            // threads per CTA (16 warps: the dependent FP64 chains of an element need the other warps to hide)
+constexpr int U = 2;              // rows per thread
 constexpr int RB = T * U;         // rows per row block
 constexpr int NCB_MAX = 64;       // column chunks per row block (= partial row products to sum)
 constexpr int CB = 256;           // columns whose per-column factors are staged in shared memory at a time
@@ -527,6 +527,47 @@ __device__ void pass_fused(const Params& pr, const Params& pw, const Tiling& tlp
     }
     double gacc = 0.0;
     int it = 0;
+    // Software pipeline over half-groups of four columns: the loads of the next half-group are issued before the current
+    // one is updated / accumulated / stored, so a thread always has 16 - 32 loads in flight (the registers are the same
+    // 8 x U doubles as one eight-column group).
+    constexpr int HG = CG / 2;
+    double bufA[HG][U], bufB[HG][U];
+    auto load_half = [&](double (&bf)[HG][U], int j0) {
+#pragma unroll
+        for (int q = 0; q < HG; ++q) {
+            const int j = j0 + q;
+#pragma unroll
+            for (int i = 0; i < U; ++i) bf[q][i] = (ok[i] && j < tk.j1 && (!TRI || j <= r[i])) ? a[r[i] + (long long)j * lda] : 0.0;
+        }
+    };
+    auto compute_half = [&](double (&bf)[HG][U], int jb, int c0, int nb, double* zl) {
+#pragma unroll
+        for (int q = 0; q < HG; ++q) {
+            const int c = c0 + q, j = jb + c;
+            zl[q] = 0.0;
+            if (c >= nb) continue;
+            const double c1 = sm.c1[c], c2 = sm.c2[c], x = sx[c];
+#pragma unroll
+            for (int i = 0; i < U; ++i) {
+                if (!ok[i] || (TRI && j > r[i])) continue;
+                double v = bf[q][i];
+                if (pend) {
+                    if (MODE == HESS) {
+                        v = __dadd_rn(__dmul_rn(c1, wr[i]), __dmul_rn(sup, v));
+                        if (r[i] > s - 1) v = __dadd_rn(__dmul_rn(c2, ur[i]), __dmul_rn(sup, v));
+                    } else {
+                        v = __dadd_rn(__dmul_rn(-c1, wr[i]), v);
+                        v = __dadd_rn(__dmul_rn(-c2, ur[i]), v);
+                        v = __dadd_rn(__dmul_rn(__dmul_rn(gp, c1), ur[i]), v);
+                    }
+                    a[r[i] + (long long)j * lda] = v;
+                }
+                wacc[i] = fma(v, x, wacc[i]);
+                if (!TRI || r[i] > j) zl[q] = fma(v, y[i], zl[q]);
+            }
+        }
+    };
+    load_half(bufA, tk.j0);
     for (int jb = tk.j0; jb < tk.j1; jb += CB) {
         const int nb = min(CB, tk.j1 - jb);
         __syncthreads();
@@ -549,39 +590,12 @@ __device__ void pass_fused(const Params& pr, const Params& pw, const Tiling& tlp
         for (int z0 = 0; z0 < nb; z0 += ZB, ++it) {
             const int buf = it & 1;
             for (int jj = 0; jj < ZB && z0 + jj < nb; jj += CG) {
-                double av[CG][U];
-#pragma unroll
-                for (int q = 0; q < CG; ++q) {
-                    const int c = z0 + jj + q, j = jb + c;
-#pragma unroll
-                    for (int i = 0; i < U; ++i) av[q][i] = (ok[i] && c < nb && (!TRI || j <= r[i])) ? a[r[i] + (long long)j * lda] : 0.0;
-                }
+                const int c0 = z0 + jj;
                 double zl[CG];
-#pragma unroll
-                for (int q = 0; q < CG; ++q) {
-                    const int c = z0 + jj + q, j = jb + c;
-                    zl[q] = 0.0;
-                    if (c >= nb) continue;
-                    const double c1 = sm.c1[c], c2 = sm.c2[c], x = sx[c];
-#pragma unroll
-                    for (int i = 0; i < U; ++i) {
-                        if (!ok[i] || (TRI && j > r[i])) continue;
-                        double v = av[q][i];
-                        if (pend) {
-                            if (MODE == HESS) {
-                                v = __dadd_rn(__dmul_rn(c1, wr[i]), __dmul_rn(sup, v));
-                                if (r[i] > s - 1) v = __dadd_rn(__dmul_rn(c2, ur[i]), __dmul_rn(sup, v));
-                            } else {
-                                v = __dadd_rn(__dmul_rn(-c1, wr[i]), v);
-                                v = __dadd_rn(__dmul_rn(-c2, ur[i]), v);
-                                v = __dadd_rn(__dmul_rn(__dmul_rn(gp, c1), ur[i]), v);
-                            }
-                            a[r[i] + (long long)j * lda] = v;
-                        }
-                        wacc[i] = fma(v, x, wacc[i]);
-                        if (!TRI || r[i] > j) zl[q] = fma(v, y[i], zl[q]);
-                    }
-                }
+                load_half(bufB, jb + c0 + HG);
+                compute_half(bufA, jb, c0, nb, zl);
+                load_half(bufA, jb + c0 + CG);                       // the next group (possibly of the next batch: only addresses matter)
+                compute_half(bufB, jb, c0 + HG, nb, zl + HG);
                 if (prod) {
                     static_assert(CG == 8, "the exchange pattern below is written for eight columns");
                     double h4[4], h2[2], h1;
@@ -653,7 +667,7 @@ __global__ void __launch_bounds__(T, 1) two_sided_fused_kernel(const Params p) {
     const long long lda = p.lda;
     if (leader) {
         bool refl;
-        const double nr = make_axis<32>(p.a + 1, n - 1, sm.red, &refl);
+        const double nr = make_axis<16>(p.a + 1, n - 1, sm.red, &refl);
         if (tid == 0) { p.d[0] = nr; p.hh[0] = signum_of(nr); p.hh[1] = refl ? 1.0 : 0.0; }
     }
     grid.sync();
@@ -746,7 +760,7 @@ __global__ void __launch_bounds__(T, 1) two_sided_fused_kernel(const Params p) {
             TS_MARK(3);
             if (c + 1 < n) {
                 bool r2;
-                const double nr = make_axis<32>(p.a + (long long)c * lda + c + 1, n - c - 1, sm.red, &r2);
+                const double nr = make_axis<16>(p.a + (long long)c * lda + c + 1, n - c - 1, sm.red, &r2);
                 if (tid == 0) { p.d[c] = nr; hn[0] = signum_of(nr); hn[1] = r2 ? 1.0 : 0.0; }
             }
         }
@@ -770,7 +784,7 @@ __global__ void __launch_bounds__(T, 1) bidiagonal_kernel(const Params p) {
     const long long lda = p.lda;
     if (leader) {
         bool refl;
-        const double nr = make_axis(p.a, m, sm.red, &refl);
+        const double nr = make_axis<8>(p.a, m, sm.red, &refl);
         if (tid == 0) { p.d[0] = nr; p.hh[0] = signum_of(nr); p.hh[1] = refl ? 1.0 : 0.0; }
     }
     grid.sync();
@@ -804,7 +818,7 @@ __global__ void __launch_bounds__(T, 1) bidiagonal_kernel(const Params p) {
             }
             __syncthreads();
             bool rv;
-            const double nr = make_axis(p.vvec + c, n - c, sm.red, &rv);
+            const double nr = make_axis<8>(p.vvec + c, n - c, sm.red, &rv);
             __syncthreads();
             for (int j = c + tid; j < n; j += T) p.a[k + (long long)j * lda] = p.vvec[j];
             if (tid == 0) { p.e[k] = nr; hh[2] = signum_of(nr); hh[3] = rv ? 1.0 : 0.0; }
@@ -838,7 +852,7 @@ __global__ void __launch_bounds__(T, 1) bidiagonal_kernel(const Params p) {
         }
         if (leader) {
             bool r2;
-            const double nr = make_axis(p.a + (long long)c * lda + c, m - c, sm.red, &r2);
+            const double nr = make_axis<8>(p.a + (long long)c * lda + c, m - c, sm.red, &r2);
             if (tid == 0) { p.d[c] = nr; hn[0] = signum_of(nr); hn[1] = r2 ? 1.0 : 0.0; }
         }
         grid.sync();
