@@ -388,18 +388,20 @@ __device__ void pass_update(const Params& p, const Tiling& tl, const Task& tk, i
                 for (int i = 0; i < U; ++i)
                     av[q][i] = (ok[i] && c0 + q < nb && j != skip_col && (MODE != SYM || j <= r[i])) ? p.a[r[i] + (long long)j * lda] : 0.0;
             }
+            // branch-free per element (masked entries were loaded as zeros and are kept out by the predicated store)
 #pragma unroll
             for (int q = 0; q < CG; ++q) {
                 const int j = jb + c0 + q;
-                if (c0 + q >= nb || j == skip_col) continue;
+                const bool cin = c0 + q < nb && j != skip_col;
                 const double c1 = sm.c1[c0 + q], c2 = sm.c2[c0 + q];
 #pragma unroll
                 for (int i = 0; i < U; ++i) {
-                    if (!ok[i] || (MODE == SYM && j > r[i])) continue;
+                    const bool act = ok[i] && cin && (MODE != SYM || j <= r[i]);
                     double v = av[q][i];
                     if (MODE == HESS) {
-                        v = __dadd_rn(__dmul_rn(c1, wr[i]), __dmul_rn(su, v));
-                        if (r[i] > k) v = __dadd_rn(__dmul_rn(c2, ur[i]), __dmul_rn(su, v));
+                        const double v1 = __dadd_rn(__dmul_rn(c1, wr[i]), __dmul_rn(su, v));
+                        const double v2 = __dadd_rn(__dmul_rn(c2, ur[i]), __dmul_rn(su, v1));
+                        v = r[i] > k ? v2 : v1;
                     } else if (MODE == SYM) {
                         v = __dadd_rn(__dmul_rn(-c1, wr[i]), v);
                         v = __dadd_rn(__dmul_rn(-c2, ur[i]), v);
@@ -408,7 +410,7 @@ __device__ void pass_update(const Params& p, const Tiling& tl, const Task& tk, i
                         if (refl_u) v = __dadd_rn(__dmul_rn(c1, ur[i]), __dmul_rn(su, v));
                         if (refl_v) v = __dadd_rn(__dmul_rn(c2, wr[i]), __dmul_rn(sv, v));
                     }
-                    p.a[r[i] + (long long)j * lda] = v;
+                    if (act) p.a[r[i] + (long long)j * lda] = v;
                 }
             }
         }
@@ -540,31 +542,41 @@ __device__ void pass_fused(const Params& pr, const Params& pw, const Tiling& tlp
             for (int i = 0; i < U; ++i) bf[q][i] = (ok[i] && j < tk.j1 && (!TRI || j <= r[i])) ? a[r[i] + (long long)j * lda] : 0.0;
         }
     };
+    // Branch-free: masked elements (rows beyond the block, columns beyond the chunk, the strict upper triangle of the
+    // symmetric case) were loaded as zeros, go through the same arithmetic and are kept out by one predicated store and two
+    // selects -- per-element `continue`s cost a divergence barrier pair each.
+    bool left[U];
+#pragma unroll
+    for (int i = 0; i < U; ++i) left[i] = r[i] > s - 1;
     auto compute_half = [&](double (&bf)[HG][U], int jb, int c0, int nb, double* zl) {
 #pragma unroll
         for (int q = 0; q < HG; ++q) {
             const int c = c0 + q, j = jb + c;
-            zl[q] = 0.0;
-            if (c >= nb) continue;
-            const double c1 = sm.c1[c], c2 = sm.c2[c], x = sx[c];
+            const bool cin = c < nb;
+            const double c1 = sm.c1[c], c2 = sm.c2[c], x = sx[c];      // c < CB always: stale entries beyond nb are never used
+            double zq = 0.0;
 #pragma unroll
             for (int i = 0; i < U; ++i) {
-                if (!ok[i] || (TRI && j > r[i])) continue;
+                const bool act = ok[i] && cin && (!TRI || j <= r[i]);
                 double v = bf[q][i];
                 if (pend) {
                     if (MODE == HESS) {
-                        v = __dadd_rn(__dmul_rn(c1, wr[i]), __dmul_rn(sup, v));
-                        if (r[i] > s - 1) v = __dadd_rn(__dmul_rn(c2, ur[i]), __dmul_rn(sup, v));
+                        const double v1 = __dadd_rn(__dmul_rn(c1, wr[i]), __dmul_rn(sup, v));
+                        const double v2 = __dadd_rn(__dmul_rn(c2, ur[i]), __dmul_rn(sup, v1));
+                        v = left[i] ? v2 : v1;
                     } else {
                         v = __dadd_rn(__dmul_rn(-c1, wr[i]), v);
                         v = __dadd_rn(__dmul_rn(-c2, ur[i]), v);
                         v = __dadd_rn(__dmul_rn(__dmul_rn(gp, c1), ur[i]), v);
                     }
-                    a[r[i] + (long long)j * lda] = v;
+                    if (act) a[r[i] + (long long)j * lda] = v;
                 }
-                wacc[i] = fma(v, x, wacc[i]);
-                if (!TRI || r[i] > j) zl[q] = fma(v, y[i], zl[q]);
+                const double ve = act ? v : 0.0;
+                wacc[i] = fma(ve, x, wacc[i]);
+                const double yz = (!TRI || r[i] > j) ? y[i] : 0.0;
+                zq = fma(ve, yz, zq);
             }
+            zl[q] = zq;
         }
     };
     load_half(bufA, tk.j0);
