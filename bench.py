@@ -711,6 +711,25 @@ def factorization_extras(L, _capi, torch, dev, stream, N, cpu=True, e2e=True):
                                  "kernel": what, "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_bytes, "note": note}}
         if key.rsplit("_", 1)[0] in base:
             out[key]["cpu_baseline"] = base[key.rsplit("_", 1)[0]]
+    if e2e:
+        # the same three through the host-pointer entry points (pinned host matrix; upload, reduce, download: the first step
+        # touches every element and every step rewrites the trailing block, so nothing can stream)
+        try:
+            hA = torch.empty(n8 * n8, dtype=torch.float64).pin_memory(); hA0 = A0.cpu()
+            hd = torch.empty(n8, dtype=torch.float64); he = torch.empty(n8, dtype=torch.float64)
+            for key, call, api in (
+                    ("hessenberg_n8192", lambda: L.na_hessenberg_f64(n8, hA.data_ptr(), n8, hd.data_ptr()), "na_hessenberg_f64"),
+                    ("symmetric_tridiagonal_n8192", lambda: L.na_symmetric_tridiagonal_f64(n8, hA.data_ptr(), n8, hd.data_ptr()), "na_symmetric_tridiagonal_f64"),
+                    ("bidiagonal_n8192", lambda: L.na_bidiagonal_f64(n8, n8, hA.data_ptr(), n8, hd.data_ptr(), he.data_ptr()), "na_bidiagonal_f64")):
+                hA.copy_(hA0)
+                t0 = time.perf_counter()
+                _capi.check(call())
+                msh = (time.perf_counter() - t0) * 1e3
+                out[key]["e2e"] = {"ms": msh, "h2d_bytes": n8 * n8 * 8, "d2h_bytes": n8 * n8 * 8 + 2 * n8 * 8,
+                                   "api": api + " (host pointer, pinned)"}
+            del hA, hA0
+        except Exception as ex:
+            out["hessenberg_n8192"]["e2e"] = {"error": repr(ex)}
     try:   # DRAM bytes of the Hessenberg launch from the committed ncu capture, valid for the kernel source it was taken with
         import hashlib
         with open(os.path.join(ROOT, "profiles", "twosided_traffic.json")) as f:
