@@ -8,23 +8,38 @@ import pytest
 
 
 class _OracleBackedLib:
-    """Same argument lists as include/nalgebra_b200.h for the five calls the mirrors make."""
+    """Same argument lists as include/nalgebra_b200.h for the calls the mirrors make."""
+    _VOID = {"na_hessenberg_f64": "na_oracle_hessenberg_f64", "na_symmetric_tridiagonal_f64": "na_oracle_symmetric_tridiagonal_f64",
+             "na_bidiagonal_f64": "na_oracle_bidiagonal_f64", "na_qr_q_f64": "na_oracle_qr_q_f64", "na_dgemm": "na_oracle_gemm_f64",
+             "na_lu_f64": "na_oracle_lu_f64", "na_qr_f64": "na_oracle_qr_f64", "na_qr_q_tr_mul_f64": "na_oracle_qr_q_tr_mul_f64",
+             "na_full_piv_lu_f64": "na_oracle_full_piv_lu_f64", "na_col_piv_qr_f64": "na_oracle_col_piv_qr_f64",
+             "na_cholesky_solve_f64": "na_oracle_cholesky_solve_f64"}
+    _BOOL = {"na_lu_solve_f64": "na_oracle_lu_solve_f64", "na_qr_solve_f64": "na_oracle_qr_solve_f64"}   # oracle: 1 = solved, 0 = singular
 
     def __init__(self, O):
         self._o = O.lib()
 
-    def _void(self, fn):
-        def call(*args):
-            fn(*args)
-            return 0
-        return call
+    def na_cholesky_f64(self, *args):                      # 0 / 1 on both sides (NA_OK / NA_NOT_PD)
+        return self._o.na_oracle_cholesky_f64(*args)
+
+    def na_tri_solve_f64(self, lower, trans, unit, n, t, ldt, b, ldb, nrhs):
+        import ctypes as C
+        import scipy.linalg
+        tm = np.ctypeslib.as_array((C.c_double * (ldt * n)).from_address(t)).reshape((ldt, n), order="F")[:n]
+        bm = np.ctypeslib.as_array((C.c_double * (ldb * nrhs)).from_address(b)).reshape((ldb, nrhs), order="F")
+        if not unit and np.any(np.diagonal(tm) == 0.0):
+            return 2                                       # NA_SINGULAR
+        bm[:n] = scipy.linalg.solve_triangular(tm, bm[:n], lower=bool(lower), trans=int(trans), unit_diagonal=bool(unit))
+        return 0
 
     def __getattr__(self, name):
-        table = {"na_hessenberg_f64": "na_oracle_hessenberg_f64", "na_symmetric_tridiagonal_f64": "na_oracle_symmetric_tridiagonal_f64",
-                 "na_bidiagonal_f64": "na_oracle_bidiagonal_f64", "na_qr_q_f64": "na_oracle_qr_q_f64", "na_dgemm": "na_oracle_gemm_f64"}
-        if name not in table:
-            raise AttributeError(name)
-        return self._void(getattr(self._o, table[name]))
+        if name in self._VOID:
+            fn = getattr(self._o, self._VOID[name])
+            return lambda *a: (fn(*a), 0)[1]
+        if name in self._BOOL:
+            fn = getattr(self._o, self._BOOL[name])
+            return lambda *a: 0 if fn(*a) else 2
+        raise AttributeError(name)
 
 
 @pytest.fixture()
@@ -69,3 +84,51 @@ def test_bidiagonal_mirror(nab_on_oracle, oracle, shape):
     assert np.array_equal(b.d(), oracle.bidiagonal_d(d, e, upper))
     u, dm, vt = b.unpack()
     assert np.abs(u @ dm @ vt - a).max() <= 1e-12
+
+
+def test_factorization_mirrors_host_logic(nab_on_oracle, oracle):
+    """Accessors, determinants, solve / inverse wrappers and the order in which the permutation sequences are applied
+    (cholesky.rs:82-185, lu.rs:132-331, qr.rs:81-294, full_piv_lu.rs:94-270, col_piv_qr.rs:97-337)."""
+    nab = nab_on_oracle
+    n = 12
+    a = oracle.uniform(n, n, 43) - 0.5
+    b = oracle.uniform(n, 3, 44)
+    det = np.linalg.det(a)
+    x_ref = np.linalg.solve(a, b)
+    for f in (nab.LU.new(a), nab.FullPivLU.new(a), nab.QR.new(a), nab.ColPivQR.new(a)):
+        x = f.solve(b)
+        assert x is not None and np.abs(x - x_ref).max() <= 1e-10, type(f).__name__
+        assert np.abs(f.try_inverse() @ a - np.eye(n)).max() <= 1e-10
+        assert f.is_invertible()
+        if isinstance(f, nab.ColPivQR):
+            # col_piv_qr.rs:324-337 multiplies the SIGNED diag entries and p.determinant(): the magnitude is the determinant's,
+            # the sign follows the reference's formula (it ignores the reflections' own determinants), and so does the mirror
+            assert abs(abs(f.determinant()) / abs(det) - 1.0) <= 1e-10
+            assert f.determinant() == np.prod(f.diag) * f.p().determinant()
+        elif not isinstance(f, nab.QR):
+            assert abs(f.determinant() / det - 1.0) <= 1e-10, type(f).__name__
+        xv = f.solve(b[:, 0])                                                    # a DVector right-hand side
+        assert xv.shape == (n,) and np.abs(xv - x_ref[:, 0]).max() <= 1e-10
+    lu = nab.LU.new(a)
+    pm, l, u = lu.unpack()
+    rec = l @ u
+    pm.inv_permute_rows(rec)
+    assert np.abs(rec - a).max() <= 1e-13
+    fp = nab.FullPivLU.new(a)
+    p, l, u, q = fp.unpack()
+    rec = l @ u
+    p.inv_permute_rows(rec); q.inv_permute_columns(rec)
+    assert np.abs(rec - a).max() <= 1e-13
+    cp = nab.ColPivQR.new(a)
+    qm, r, pc = cp.unpack()
+    rec = qm @ r
+    pc.inv_permute_columns(rec)
+    assert np.abs(rec - a).max() <= 1e-13
+    spd = oracle.spd_wellcond(n, 45)
+    ch = nab.Cholesky.new(spd)
+    assert np.abs(ch.l() @ ch.l().T - spd).max() <= 1e-12 and np.abs(ch.solve(b) - np.linalg.solve(spd, b)).max() <= 1e-12
+    assert abs(ch.determinant() / np.linalg.det(spd) - 1.0) <= 1e-10 and abs(ch.ln_determinant() - np.log(np.linalg.det(spd))) <= 1e-9
+    assert np.abs(ch.inverse() @ spd - np.eye(n)).max() <= 1e-12
+    assert nab.Cholesky.new(-spd) is None
+    sing = a.copy(); sing[:, 3] = 0.0                                          # exactly singular: only an exact zero pivot makes the reference return None
+    assert nab.LU.new(sing).solve(b) is None and not nab.FullPivLU.new(sing).is_invertible() and nab.FullPivLU.new(sing).determinant() == 0.0
