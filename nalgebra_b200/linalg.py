@@ -693,6 +693,12 @@ class Hessenberg:
         check(_capi.lib().na_hessenberg_f64(n, m.ctypes.data, n, sub.ctypes.data))
         return cls(m, sub[: n - 1].copy())
 
+    @classmethod
+    def new_with_workspace(cls, hess, work) -> "Hessenberg":           # :61-100: `work` (n entries) is the reference's scratch vector
+        if np.asarray(work).shape[0] != np.asarray(hess).shape[0]:
+            raise ValueError("Hessenberg: invalid workspace size.")
+        return cls.new(hess)
+
     def hess_internal(self) -> np.ndarray:                            # :152
         return self.hess
 
@@ -884,3 +890,104 @@ def solve_lower_triangular_with_diag(t, b, diag: float):
         return _tri_solve(t, b, True, False, True)
     tm = _as_matrix(t)
     return _tri_solve(np.tril(tm, -1) / float(diag), b, True, False, True)
+
+
+# ---------------------------------------------------------------------------------------------
+# Matrix-level entry points  (src/linalg/decomposition.rs: `m.lu()`, `m.qr()`, ... consume the matrix and
+# return the factor object; determinant / try_inverse: src/linalg/determinant.rs:57, inverse.rs:137)
+# ---------------------------------------------------------------------------------------------
+def cholesky(m):                        # decomposition.rs:257
+    return Cholesky.new(m)
+
+
+def lu(m):                              # :48
+    return LU.new(m)
+
+
+def qr(m):                              # :57
+    return QR.new(m)
+
+
+def full_piv_lu(m):                     # :39
+    return FullPivLU.new(m)
+
+
+def col_piv_qr(m):                      # :66
+    return ColPivQR.new(m)
+
+
+def hessenberg(m):                      # :289
+    return Hessenberg.new(m)
+
+
+def symmetric_tridiagonalize(m):        # :370
+    return SymmetricTridiagonal.new(m)
+
+
+def bidiagonalize(m):                   # :23
+    return Bidiagonal.new(m)
+
+
+def determinant(m) -> float:
+    """``Matrix::determinant`` (determinant.rs:20-58): the reference's closed forms up to dimension 3 (scalar host arithmetic,
+    same operation order), ``LU::new(..).determinant()`` beyond."""
+    a = _as_matrix(m)
+    if a.shape[0] != a.shape[1]:
+        raise ValueError("Unable to compute the determinant of a non-square matrix.")
+    dim = a.shape[0]
+    if dim == 0:
+        return 1.0
+    if dim == 1:
+        return float(a[0, 0])
+    if dim == 2:
+        return float(a[0, 0] * a[1, 1] - a[1, 0] * a[0, 1])
+    if dim == 3:
+        (m11, m12, m13), (m21, m22, m23), (m31, m32, m33) = (tuple(float(v) for v in row) for row in a)
+        minor_m12_m23 = m22 * m33 - m32 * m23
+        minor_m11_m23 = m21 * m33 - m31 * m23
+        minor_m11_m22 = m21 * m32 - m31 * m22
+        return m11 * minor_m12_m23 - m12 * minor_m11_m23 + m13 * minor_m11_m22
+    return LU.new(a).determinant()
+
+
+def try_inverse(m):
+    """``Matrix::try_inverse`` (inverse.rs:16-150): closed forms up to dimension 4 on the host (dimensions 1-3 in the
+    reference's operation order; 4 by cofactors, the reference unrolls the same expansion), ``lu::try_invert_to`` beyond.
+    ``None`` when the determinant (or a pivot of U) is exactly zero."""
+    a = _as_matrix(m)
+    if a.shape[0] != a.shape[1]:
+        raise ValueError("Unable to invert a non-square matrix.")
+    dim = a.shape[0]
+    if dim == 0:
+        return np.zeros((0, 0), order="F")
+    if dim == 1:
+        return None if a[0, 0] == 0.0 else np.asfortranarray([[1.0 / float(a[0, 0])]])
+    if dim == 2:
+        m11, m12, m21, m22 = float(a[0, 0]), float(a[0, 1]), float(a[1, 0]), float(a[1, 1])
+        det = m11 * m22 - m21 * m12
+        if det == 0.0:
+            return None
+        return np.asfortranarray([[m22 / det, -m12 / det], [-m21 / det, m11 / det]])
+    if dim == 3:
+        (m11, m12, m13), (m21, m22, m23), (m31, m32, m33) = (tuple(float(v) for v in row) for row in a)
+        minor_m12_m23 = m22 * m33 - m32 * m23
+        minor_m11_m23 = m21 * m33 - m31 * m23
+        minor_m11_m22 = m21 * m32 - m31 * m22
+        det = m11 * minor_m12_m23 - m12 * minor_m11_m23 + m13 * minor_m11_m22
+        if det == 0.0:
+            return None
+        return np.asfortranarray([
+            [minor_m12_m23 / det, (m13 * m32 - m33 * m12) / det, (m12 * m23 - m22 * m13) / det],
+            [-minor_m11_m23 / det, (m11 * m33 - m31 * m13) / det, (m13 * m21 - m23 * m11) / det],
+            [minor_m11_m22 / det, (m12 * m31 - m32 * m11) / det, (m11 * m22 - m21 * m12) / det]])
+    if dim == 4:
+        cof = np.empty((4, 4))
+        for i in range(4):
+            for j in range(4):
+                minor = np.delete(np.delete(a, i, axis=0), j, axis=1)
+                cof[i, j] = (-1.0) ** (i + j) * determinant(minor)
+        det = float(np.dot(a[0, :], cof[0, :]))
+        if det == 0.0:
+            return None
+        return np.asfortranarray(cof.T / det)
+    return LU.new(a).try_inverse()

@@ -132,3 +132,28 @@ def test_factorization_mirrors_host_logic(nab_on_oracle, oracle):
     assert nab.Cholesky.new(-spd) is None
     sing = a.copy(); sing[:, 3] = 0.0                                          # exactly singular: only an exact zero pivot makes the reference return None
     assert nab.LU.new(sing).solve(b) is None and not nab.FullPivLU.new(sing).is_invertible() and nab.FullPivLU.new(sing).determinant() == 0.0
+
+
+def test_matrix_level_entry_points(nab_on_oracle, oracle):
+    """decomposition.rs / determinant.rs:20-58 / inverse.rs:16-150: closed forms up to dimension 3 (4 for the inverse), LU
+    beyond; the 5 x 5 table of tests/linalg/inverse.rs:62-81 (relative 1e-4 there)."""
+    nab = nab_on_oracle
+    for n in range(0, 9):
+        a = oracle.uniform(n, n, 46 + n) - 0.5
+        assert abs(nab.determinant(a) - (np.linalg.det(a) if n else 1.0)) <= 1e-12
+        inv = nab.try_inverse(a)
+        assert inv is not None and inv.shape == (n, n) and (n == 0 or np.abs(inv @ a - np.eye(n)).max() <= 1e-9)
+    for n in (1, 2, 3, 4, 6):
+        z = np.zeros((n, n)); z[:, : n - 1] = oracle.uniform(n, n - 1, 3) if n > 1 else z[:, :0]
+        assert nab.try_inverse(z) is None and nab.determinant(z) == 0.0
+    with pytest.raises(ValueError):
+        nab.determinant(np.zeros((2, 3)))
+    a = oracle.uniform(7, 7, 60) - 0.5
+    assert isinstance(nab.lu(a), nab.LU) and isinstance(nab.qr(a), nab.QR) and isinstance(nab.hessenberg(a), nab.Hessenberg)
+    assert isinstance(nab.bidiagonalize(a), nab.Bidiagonal) and isinstance(nab.full_piv_lu(a), nab.FullPivLU)
+    assert isinstance(nab.col_piv_qr(a), nab.ColPivQR) and isinstance(nab.symmetric_tridiagonalize(a + a.T), nab.SymmetricTridiagonal)
+    assert nab.cholesky(a @ a.T + 7 * np.eye(7)) is not None and nab.cholesky(-np.eye(7)) is None
+    h = nab.Hessenberg.new_with_workspace(a, np.zeros(7))
+    assert np.array_equal(h.hess_internal(), nab.hessenberg(a).hess_internal())
+    with pytest.raises(ValueError):
+        nab.Hessenberg.new_with_workspace(a, np.zeros(6))
